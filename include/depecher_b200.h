@@ -1,0 +1,156 @@
+/*
+ * depecher_b200.h — C ABI of the B200-native penalized k-means engine.
+ *
+ * This is the drop-in boundary for DepecheR's hot path: the four entry points below replace,
+ * one for one, the bodies of the four Rcpp exports of the reference
+ *     sparse_k_means   src/InterfaceUtils.cpp:66-94
+ *     grid_search      src/InterfaceUtils.cpp:99-131
+ *     allocate_points  src/InterfaceUtils.cpp:134-148
+ *     rand_index       src/InterfaceUtils.cpp:151-161
+ * which are what `.Call('_DepecheR_*')` (R/RcppExports.R:4-18, src/RcppExports.cpp:14-83)
+ * reaches.  Plain pointers and sizes only; matrices are COLUMN-MAJOR doubles exactly as R
+ * hands them over (no transpose at the boundary, unlike numeric_to_eigen,
+ * src/InterfaceUtils.cpp:23-33); labels are 0-based int32 like the reference returns them.
+ *
+ * All functions return DPR_OK (0) or a negative error code; dpr_last_error() gives the text
+ * (thread-local).  There is NO CPU fallback: without a usable sm_100 device every compute
+ * entry point fails with DPR_ERR_NO_DEVICE.
+ *
+ * Randomness: the reference seeds libc rand() from time(0) (src/Clusterer.h:51-53).  Here
+ * every entry point that draws takes an explicit 64-bit seed; the stream layout is fixed in
+ * include/dpr_philox.h so results are reproducible and checkable against the oracle.
+ */
+#ifndef DEPECHER_B200_H
+#define DEPECHER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPR_OK 0
+#define DPR_ERR_INVALID (-1)   /* bad argument (k < 2, n < 1, null pointer, label out of range ...) */
+#define DPR_ERR_NO_DEVICE (-2) /* no sm_100 CUDA device / driver */
+#define DPR_ERR_CUDA (-3)      /* CUDA runtime error; text in dpr_last_error() */
+#define DPR_ERR_NCCL (-4)      /* NCCL error or NCCL not loadable */
+#define DPR_ERR_STATE (-5)     /* call order / handle misuse */
+
+/* rand_index estimator: the contingency-table value is the expectation of the reference's
+ * 10 000-pair Monte-Carlo estimate (src/Clusterer.cpp:286-304). */
+#define DPR_ARI_EXACT 0
+#define DPR_ARI_MONTE_CARLO 1
+
+typedef struct dpr_dataset* dpr_dataset_t;
+
+/* ---- housekeeping ------------------------------------------------------------------- */
+const char* dpr_last_error(void);
+int dpr_version(void);                   /* 10000*major + 100*minor + patch */
+int dpr_device_count(int32_t* out);
+int dpr_set_device(int32_t ordinal);     /* default: device 0 (or LOCAL_RANK via the host layer) */
+int dpr_set_stream(void* cuda_stream);   /* run everything on the caller's cudaStream_t (NULL = library stream) */
+int dpr_synchronize(void);
+int dpr_set_ari_mode(int32_t mode);      /* DPR_ARI_EXACT (default) | DPR_ARI_MONTE_CARLO */
+/* counters for bench/test evidence: kernels launched by this library since the last reset */
+int dpr_kernel_launches(int64_t* out, int32_t reset);
+
+/* ---- the four drop-in entry points (host buffers in, host buffers out) ------------------ */
+
+/* allocate_points(X, mu, no_zero) -> i       src/InterfaceUtils.cpp:134-148 -> Clusterer::allocate_clusters
+ * (src/Clusterer.cpp:34-87).  X: n x d col-major, mu: k x d col-major, idx_out: n labels (row of mu). */
+int dpr_allocate_points(const double* X, int64_t n, int32_t d, const double* mu, int32_t k,
+                        int32_t no_zero, int32_t* idx_out);
+
+/* sparse_k_means(X, k, reg, no_zero, seed_off_set) -> {i,c,n}   src/InterfaceUtils.cpp:66-94 ->
+ * Clusterer::find_centers (src/Clusterer.cpp:213-265).  centers_out: k x d col-major; norm_out: the
+ * penalised SSQ of cluster_norm (:198-211); n_iter_out (nullable): assignments performed. */
+int dpr_sparse_k_means(const double* X, int64_t n, int32_t d, uint32_t k, double reg, int32_t no_zero,
+                       uint64_t seed, int32_t* idx_out, double* centers_out, double* norm_out,
+                       int32_t* n_iter_out);
+
+/* grid_search(X, k, reg, iterations, bootstrapSamples, seed_off_set) -> {d,n,c}
+ * src/InterfaceUtils.cpp:99-131 -> Clusterer::optimize_param (src/Clusterer.cpp:334-394).
+ * ari_out, nclust_out: nk x nreg col-major (the reference's d/z and n/m, which are copies of each other,
+ * :387-390).  centers_out (nullable): for every problem (it, j, l) in the reference's loop order
+ * (:349-352) the two fitted centre matrices ret1, ret2, each k[j] x d col-major, packed back to back
+ * (entries [3],[4] of the reference's list are duplicates of [1],[2], :363-368). */
+int dpr_grid_search(const double* X, int64_t n, int32_t d, const int32_t* k, int32_t nk,
+                    const double* reg, int32_t nreg, uint32_t iterations, uint32_t boot_n,
+                    uint64_t seed, double* ari_out, double* nclust_out, double* centers_out);
+
+/* rand_index(inds1, inds2, k) -> double      src/InterfaceUtils.cpp:151-161 -> Clusterer::cluster_distance
+ * (src/Clusterer.cpp:267-305).  Labels must lie in [0, k] (R passes 1-based labels with k = max, SURVEY A-9). */
+int dpr_rand_index(const int32_t* a, const int32_t* b, int64_t n, uint32_t k, double* out);
+
+/* ---- resident dataset: X stays in HBM (fp32, column-major) across calls ---------------------- */
+/* The reference re-marshals X on every call (src/InterfaceUtils.cpp:70,102,137); depeche() makes
+ * dozens of grid_search calls on the same matrix (R/depechePenaltyOpt.R:47-55). */
+int dpr_dataset_create(const double* X, int64_t n, int32_t d, dpr_dataset_t* out);
+int dpr_dataset_create_f32(const float* X, int64_t n, int32_t d, dpr_dataset_t* out);
+/* synthetic generator on device (bench only): G blobs, centre coords in {-a,0,a}, unit noise, / sd. */
+int dpr_dataset_create_synthetic(int64_t n, int32_t d, int32_t groups, double amplitude, uint64_t seed,
+                                 dpr_dataset_t* out);
+int dpr_dataset_destroy(dpr_dataset_t ds);
+int dpr_dataset_shape(dpr_dataset_t ds, int64_t* n, int32_t* d);
+/* copy rows [row0, row0+rows) back as column-major doubles (tests / CPU baseline sample) */
+int dpr_dataset_read(dpr_dataset_t ds, int64_t row0, int64_t rows, double* out);
+
+int dpr_dataset_allocate_points(dpr_dataset_t ds, const double* mu, int32_t k, int32_t no_zero,
+                                int32_t* idx_out /* host, nullable */);
+int dpr_dataset_sparse_k_means(dpr_dataset_t ds, uint32_t k, double reg, int32_t no_zero, uint64_t seed,
+                               int32_t* idx_out /* nullable */, double* centers_out, double* norm_out,
+                               int32_t* n_iter_out);
+int dpr_dataset_grid_search(dpr_dataset_t ds, const int32_t* k, int32_t nk, const double* reg, int32_t nreg,
+                            uint32_t iterations, uint32_t boot_n, uint64_t seed, double* ari_out,
+                            double* nclust_out, double* centers_out);
+
+/* ---- stage-level entry points (parity hooks; each is one deterministic stage of the reference) ----- */
+
+/* Lloyd loop from injected initial centres: find_centers (src/Clusterer.cpp:244-252) without
+ * initialize_mu.  init_mu/centers_out k x d col-major. */
+int dpr_dataset_find_centers_from(dpr_dataset_t ds, const double* init_mu, uint32_t k, double reg,
+                                  int32_t no_zero, int32_t max_iter, int32_t* idx_out, double* centers_out,
+                                  double* norm_out, int32_t* n_iter_out);
+/* one centre update for given labels: reevaluate_centers (src/Clusterer.cpp:89-108). */
+int dpr_dataset_reevaluate_centers(dpr_dataset_t ds, const int32_t* idx, uint32_t k, double reg,
+                                   double* centers_out, int64_t* counts_out /* nullable */);
+/* k-means++ seeding: initialize_mu + element_from_vector (src/Clusterer.cpp:123-176); stream = fit id.
+ * rows_out (nullable): the k chosen row numbers. */
+int dpr_dataset_initialize_mu(dpr_dataset_t ds, uint32_t k, uint64_t seed, uint32_t fit_id,
+                              double* mu_out, int64_t* rows_out);
+/* bootstrap row numbers of bootstrap_data (src/Clusterer.cpp:308-321) for one fit id */
+int dpr_bootstrap_rows(int64_t n, uint32_t boot_n, uint64_t seed, uint32_t fit_id, int64_t* rows_out);
+/* resample a dataset by explicit rows (with replacement) into a new resident dataset */
+int dpr_dataset_gather(dpr_dataset_t ds, const int64_t* rows, int64_t m, dpr_dataset_t* out);
+/* cluster_norm (src/Clusterer.cpp:198-211) and n_used_clusters (:323-332) */
+int dpr_dataset_cluster_norm(dpr_dataset_t ds, const double* mu, uint32_t k, const int32_t* idx, double reg,
+                             double* out);
+int dpr_n_used_clusters(const int32_t* idx, int64_t n, uint32_t k, uint32_t* out);
+/* batched scoring: allocate the dataset to m centre sets (no_zero per call) in ONE pass over X and
+ * return the all-pairs ARI matrix (m x m, col-major) of depecheClusterCenterSelection
+ * (R/depecheClusterCenterSelection.R:11-29).  mus: m matrices k x d col-major back to back.
+ * labels_out (nullable): m x n int32 (set-major). */
+int dpr_dataset_allocate_many(dpr_dataset_t ds, const double* mus, int32_t m, int32_t k, int32_t no_zero,
+                              int32_t* labels_out, double* ari_out);
+
+/* ---- device-resident Lloyd iterations (bench: the timed hot loop, nothing crosses PCIe) --------- */
+/* Runs `iters` fused iterations (assignment + sums/counts + soft-threshold update, ramp frozen at
+ * ramp_i) from mu_inout, without convergence exit; changed_out (nullable) = labels changed in the last. */
+int dpr_dataset_lloyd_iterations(dpr_dataset_t ds, double* mu_inout, uint32_t k, double reg, int32_t no_zero,
+                                 int32_t ramp_i, int32_t iters, int64_t* changed_out);
+/* same for the plain assignment pass (dAllocate's kernel), labels stay on device */
+int dpr_dataset_assign_iterations(dpr_dataset_t ds, const double* mu, uint32_t k, int32_t no_zero,
+                                  int32_t iters);
+
+/* ---- multi-GPU (one process per GPU; rows of X sharded; NCCL allreduce of K x (D+1) partials) ------ */
+/* unique_id: the 128-byte ncclUniqueId made by rank 0 (dpr_comm_unique_id) and broadcast by the host
+ * layer (torch.distributed / MPI / R sockets).  nccl_path: library to dlopen (NULL = "libnccl.so.2"). */
+int dpr_comm_unique_id(void* id128, const char* nccl_path);
+int dpr_comm_init(int32_t rank, int32_t world, const void* id128, const char* nccl_path);
+int dpr_comm_destroy(void);
+int dpr_comm_info(int32_t* rank, int32_t* world);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEPECHER_B200_H */

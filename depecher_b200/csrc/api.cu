@@ -1,0 +1,732 @@
+// api.cu — the C ABI (include/depecher_b200.h): context, resident datasets and the entry points that
+// replace the reference's four Rcpp exports (/root/reference/src/InterfaceUtils.cpp:66-161).
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "comm.cuh"
+#include "common.cuh"
+#include "session.cuh"
+#include "../../include/dpr_philox.h"
+
+namespace dpr {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+Context& ctx() {
+    static Context c;
+    return c;
+}
+int ensure_ready() {
+    Context& c = ctx();
+    if (c.ready) return DPR_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1)
+        return fail(DPR_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                           " (this library has no CPU fallback)");
+    if (c.device >= n) return fail(DPR_ERR_NO_DEVICE, "device ordinal out of range");
+    DPR_CUDA(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    DPR_CUDA(cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major != 10)
+        return fail(DPR_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                           "; the kernels are built for sm_100a (B200) only");
+    c.sms = prop.multiProcessorCount;
+    DPR_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    if (!c.stream) c.stream = c.own_stream;
+    c.ready = true;
+    return DPR_OK;
+}
+
+void bench_session_forget(dpr_dataset* ds);
+
+// ---- small RAII helpers for temporaries ----------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes, bool zero = false) {
+        DPR_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+        if (zero) DPR_CUDA(cudaMemsetAsync(p, 0, bytes ? bytes : 1, ctx().stream));
+        return DPR_OK;
+    }
+    template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+static void colmajor_to_rowmajor(const double* cm, int rows, int cols, std::vector<double>& rm) {
+    rm.resize((size_t)rows * cols);
+    for (int i = 0; i < rows; ++i)
+        for (int j = 0; j < cols; ++j) rm[(size_t)i * cols + j] = cm[(size_t)j * rows + i];
+}
+static void rowmajor_to_colmajor(const std::vector<double>& rm, int rows, int cols, double* cm) {
+    for (int i = 0; i < rows; ++i)
+        for (int j = 0; j < cols; ++j) cm[(size_t)j * rows + i] = rm[(size_t)i * cols + j];
+}
+
+static int dataset_alloc(int64_t n, int32_t d, dpr_dataset** out) {
+    DPR_TRY(ensure_ready());
+    if (n < 1 || d < 1 || !out) return fail(DPR_ERR_INVALID, "dataset needs n >= 1, d >= 1");
+    std::unique_ptr<dpr_dataset> ds(new dpr_dataset());
+    ds->n = n;
+    ds->d = d;
+    ds->ld = (n + kSlotCells - 1) / kSlotCells * kSlotCells;
+    const size_t bytes = sizeof(float) * (size_t)ds->ld * d;
+    DPR_CUDA(cudaMalloc(&ds->x, bytes));
+    DPR_CUDA(cudaMemsetAsync(ds->x, 0, bytes, ctx().stream));
+    *out = ds.release();
+    return DPR_OK;
+}
+static int dataset_labels(dpr_dataset* ds) {
+    if (!ds->labels) DPR_CUDA(cudaMalloc(&ds->labels, sizeof(int32_t) * (size_t)ds->ld));
+    return DPR_OK;
+}
+
+// host -> device in bounded chunks through a device staging buffer (R hands over pageable memory)
+template <typename T>
+static int dataset_upload(dpr_dataset* ds, const T* X) {
+    const int64_t total = ds->n * ds->d;
+    const int64_t chunk = std::min<int64_t>(total, (int64_t)16 << 20);  // elements
+    DevBuf stage[2];
+    DPR_TRY(stage[0].alloc(sizeof(T) * chunk));
+    DPR_TRY(stage[1].alloc(sizeof(T) * chunk));
+    cudaEvent_t freed[2];
+    for (auto& e : freed) DPR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int b = 0;
+    for (int64_t e0 = 0; e0 < total; e0 += chunk, b ^= 1) {
+        const int64_t cnt = std::min(chunk, total - e0);
+        DPR_CUDA(cudaEventSynchronize(freed[b]));
+        DPR_CUDA(cudaMemcpyAsync(stage[b].p, X + e0, sizeof(T) * cnt, cudaMemcpyHostToDevice, ctx().stream));
+        if (sizeof(T) == 8) DPR_TRY(launch_f64_to_cols(stage[b].as<double>(), e0, cnt, ds->n, ds->ld, ds->x, ctx().stream));
+        else DPR_TRY(launch_f32_to_cols(stage[b].as<float>(), e0, cnt, ds->n, ds->ld, ds->x, ctx().stream));
+        DPR_CUDA(cudaEventRecord(freed[b], ctx().stream));
+    }
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    for (auto& e : freed) cudaEventDestroy(e);
+    return DPR_OK;
+}
+
+// one Session over `ds` with a single problem
+static int single_session(dpr_dataset* ds, int k, double reg, int no_zero, bool want_sums, Session& s) {
+    DPR_TRY(dataset_labels(ds));
+    std::vector<ProblemSpec> specs(1);
+    specs[0] = ProblemSpec{ds->x, ds->ld, ds->n, k, reg, no_zero, ds->labels};
+    return s.init(specs, ds->d, want_sums);
+}
+
+static int copy_labels_out(const int32_t* d_labels, int64_t n, int32_t* host) {
+    if (!host) return DPR_OK;
+    DPR_CUDA(cudaMemcpyAsync(host, d_labels, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx().stream));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    return DPR_OK;
+}
+
+// cluster_norm (Clusterer.cpp:198-211) for problem p of a session
+static int cluster_norm_dev(const Problem& pr, int d, double reg, double* out) {
+    const int blocks = (int)std::min<int64_t>(148 * 4, (pr.n + 255) / 256);
+    DevBuf part;
+    DPR_TRY(part.alloc(sizeof(double) * blocks));
+    DPR_TRY(launch_ssq(pr.x, pr.ld, pr.n, d, pr.mu, pr.k, pr.labels, part.as<double>(), blocks, ctx().stream));
+    std::vector<double> hp(blocks), mu((size_t)pr.k * d);
+    DPR_CUDA(cudaMemcpyAsync(hp.data(), part.p, sizeof(double) * blocks, cudaMemcpyDeviceToHost, ctx().stream));
+    DPR_CUDA(cudaMemcpyAsync(mu.data(), pr.mu, sizeof(double) * mu.size(), cudaMemcpyDeviceToHost, ctx().stream));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    double ssq = 0.0;
+    for (double v : hp) ssq += v;
+    for (int j = 0; j < d; ++j)                      // column by column, like the reference (:204-208)
+        for (int c = 0; c < pr.k; ++c) ssq += mu[(size_t)c * d + j] * reg;
+    *out = ssq;
+    return DPR_OK;
+}
+
+// k-means++ for a list of fits (data pointers may differ); mus[f] = device k x d row-major
+struct SeedJob {
+    const float* x;
+    int64_t ld, n;
+    uint32_t fit_id;
+    double* mu;
+    long long* rows;
+};
+static int run_seeding(const std::vector<SeedJob>& jobs, int d, int k, uint64_t seed) {
+    const int F = (int)jobs.size();
+    int64_t n_max = 0, w_total = 0, b_total = 0;
+    for (auto& j : jobs) {
+        n_max = std::max(n_max, j.n);
+        w_total += j.n;
+        b_total += (j.n + kSeedBlock - 1) / kSeedBlock;
+    }
+    DevBuf w, bs, fits;
+    DPR_TRY(w.alloc(sizeof(double) * w_total));
+    DPR_TRY(bs.alloc(sizeof(double) * b_total));
+    DPR_TRY(fits.alloc(sizeof(SeedFit) * F));
+    std::vector<SeedFit> h(F);
+    int64_t wo = 0, bo = 0;
+    for (int f = 0; f < F; ++f) {
+        h[f] = SeedFit{jobs[f].x, jobs[f].ld, jobs[f].n, jobs[f].fit_id, 0, jobs[f].mu, w.as<double>() + wo, bs.as<double>() + bo, jobs[f].rows};
+        wo += jobs[f].n;
+        bo += (jobs[f].n + kSeedBlock - 1) / kSeedBlock;
+    }
+    DPR_CUDA(cudaMemcpyAsync(fits.p, h.data(), sizeof(SeedFit) * F, cudaMemcpyHostToDevice, ctx().stream));
+    DPR_TRY(launch_seeding(fits.as<SeedFit>(), F, n_max, d, k, seed, ctx().stream));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    return DPR_OK;
+}
+
+// ARI for pairs of device label arrays
+struct PairJob {
+    const int32_t* a;
+    const int32_t* b;
+    int64_t n;
+    uint32_t pair_id;
+};
+static int run_ari(const std::vector<PairJob>& jobs, uint32_t k, uint64_t seed, double* out_host) {
+    const int P = (int)jobs.size();
+    const int kk = (int)k + 1;
+    int64_t n_max = 0;
+    std::vector<AriPair> h(P);
+    for (int p = 0; p < P; ++p) {
+        h[p] = AriPair{jobs[p].a, jobs[p].b, jobs[p].n, jobs[p].pair_id, 0};
+        n_max = std::max(n_max, jobs[p].n);
+    }
+    DevBuf pairs, tables, stab, bad, out;
+    DPR_TRY(pairs.alloc(sizeof(AriPair) * P));
+    DPR_TRY(tables.alloc(sizeof(unsigned long long) * (size_t)P * kk * kk, true));
+    DPR_TRY(stab.alloc(sizeof(unsigned int) * P, true));
+    DPR_TRY(bad.alloc(sizeof(int32_t), true));
+    DPR_TRY(out.alloc(sizeof(double) * P));
+    DPR_CUDA(cudaMemcpyAsync(pairs.p, h.data(), sizeof(AriPair) * P, cudaMemcpyHostToDevice, ctx().stream));
+    DPR_TRY(launch_ari(pairs.as<AriPair>(), P, n_max, kk, ctx().ari_mode, seed, tables.as<unsigned long long>(), stab.as<unsigned int>(),
+                       bad.as<int32_t>(), out.as<double>(), ctx().stream));
+    int32_t hbad = 0;
+    DPR_CUDA(cudaMemcpyAsync(out_host, out.p, sizeof(double) * P, cudaMemcpyDeviceToHost, ctx().stream));
+    DPR_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx().stream));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (hbad) return fail(DPR_ERR_INVALID, "rand_index: a label lies outside [0, k]");
+    return DPR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// find_centers on a resident dataset (Clusterer.cpp:213-265), from k-means++ or from given centres
+// ------------------------------------------------------------------------------------------------
+static int find_centers_dev(dpr_dataset* ds, const double* init_mu_colmajor, uint32_t k, double reg, int no_zero, int max_iter,
+                            uint64_t seed, uint32_t fit_id, int32_t* idx_out, double* centers_out, double* norm_out,
+                            int32_t* n_iter_out) {
+    if (!ds) return fail(DPR_ERR_INVALID, "null dataset");
+    if (k < 2) return fail(DPR_ERR_INVALID, "k must be >= 2 (initialize_mu writes two rows, Clusterer.cpp:157-162)");
+    if (max_iter < 1) return fail(DPR_ERR_INVALID, "max_iter must be >= 1");
+    Session s;
+    DPR_TRY(single_session(ds, (int)k, reg, no_zero, true, s));
+    if (init_mu_colmajor) {
+        std::vector<double> rm;
+        colmajor_to_rowmajor(init_mu_colmajor, (int)k, ds->d, rm);
+        DPR_TRY(s.set_centres(0, rm.data()));
+    } else {
+        std::vector<SeedJob> jobs(1);
+        jobs[0] = SeedJob{ds->x, ds->ld, ds->n, fit_id, s.h_problems[0].mu, nullptr};
+        DPR_TRY(run_seeding(jobs, ds->d, (int)k, seed));
+    }
+    DPR_TRY(s.prepare());
+    DPR_TRY(s.zero_labels());
+    DPR_TRY(s.lloyd(max_iter));
+    DPR_TRY(s.fetch_state());
+    const Problem& pr = s.h_problems[0];
+    if (n_iter_out) *n_iter_out = pr.n_assign;
+    DPR_TRY(copy_labels_out(pr.labels, ds->n, idx_out));
+    if (centers_out) {
+        std::vector<double> rm((size_t)k * ds->d);
+        DPR_TRY(s.get_centres(0, rm.data()));
+        rowmajor_to_colmajor(rm, (int)k, ds->d, centers_out);
+    }
+    if (norm_out) DPR_TRY(cluster_norm_dev(pr, ds->d, reg, norm_out));
+    return DPR_OK;
+}
+
+static std::unique_ptr<Session> g_bench_session;
+static dpr_dataset* g_bench_ds = nullptr;
+static int g_bench_k = 0, g_bench_mode = -1;
+void bench_session_forget(dpr_dataset* ds) {
+    if (ds == g_bench_ds) {
+        g_bench_session.reset();
+        g_bench_ds = nullptr;
+    }
+}
+
+}  // namespace dpr
+
+using namespace dpr;
+
+extern "C" {
+
+const char* dpr_last_error(void) { return g_error.c_str(); }
+int dpr_version(void) { return 100; }
+int dpr_device_count(int32_t* out) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
+    if (out) *out = n;
+    return DPR_OK;
+}
+int dpr_set_device(int32_t ordinal) {
+    if (ctx().ready && ctx().device != ordinal) return fail(DPR_ERR_STATE, "device already initialised");
+    ctx().device = ordinal;
+    return DPR_OK;
+}
+int dpr_set_stream(void* s) {
+    DPR_TRY(ensure_ready());
+    ctx().stream = s ? (cudaStream_t)s : ctx().own_stream;
+    return DPR_OK;
+}
+int dpr_synchronize(void) {
+    DPR_TRY(ensure_ready());
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    return DPR_OK;
+}
+int dpr_set_ari_mode(int32_t mode) {
+    if (mode != DPR_ARI_EXACT && mode != DPR_ARI_MONTE_CARLO) return fail(DPR_ERR_INVALID, "unknown ARI mode");
+    ctx().ari_mode = mode;
+    return DPR_OK;
+}
+int dpr_kernel_launches(int64_t* out, int32_t reset) {
+    if (out) *out = ctx().launches;
+    if (reset) ctx().launches = 0;
+    return DPR_OK;
+}
+
+// ---- datasets -------------------------------------------------------------------------------------
+int dpr_dataset_create(const double* X, int64_t n, int32_t d, dpr_dataset_t* out) {
+    if (!X) return fail(DPR_ERR_INVALID, "null X");
+    dpr_dataset* ds = nullptr;
+    DPR_TRY(dataset_alloc(n, d, &ds));
+    int rc = dataset_upload(ds, X);
+    if (rc != DPR_OK) { dpr_dataset_destroy(ds); return rc; }
+    *out = ds;
+    return DPR_OK;
+}
+int dpr_dataset_create_f32(const float* X, int64_t n, int32_t d, dpr_dataset_t* out) {
+    if (!X) return fail(DPR_ERR_INVALID, "null X");
+    dpr_dataset* ds = nullptr;
+    DPR_TRY(dataset_alloc(n, d, &ds));
+    int rc = dataset_upload(ds, X);
+    if (rc != DPR_OK) { dpr_dataset_destroy(ds); return rc; }
+    *out = ds;
+    return DPR_OK;
+}
+int dpr_dataset_create_synthetic(int64_t n, int32_t d, int32_t groups, double amplitude, uint64_t seed, dpr_dataset_t* out) {
+    if (groups < 1) return fail(DPR_ERR_INVALID, "groups must be >= 1");
+    dpr_dataset* ds = nullptr;
+    DPR_TRY(dataset_alloc(n, d, &ds));
+    // centre coordinates iid from {-a, 0, +a}; group g additionally has ceil(g*d/(2G)) zeroed markers
+    std::vector<float> cen((size_t)groups * d);
+    for (int g = 0; g < groups; ++g) {
+        for (int j = 0; j < d; ++j) {
+            const uint32_t r = dpr_rng_draw(seed, 10, (uint32_t)g, (uint32_t)j, 0).w[0] % 3u;
+            cen[(size_t)g * d + j] = (float)((double)((int)r - 1) * amplitude);
+        }
+        const int zeros = (g * d + 2 * groups - 1) / (2 * groups);
+        for (int z = 0; z < zeros; ++z) cen[(size_t)g * d + dpr_rng_draw(seed, 10, (uint32_t)g, (uint32_t)z, 1).w[0] % (uint32_t)d] = 0.f;
+    }
+    DevBuf dc, acc;
+    int rc = dc.alloc(sizeof(float) * cen.size());
+    if (rc == DPR_OK) rc = acc.alloc(sizeof(double) * 2, true);
+    if (rc != DPR_OK) { dpr_dataset_destroy(ds); return rc; }
+    cudaMemcpyAsync(dc.p, cen.data(), sizeof(float) * cen.size(), cudaMemcpyHostToDevice, ctx().stream);
+    rc = launch_synth(ds->x, ds->ld, n, d, dc.as<float>(), groups, seed, acc.as<double>(), acc.as<double>() + 1, ctx().stream);
+    double h[2] = {0, 0};
+    cudaMemcpyAsync(h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, ctx().stream);
+    cudaStreamSynchronize(ctx().stream);
+    const double cnt = (double)n * d, mean = h[0] / cnt;
+    const double var = (h[1] - cnt * mean * mean) / (cnt - 1);
+    if (rc == DPR_OK) rc = launch_scale(ds->x, ds->ld, n, d, (float)(1.0 / std::sqrt(var)), ctx().stream);
+    if (rc == DPR_OK && cudaStreamSynchronize(ctx().stream) != cudaSuccess) rc = fail(DPR_ERR_CUDA, "synthetic generation failed");
+    if (rc != DPR_OK) { dpr_dataset_destroy(ds); return rc; }
+    *out = ds;
+    return DPR_OK;
+}
+int dpr_dataset_destroy(dpr_dataset_t ds) {
+    if (!ds) return DPR_OK;
+    bench_session_forget(ds);
+    if (ds->x) cudaFree(ds->x);
+    if (ds->labels) cudaFree(ds->labels);
+    delete ds;
+    return DPR_OK;
+}
+int dpr_dataset_shape(dpr_dataset_t ds, int64_t* n, int32_t* d) {
+    if (!ds) return fail(DPR_ERR_INVALID, "null dataset");
+    if (n) *n = ds->n;
+    if (d) *d = ds->d;
+    return DPR_OK;
+}
+int dpr_dataset_read(dpr_dataset_t ds, int64_t row0, int64_t rows, double* out) {
+    if (!ds || !out || row0 < 0 || rows < 1 || row0 + rows > ds->n) return fail(DPR_ERR_INVALID, "bad row range");
+    DevBuf tmp;
+    DPR_TRY(tmp.alloc(sizeof(double) * rows * ds->d));
+    DPR_TRY(launch_cols_to_f64(ds->x, ds->ld, row0, rows, ds->d, tmp.as<double>(), ctx().stream));
+    DPR_CUDA(cudaMemcpyAsync(out, tmp.p, sizeof(double) * rows * ds->d, cudaMemcpyDeviceToHost, ctx().stream));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    return DPR_OK;
+}
+int dpr_dataset_gather(dpr_dataset_t ds, const int64_t* rows, int64_t m, dpr_dataset_t* out) {
+    if (!ds || !rows || m < 1 || !out) return fail(DPR_ERR_INVALID, "bad gather arguments");
+    for (int64_t i = 0; i < m; ++i)
+        if (rows[i] < 0 || rows[i] >= ds->n) return fail(DPR_ERR_INVALID, "row index out of range");
+    dpr_dataset* g = nullptr;
+    DPR_TRY(dataset_alloc(m, ds->d, &g));
+    DevBuf dr;
+    int rc = dr.alloc(sizeof(int64_t) * m);
+    if (rc == DPR_OK && cudaMemcpyAsync(dr.p, rows, sizeof(int64_t) * m, cudaMemcpyHostToDevice, ctx().stream) != cudaSuccess)
+        rc = fail(DPR_ERR_CUDA, "copy of row indices failed");
+    if (rc == DPR_OK) rc = launch_gather(ds->x, ds->ld, ds->n, ds->d, dr.as<int64_t>(), 0, 0, m, g->ld, g->x, 1, 0, ctx().stream);
+    if (rc == DPR_OK && cudaStreamSynchronize(ctx().stream) != cudaSuccess) rc = fail(DPR_ERR_CUDA, "gather failed");
+    if (rc != DPR_OK) { dpr_dataset_destroy(g); return rc; }
+    *out = g;
+    return DPR_OK;
+}
+
+// ---- allocate_points -------------------------------------------------------------------------------
+int dpr_dataset_allocate_points(dpr_dataset_t ds, const double* mu, int32_t k, int32_t no_zero, int32_t* idx_out) {
+    if (!ds || !mu || k < 1) return fail(DPR_ERR_INVALID, "allocate_points: null argument or k < 1");
+    Session s;
+    DPR_TRY(single_session(ds, k, 0.0, no_zero, false, s));
+    std::vector<double> rm;
+    colmajor_to_rowmajor(mu, k, ds->d, rm);
+    DPR_TRY(s.set_centres(0, rm.data()));
+    DPR_TRY(s.prepare());
+    DPR_TRY(s.pass(kPassAssign, false));
+    return copy_labels_out(ds->labels, ds->n, idx_out);
+}
+int dpr_allocate_points(const double* X, int64_t n, int32_t d, const double* mu, int32_t k, int32_t no_zero, int32_t* idx_out) {
+    if (!idx_out) return fail(DPR_ERR_INVALID, "null output");
+    dpr_dataset_t ds = nullptr;
+    DPR_TRY(dpr_dataset_create(X, n, d, &ds));
+    const int rc = dpr_dataset_allocate_points(ds, mu, k, no_zero, idx_out);
+    dpr_dataset_destroy(ds);
+    return rc;
+}
+
+// ---- sparse_k_means ----------------------------------------------------------------------------------
+int dpr_dataset_sparse_k_means(dpr_dataset_t ds, uint32_t k, double reg, int32_t no_zero, uint64_t seed, int32_t* idx_out,
+                               double* centers_out, double* norm_out, int32_t* n_iter_out) {
+    return find_centers_dev(ds, nullptr, k, reg, no_zero, 1000, seed, 0, idx_out, centers_out, norm_out, n_iter_out);
+}
+int dpr_sparse_k_means(const double* X, int64_t n, int32_t d, uint32_t k, double reg, int32_t no_zero, uint64_t seed,
+                       int32_t* idx_out, double* centers_out, double* norm_out, int32_t* n_iter_out) {
+    dpr_dataset_t ds = nullptr;
+    DPR_TRY(dpr_dataset_create(X, n, d, &ds));
+    const int rc = dpr_dataset_sparse_k_means(ds, k, reg, no_zero, seed, idx_out, centers_out, norm_out, n_iter_out);
+    dpr_dataset_destroy(ds);
+    return rc;
+}
+int dpr_dataset_find_centers_from(dpr_dataset_t ds, const double* init_mu, uint32_t k, double reg, int32_t no_zero, int32_t max_iter,
+                                  int32_t* idx_out, double* centers_out, double* norm_out, int32_t* n_iter_out) {
+    if (!init_mu) return fail(DPR_ERR_INVALID, "null initial centres");
+    return find_centers_dev(ds, init_mu, k, reg, no_zero, max_iter, 0, 0, idx_out, centers_out, norm_out, n_iter_out);
+}
+
+int dpr_dataset_initialize_mu(dpr_dataset_t ds, uint32_t k, uint64_t seed, uint32_t fit_id, double* mu_out, int64_t* rows_out) {
+    if (!ds || !mu_out || k < 2) return fail(DPR_ERR_INVALID, "initialize_mu: null argument or k < 2");
+    DPR_TRY(ensure_ready());
+    DevBuf mu, rows;
+    DPR_TRY(mu.alloc(sizeof(double) * k * ds->d, true));
+    DPR_TRY(rows.alloc(sizeof(long long) * k, true));
+    std::vector<SeedJob> jobs(1);
+    jobs[0] = SeedJob{ds->x, ds->ld, ds->n, fit_id, mu.as<double>(), rows.as<long long>()};
+    DPR_TRY(run_seeding(jobs, ds->d, (int)k, seed));
+    std::vector<double> rm((size_t)k * ds->d);
+    std::vector<long long> hr(k);
+    DPR_CUDA(cudaMemcpyAsync(rm.data(), mu.p, sizeof(double) * rm.size(), cudaMemcpyDeviceToHost, ctx().stream));
+    DPR_CUDA(cudaMemcpyAsync(hr.data(), rows.p, sizeof(long long) * k, cudaMemcpyDeviceToHost, ctx().stream));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    rowmajor_to_colmajor(rm, (int)k, ds->d, mu_out);
+    if (rows_out)
+        for (uint32_t c = 0; c < k; ++c) rows_out[c] = hr[c];
+    return DPR_OK;
+}
+
+int dpr_bootstrap_rows(int64_t n, uint32_t boot_n, uint64_t seed, uint32_t fit_id, int64_t* rows_out) {
+    if (n < 1 || boot_n < 1 || !rows_out) return fail(DPR_ERR_INVALID, "bootstrap_rows: bad arguments");
+    DPR_TRY(ensure_ready());
+    DevBuf rows;
+    DPR_TRY(rows.alloc(sizeof(int64_t) * boot_n));
+    DPR_TRY(launch_bootstrap_rows(n, boot_n, seed, fit_id, rows.as<int64_t>(), ctx().stream));
+    DPR_CUDA(cudaMemcpyAsync(rows_out, rows.p, sizeof(int64_t) * boot_n, cudaMemcpyDeviceToHost, ctx().stream));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    return DPR_OK;
+}
+
+// reevaluate_centers for explicit labels (Clusterer.cpp:89-108)
+int dpr_dataset_reevaluate_centers(dpr_dataset_t ds, const int32_t* idx, uint32_t k, double reg, double* centers_out,
+                                   int64_t* counts_out) {
+    if (!ds || !idx || !centers_out || k < 1) return fail(DPR_ERR_INVALID, "reevaluate_centers: bad arguments");
+    for (int64_t i = 0; i < ds->n; ++i)
+        if (idx[i] < 0 || (uint32_t)idx[i] >= k) return fail(DPR_ERR_INVALID, "label outside [0, k)");
+    Session s;
+    DPR_TRY(single_session(ds, (int)k, reg, 0, true, s));
+    DPR_CUDA(cudaMemcpyAsync(ds->labels, idx, sizeof(int32_t) * ds->n, cudaMemcpyHostToDevice, ctx().stream));
+    DPR_TRY(s.prepare());
+    DPR_TRY(s.pass(kPassSums, false));
+    // iter = 20 makes the ramp factor exactly 1 (reg_i = reg); max_iter large so no cap handling
+    DPR_TRY(s.reduce_and_finalize(20, 1 << 30));
+    std::vector<double> rm((size_t)k * ds->d);
+    DPR_TRY(s.get_centres(0, rm.data()));
+    rowmajor_to_colmajor(rm, (int)k, ds->d, centers_out);
+    if (counts_out) {
+        std::vector<long long> c(k);
+        DPR_CUDA(cudaMemcpyAsync(c.data(), s.h_problems[0].counts, sizeof(long long) * k, cudaMemcpyDeviceToHost, ctx().stream));
+        DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+        for (uint32_t i = 0; i < k; ++i) counts_out[i] = c[i];
+    }
+    return DPR_OK;
+}
+
+int dpr_dataset_cluster_norm(dpr_dataset_t ds, const double* mu, uint32_t k, const int32_t* idx, double reg, double* out) {
+    if (!ds || !mu || !idx || !out || k < 1) return fail(DPR_ERR_INVALID, "cluster_norm: bad arguments");
+    for (int64_t i = 0; i < ds->n; ++i)
+        if (idx[i] < 0 || (uint32_t)idx[i] >= k) return fail(DPR_ERR_INVALID, "label outside [0, k)");
+    DPR_TRY(dataset_labels(ds));
+    DevBuf dmu;
+    DPR_TRY(dmu.alloc(sizeof(double) * k * ds->d));
+    std::vector<double> rm;
+    colmajor_to_rowmajor(mu, (int)k, ds->d, rm);
+    DPR_CUDA(cudaMemcpyAsync(dmu.p, rm.data(), sizeof(double) * rm.size(), cudaMemcpyHostToDevice, ctx().stream));
+    DPR_CUDA(cudaMemcpyAsync(ds->labels, idx, sizeof(int32_t) * ds->n, cudaMemcpyHostToDevice, ctx().stream));
+    Problem pr{};
+    pr.x = ds->x;
+    pr.ld = ds->ld;
+    pr.n = ds->n;
+    pr.k = (int)k;
+    pr.mu = dmu.as<double>();
+    pr.labels = ds->labels;
+    return cluster_norm_dev(pr, ds->d, reg, out);
+}
+
+int dpr_n_used_clusters(const int32_t* idx, int64_t n, uint32_t k, uint32_t* out) {
+    if (!idx || !out || n < 1) return fail(DPR_ERR_INVALID, "n_used_clusters: bad arguments");
+    DPR_TRY(ensure_ready());
+    DevBuf lab, present, bad;
+    DPR_TRY(lab.alloc(sizeof(int32_t) * n));
+    DPR_TRY(present.alloc(sizeof(int32_t) * (k + 1), true));
+    DPR_TRY(bad.alloc(sizeof(int32_t), true));
+    DPR_CUDA(cudaMemcpyAsync(lab.p, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx().stream));
+    DPR_TRY(launch_label_presence(lab.as<int32_t>(), n, (int)k + 1, present.as<int32_t>(), bad.as<int32_t>(), ctx().stream));
+    std::vector<int32_t> h(k + 1);
+    int32_t hbad = 0;
+    DPR_CUDA(cudaMemcpyAsync(h.data(), present.p, sizeof(int32_t) * (k + 1), cudaMemcpyDeviceToHost, ctx().stream));
+    DPR_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx().stream));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (hbad) return fail(DPR_ERR_INVALID, "label outside [0, k]");
+    uint32_t c = 0;
+    for (int32_t v : h) c += v != 0;
+    *out = c;
+    return DPR_OK;
+}
+
+// ---- rand_index ------------------------------------------------------------------------------------------
+int dpr_rand_index(const int32_t* a, const int32_t* b, int64_t n, uint32_t k, double* out) {
+    if (!a || !b || !out || n < 2) return fail(DPR_ERR_INVALID, "rand_index: null argument or n < 2");
+    DPR_TRY(ensure_ready());
+    DevBuf da, db;
+    DPR_TRY(da.alloc(sizeof(int32_t) * n));
+    DPR_TRY(db.alloc(sizeof(int32_t) * n));
+    DPR_CUDA(cudaMemcpyAsync(da.p, a, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx().stream));
+    DPR_CUDA(cudaMemcpyAsync(db.p, b, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx().stream));
+    std::vector<PairJob> jobs(1);
+    jobs[0] = PairJob{da.as<int32_t>(), db.as<int32_t>(), n, 0};
+    return run_ari(jobs, k, 0, out);
+}
+
+// ---- grid_search (optimize_param, Clusterer.cpp:334-394) ---------------------------------------------------
+// All (iteration, k, penalty) cells are independent: the 2 * iterations * nk * nreg bootstrap fits run as ONE
+// batch of problems (every launch serves all of them), then the 2 * ... scoring assignments of the full data
+// run as one batch, then one batched ARI launch.  The two extra allocations of the reference whose results
+// are discarded (:373-374) are not performed.
+int dpr_dataset_grid_search(dpr_dataset_t ds, const int32_t* k, int32_t nk, const double* reg, int32_t nreg, uint32_t iterations,
+                            uint32_t boot_n, uint64_t seed, double* ari_out, double* nclust_out, double* centers_out) {
+    if (!ds || !k || !reg || !ari_out || !nclust_out || nk < 1 || nreg < 1 || iterations < 1 || boot_n < 1)
+        return fail(DPR_ERR_INVALID, "grid_search: bad arguments");
+    for (int j = 0; j < nk; ++j)
+        if (k[j] < 2) return fail(DPR_ERR_INVALID, "grid_search: every k must be >= 2");
+    DPR_TRY(ensure_ready());
+    const int d = ds->d;
+    const int cells = (int)iterations * nk * nreg;
+    const int F = 2 * cells;
+    const int64_t ldb = ((int64_t)boot_n + kSlotCells - 1) / kSlotCells * kSlotCells;
+    // 1. bootstrap samples (bootstrap_data, :354-355): fit f = 2 * problem + which
+    DevBuf xb, lab_b;
+    DPR_TRY(xb.alloc(sizeof(float) * (size_t)F * ldb * d, true));
+    DPR_TRY(lab_b.alloc(sizeof(int32_t) * (size_t)F * ldb, true));
+    DPR_TRY(launch_gather(ds->x, ds->ld, ds->n, d, nullptr, seed, 0, boot_n, ldb, xb.as<float>(), F, ldb * d, ctx().stream));
+    // 2. the fits (find_centers with zero-centre removal, :361-362)
+    std::vector<ProblemSpec> specs(F);
+    auto cell_of = [&](int f, int& it, int& j, int& l) {
+        const int c = f / 2;
+        l = c % nreg;
+        j = (c / nreg) % nk;
+        it = c / (nreg * nk);
+    };
+    for (int f = 0; f < F; ++f) {
+        int it, j, l;
+        cell_of(f, it, j, l);
+        specs[f] = ProblemSpec{xb.as<float>() + (size_t)f * ldb * d, ldb, (int64_t)boot_n, k[j], reg[l], 1, lab_b.as<int32_t>() + (size_t)f * ldb};
+    }
+    Session fits;
+    DPR_TRY(fits.init(specs, d, true));
+    {
+        std::vector<SeedJob> jobs(F);
+        for (int f = 0; f < F; ++f) jobs[f] = SeedJob{specs[f].x, ldb, (int64_t)boot_n, (uint32_t)f, fits.h_problems[f].mu, nullptr};
+        // seeding rounds are batched per k (the number of rounds is k - 1)
+        for (int j = 0; j < nk; ++j) {
+            std::vector<SeedJob> sub;
+            for (int f = 0; f < F; ++f) {
+                int it, jj, l;
+                cell_of(f, it, jj, l);
+                if (jj == j) sub.push_back(jobs[f]);
+            }
+            if (!sub.empty()) DPR_TRY(run_seeding(sub, d, k[j], seed));
+        }
+    }
+    DPR_TRY(fits.prepare());
+    DPR_TRY(fits.lloyd(1000));
+    DPR_TRY(fits.fetch_state());
+    // distinct labels of each bootstrap fit (n_used_clusters, :379-380) = clusters with a non-zero count
+    std::vector<long long> counts((size_t)F * fits.k_max());
+    DPR_CUDA(cudaMemcpyAsync(counts.data(), fits.h_problems[0].counts, sizeof(long long) * counts.size(), cudaMemcpyDeviceToHost, ctx().stream));
+    // 3. score on the full data, no_zero = false (:370-371)
+    DevBuf lab_full;
+    DPR_TRY(lab_full.alloc(sizeof(int32_t) * (size_t)F * ds->ld));
+    std::vector<ProblemSpec> sspecs(F);
+    for (int f = 0; f < F; ++f)
+        sspecs[f] = ProblemSpec{ds->x, ds->ld, ds->n, specs[f].k, 0.0, 0, lab_full.as<int32_t>() + (size_t)f * ds->ld};
+    Session score;
+    DPR_TRY(score.init(sspecs, d, false));
+    for (int f = 0; f < F; ++f) DPR_TRY(score.set_centres_device(f, fits.h_problems[f].mu));
+    DPR_TRY(score.prepare());
+    DPR_TRY(score.pass(kPassAssign, false));
+    // 4. ARI per cell; tables are sized by the largest k
+    int kmax = 0;
+    for (int j = 0; j < nk; ++j) kmax = std::max(kmax, (int)k[j]);
+    std::vector<PairJob> pairs(cells);
+    for (int c = 0; c < cells; ++c)
+        pairs[c] = PairJob{sspecs[2 * c].labels, sspecs[2 * c + 1].labels, ds->n, (uint32_t)c};
+    std::vector<double> ari(cells);
+    DPR_TRY(run_ari(pairs, (uint32_t)kmax, seed, ari.data()));
+    // 5. reduce over iterations like the reference (:387-390)
+    for (int e = 0; e < nk * nreg; ++e) ari_out[e] = nclust_out[e] = 0.0;
+    size_t coff = 0;
+    for (int c = 0; c < cells; ++c) {
+        const int l = c % nreg, j = (c / nreg) % nk;
+        ari_out[(size_t)l * nk + j] += ari[c];
+        for (int w = 0; w < 2; ++w) {
+            int used = 0;
+            for (int q = 0; q < k[j]; ++q) used += counts[(size_t)(2 * c + w) * fits.k_max() + q] > 0;
+            nclust_out[(size_t)l * nk + j] += used;
+            if (centers_out) {
+                std::vector<double> rm((size_t)k[j] * d);
+                DPR_TRY(fits.get_centres(2 * c + w, rm.data()));
+                rowmajor_to_colmajor(rm, k[j], d, centers_out + coff);
+                coff += (size_t)k[j] * d;
+            }
+        }
+    }
+    for (int e = 0; e < nk * nreg; ++e) {
+        ari_out[e] /= iterations;
+        nclust_out[e] /= (iterations * 2);
+    }
+    return DPR_OK;
+}
+int dpr_grid_search(const double* X, int64_t n, int32_t d, const int32_t* k, int32_t nk, const double* reg, int32_t nreg,
+                    uint32_t iterations, uint32_t boot_n, uint64_t seed, double* ari_out, double* nclust_out, double* centers_out) {
+    dpr_dataset_t ds = nullptr;
+    DPR_TRY(dpr_dataset_create(X, n, d, &ds));
+    const int rc = dpr_dataset_grid_search(ds, k, nk, reg, nreg, iterations, boot_n, seed, ari_out, nclust_out, centers_out);
+    dpr_dataset_destroy(ds);
+    return rc;
+}
+
+// ---- allocate to many centre sets + all-pairs ARI (depecheClusterCenterSelection.R:11-29) ---------------------
+int dpr_dataset_allocate_many(dpr_dataset_t ds, const double* mus, int32_t m, int32_t k, int32_t no_zero, int32_t* labels_out,
+                              double* ari_out) {
+    if (!ds || !mus || m < 1 || k < 1) return fail(DPR_ERR_INVALID, "allocate_many: bad arguments");
+    DPR_TRY(ensure_ready());
+    const int d = ds->d;
+    DevBuf lab;
+    DPR_TRY(lab.alloc(sizeof(int32_t) * (size_t)m * ds->ld));
+    std::vector<ProblemSpec> specs(m);
+    for (int s = 0; s < m; ++s) specs[s] = ProblemSpec{ds->x, ds->ld, ds->n, k, 0.0, no_zero, lab.as<int32_t>() + (size_t)s * ds->ld};
+    Session sess;
+    DPR_TRY(sess.init(specs, d, false));
+    std::vector<double> rm;
+    for (int s = 0; s < m; ++s) {
+        colmajor_to_rowmajor(mus + (size_t)s * k * d, k, d, rm);
+        DPR_CUDA(cudaMemcpyAsync(sess.h_problems[s].mu, rm.data(), sizeof(double) * rm.size(), cudaMemcpyHostToDevice, ctx().stream));
+        DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
+    DPR_TRY(sess.prepare());
+    DPR_TRY(sess.pass(kPassAssign, false));
+    if (labels_out)
+        for (int s = 0; s < m; ++s) DPR_TRY(copy_labels_out(specs[s].labels, ds->n, labels_out + (size_t)s * ds->n));
+    if (ari_out) {
+        // dAllocate returns 1-based labels and rand_index gets k (R/dAllocate.R:134, depecheClusterCenterSelection.R:26-29);
+        // the partition is the same with 0-based labels, and the (k+1)-wide table holds both.
+        std::vector<PairJob> pairs;
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) pairs.push_back(PairJob{specs[j].labels, specs[i].labels, ds->n, (uint32_t)(i * m + j)});
+        std::vector<double> vals(pairs.size());
+        DPR_TRY(run_ari(pairs, (uint32_t)k, 0, vals.data()));
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) ari_out[(size_t)i * m + j] = vals[(size_t)i * m + j];
+    }
+    return DPR_OK;
+}
+
+// ---- device-resident iterations for the bench ----------------------------------------------------------------------
+
+static int bench_session(dpr_dataset_t ds, const double* mu, uint32_t k, double reg, int no_zero, bool sums) {
+    if (!g_bench_session || g_bench_ds != ds || g_bench_k != (int)k || g_bench_mode != (int)sums) {
+        g_bench_session.reset(new Session());
+        DPR_TRY(single_session(ds, (int)k, reg, no_zero, sums, *g_bench_session));
+        g_bench_ds = ds;
+        g_bench_k = (int)k;
+        g_bench_mode = (int)sums;
+    }
+    std::vector<double> rm;
+    colmajor_to_rowmajor(mu, (int)k, ds->d, rm);
+    DPR_TRY(g_bench_session->set_centres(0, rm.data()));
+    Problem& pr = g_bench_session->h_problems[0];
+    pr.reg = reg;
+    pr.no_zero = no_zero;
+    pr.done = 0;
+    DPR_CUDA(cudaMemcpyAsync(g_bench_session->d_problems, &pr, sizeof(Problem), cudaMemcpyHostToDevice, ctx().stream));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    return g_bench_session->prepare();
+}
+
+int dpr_dataset_lloyd_iterations(dpr_dataset_t ds, double* mu_inout, uint32_t k, double reg, int32_t no_zero, int32_t ramp_i,
+                                 int32_t iters, int64_t* changed_out) {
+    if (!ds || !mu_inout || k < 2 || iters < 1) return fail(DPR_ERR_INVALID, "lloyd_iterations: bad arguments");
+    DPR_TRY(bench_session(ds, mu_inout, k, reg, no_zero, true));
+    Session& s = *g_bench_session;
+    for (int i = 0; i < iters; ++i) {
+        DPR_TRY(s.pass(kPassLloyd, true));
+        DPR_TRY(s.reduce_and_finalize(std::min(ramp_i, 20), 1 << 30));  // i <= 20: never "converged", ramp frozen
+    }
+    DPR_TRY(s.fetch_state());
+    if (changed_out) *changed_out = s.h_problems[0].changed;
+    std::vector<double> rm((size_t)k * ds->d);
+    DPR_TRY(s.get_centres(0, rm.data()));
+    rowmajor_to_colmajor(rm, (int)k, ds->d, mu_inout);
+    return DPR_OK;
+}
+int dpr_dataset_assign_iterations(dpr_dataset_t ds, const double* mu, uint32_t k, int32_t no_zero, int32_t iters) {
+    if (!ds || !mu || k < 1 || iters < 1) return fail(DPR_ERR_INVALID, "assign_iterations: bad arguments");
+    DPR_TRY(bench_session(ds, mu, k, 0.0, no_zero, false));
+    for (int i = 0; i < iters; ++i) DPR_TRY(g_bench_session->pass(kPassAssign, false));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    return DPR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,458 @@
+// aux_kernels.cu — the O(N) helpers around the fused pass: layout conversion, bootstrap gather,
+// k-means++ seeding, cluster_norm, contingency tables / adjusted Rand index, synthetic data.
+// Each kernel names the reference lines it replaces.
+#include "aux_kernels.cuh"
+
+#include "../../include/dpr_philox.h"
+
+namespace dpr {
+
+// ---------------------------------------------------------------------------------------------------
+// R doubles (column-major n x d, flat range [e0, e0+count)) -> resident fp32 columns with leading
+// dimension ld.  Replaces numeric_to_eigen (src/InterfaceUtils.cpp:23-33), which transposes; here R's
+// layout is already the one the kernels want.
+// ---------------------------------------------------------------------------------------------------
+__global__ void f64_to_f32_cols_kernel(const double* __restrict__ src, int64_t e0, int64_t count, int64_t n, int64_t ld,
+                                       float* __restrict__ dst) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = e0 + t;
+        const int64_t j = e / n, i = e - j * n;
+        dst[j * ld + i] = (float)src[t];
+    }
+}
+__global__ void f32_to_f32_cols_kernel(const float* __restrict__ src, int64_t e0, int64_t count, int64_t n, int64_t ld,
+                                       float* __restrict__ dst) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = e0 + t;
+        const int64_t j = e / n, i = e - j * n;
+        dst[j * ld + i] = src[t];
+    }
+}
+__global__ void cols_to_f64_kernel(const float* __restrict__ x, int64_t ld, int64_t row0, int64_t rows, int d, double* __restrict__ out) {
+    const int64_t total = rows * d;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = t / rows, i = t - j * rows;
+        out[t] = (double)x[j * ld + row0 + i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bootstrap_data (src/Clusterer.cpp:308-321): rows drawn with replacement, gathered into a new matrix.
+// rows_explicit == nullptr -> row = Philox(seed, BOOT, fit, i) % n   (include/dpr_philox.h)
+// ---------------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const float* __restrict__ x, int64_t ld, int64_t n, int d, const int64_t* __restrict__ rows_explicit,
+                                   uint64_t seed, uint32_t fit0, int64_t m, int64_t ld_out, float* __restrict__ out, int n_fits,
+                                   int64_t fit_stride) {
+    const int64_t total = m * n_fits;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(t / m);
+        const int64_t i = t - (int64_t)f * m;
+        int64_t row;
+        if (rows_explicit) row = rows_explicit[t];
+        else row = (int64_t)(dpr_rng_draw(seed, DPR_RNG_BOOT, fit0 + (uint32_t)f, (uint32_t)i, 0).w[0] % (uint64_t)n);
+        float* o = out + (int64_t)f * fit_stride + i;
+        for (int j = 0; j < d; ++j) o[(int64_t)j * ld_out] = x[(int64_t)j * ld + row];
+    }
+}
+__global__ void bootstrap_rows_kernel(int64_t n, uint32_t boot_n, uint64_t seed, uint32_t fit, int64_t* rows) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < boot_n; i += gridDim.x * blockDim.x)
+        rows[i] = (int64_t)(dpr_rng_draw(seed, DPR_RNG_BOOT, fit, i, 0).w[0] % (uint64_t)n);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k-means++ seeding: initialize_mu + element_from_vector (src/Clusterer.cpp:123-176), batched over fits.
+// Round c (c = 1..k-1):  seed_dist   w_i = min(w_i, ||(-x_i) + mu_{c-1}||^2) in fp64, same operation
+//                                    order as the reference (weights are bit-identical), + block sums
+//                        seed_pick   x = u * total, first i whose running sum exceeds x (upper_bound of
+//                                    the cumulative map, :139-140; zero weights are skipped, :130)
+// ---------------------------------------------------------------------------------------------------
+__global__ void seed_first_kernel(SeedFit* fits, int d, uint64_t seed) {
+    SeedFit f = fits[blockIdx.x];
+    const int64_t row = (int64_t)(dpr_rng_draw(seed, DPR_RNG_SEED, f.fit_id, 0, 0).w[0] % (uint64_t)f.n);
+    for (int j = threadIdx.x; j < d; j += blockDim.x) f.mu[j] = (double)f.x[(int64_t)j * f.ld + row];
+    if (threadIdx.x == 0 && f.rows) f.rows[0] = row;
+}
+
+__global__ void seed_dist_kernel(const SeedFit* fits, int d, int c /* centre just chosen: c-1 >= 0 */, int first) {
+    extern __shared__ double s_mu[];
+    const SeedFit f = fits[blockIdx.y];
+    const int nb = (int)((f.n + kSeedBlock - 1) / kSeedBlock);
+    for (int j = threadIdx.x; j < d; j += blockDim.x) s_mu[j] = f.mu[(size_t)(c - 1) * d + j];
+    __syncthreads();
+    __shared__ double s_red[kSeedBlock / 32];
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        const int64_t i = (int64_t)b * kSeedBlock + threadIdx.x;
+        double w = 0.0;
+        if (i < f.n) {
+            double s = 0.0;
+            for (int j = 0; j < d; ++j) {
+                const double diff = __dadd_rn(-(double)f.x[(int64_t)j * f.ld + i], s_mu[j]);
+                s = __dadd_rn(s, __dmul_rn(diff, diff));
+            }
+            if (!first) {
+                const double old = f.w[i];
+                if (!(s < old)) s = old;   // if (temp_dists(j) < dists(j)) dists(j) = temp_dists(j)   (:167-169)
+            }
+            f.w[i] = s;
+            w = s > 0 ? s : 0.0;
+        }
+        // deterministic block sum
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = w;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int q = 0; q < kSeedBlock / 32; ++q) t += s_red[q];
+            f.block_sums[b] = t;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void seed_pick_kernel(SeedFit* fits, int d, int c, uint64_t seed) {
+    SeedFit f = fits[blockIdx.x];
+    const int nb = (int)((f.n + kSeedBlock - 1) / kSeedBlock);
+    __shared__ double s_total, s_before;
+    __shared__ int s_block;
+    __shared__ long long s_row;
+    if (threadIdx.x == 0) {
+        double total = 0.0;
+        for (int b = 0; b < nb; ++b) total += f.block_sums[b];
+        const double u = dpr_rng_unit(dpr_rng_draw(seed, DPR_RNG_SEED, f.fit_id, (uint32_t)c, 0).w[0]);
+        const double x = u * total;
+        double cum = 0.0;
+        int blk = -1;
+        double before = 0.0;
+        for (int b = 0; b < nb; ++b) {
+            const double nxt = cum + f.block_sums[b];
+            if (nxt > x && f.block_sums[b] > 0) { blk = b; before = cum; break; }
+            cum = nxt;
+        }
+        long long row = 0;
+        if (blk >= 0) {
+            double run = before;
+            const int64_t i0 = (int64_t)blk * kSeedBlock, i1 = min(f.n, i0 + (int64_t)kSeedBlock);
+            long long last_pos = -1;
+            row = -1;
+            for (int64_t i = i0; i < i1; ++i) {
+                const double w = f.w[i];
+                if (w > 0) {
+                    run += w;
+                    last_pos = i;
+                    if (run > x) { row = i; break; }
+                }
+            }
+            if (row < 0) row = last_pos < 0 ? i0 : last_pos;  // rounding of the block sums: take the block's last positive weight
+        }
+        s_row = row;
+        if (f.rows) f.rows[c] = row;
+    }
+    __syncthreads();
+    const long long row = s_row;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) f.mu[(size_t)c * d + j] = (double)f.x[(int64_t)j * f.ld + row];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cluster_norm (src/Clusterer.cpp:198-211): sum_i ||x_i - mu_{l_i}||^2  (+ reg * sum(mu), added by the host)
+// ---------------------------------------------------------------------------------------------------
+__global__ void ssq_kernel(const float* __restrict__ x, int64_t ld, int64_t n, int d, const double* __restrict__ mu, int k,
+                           const int32_t* __restrict__ labels, double* __restrict__ block_out) {
+    extern __shared__ double s_mu[];
+    for (int e = threadIdx.x; e < k * d; e += blockDim.x) s_mu[e] = mu[e];
+    __syncthreads();
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double* m = s_mu + (size_t)labels[i] * d;
+        double s = 0.0;
+        for (int j = 0; j < d; ++j) {
+            const double diff = (double)x[(int64_t)j * ld + i] - m[j];
+            s += diff * diff;
+        }
+        acc += s;
+    }
+    __shared__ double s_red[32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += s_red[q];
+        block_out[blockIdx.x] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// adjusted Rand index.  Exact: contingency table (warp-aggregated shared-memory histogram) -> the value the
+// reference's 10 000-pair Monte-Carlo estimate converges to (src/Clusterer.cpp:267-305).  MC: the estimate
+// itself with Philox pairs.  Labels in [0, k]  (tables are (k+1) wide, SURVEY A-9).
+// ---------------------------------------------------------------------------------------------------
+__global__ void contingency_kernel(const AriPair* pairs, int kk /* k+1 */, unsigned long long* tables, int32_t* bad) {
+    extern __shared__ unsigned int s_tab[];
+    const AriPair pr = pairs[blockIdx.y];
+    const int cells = kk * kk;
+    for (int e = threadIdx.x; e < cells; e += blockDim.x) s_tab[e] = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t per_block = ((pr.n + gridDim.x - 1) / gridDim.x + 31) & ~(int64_t)31;
+    const int64_t i0 = blockIdx.x * per_block, i1 = min(pr.n, i0 + per_block);
+    for (int64_t base = i0 + (threadIdx.x & ~31); base < i1; base += blockDim.x) {
+        const int64_t i = base + lane;
+        int key = -1;
+        if (i < i1) {
+            const int a = pr.a[i], b = pr.b[i];
+            if (a < 0 || b < 0 || a >= kk || b >= kk) *bad = 1;
+            else key = a * kk + b;
+        }
+        const unsigned m = __match_any_sync(0xffffffffu, key);
+        if (key >= 0 && lane == __ffs(m) - 1) atomicAdd(&s_tab[key], (unsigned)__popc(m));
+    }
+    __syncthreads();
+    unsigned long long* out = tables + (size_t)blockIdx.y * cells;
+    for (int e = threadIdx.x; e < cells; e += blockDim.x)
+        if (s_tab[e]) atomicAdd(&out[e], (unsigned long long)s_tab[e]);
+}
+
+// same value from a table that is too wide for shared memory (rare: k > ~230)
+__global__ void contingency_global_kernel(const AriPair* pairs, int kk, unsigned long long* tables, int32_t* bad) {
+    const AriPair pr = pairs[blockIdx.y];
+    unsigned long long* out = tables + (size_t)blockIdx.y * kk * kk;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < pr.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int a = pr.a[i], b = pr.b[i];
+        if (a < 0 || b < 0 || a >= kk || b >= kk) *bad = 1;
+        else atomicAdd(&out[(size_t)a * kk + b], 1ULL);
+    }
+}
+
+__global__ void ari_from_tables_kernel(const AriPair* pairs, int kk, const unsigned long long* tables, double* out) {
+    const int p = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const unsigned long long* t = tables + (size_t)p * kk * kk;
+    const double N = (double)pairs[p].n, denom = N * (N - 1.0);
+    double same12 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int a = 0; a < kk; ++a) {
+        unsigned long long r = 0;
+        for (int b = 0; b < kk; ++b) {
+            const unsigned long long v = t[(size_t)a * kk + b];
+            r += v;
+            same12 += (double)v * (double)(v ? v - 1 : 0);
+        }
+        s1 += (double)r * (double)(r ? r - 1 : 0);
+    }
+    for (int b = 0; b < kk; ++b) {
+        unsigned long long c = 0;
+        for (int a = 0; a < kk; ++a) c += t[(size_t)a * kk + b];
+        s2 += (double)c * (double)(c ? c - 1 : 0);
+    }
+    const double A = s1 / denom, B = s2 / denom, both = same12 / denom;
+    const double ri = both + (1.0 - A - B + both);
+    const double e = A * B + (1.0 - A) * (1.0 - B);
+    out[p] = (ri - e) / (1.0 - e);
+}
+
+// Monte-Carlo estimate: pair `num` is (w0 % n, w1 % n) of Philox(seed, PAIR, pair_id, num, attempt), redrawn
+// while i == j (:291-295); `stab` counts agreeing pairs (:296-300).
+__global__ void ari_mc_count_kernel(const AriPair* pairs, uint64_t seed, unsigned int* stab, int32_t* bad, int kk) {
+    const AriPair pr = pairs[blockIdx.y];
+    const uint32_t num = blockIdx.x * blockDim.x + threadIdx.x;
+    int agree = 0;
+    if (num < 10000u) {
+        uint64_t i = 0, j = 0;
+        uint32_t attempt = 0;
+        while (i == j) {
+            const dpr_u32x4 w = dpr_rng_draw(seed, DPR_RNG_PAIR, pr.pair_id, num, attempt++);
+            i = w.w[0] % (uint64_t)pr.n;
+            j = w.w[1] % (uint64_t)pr.n;
+        }
+        const int a1 = pr.a[i], a2 = pr.a[j], b1 = pr.b[i], b2 = pr.b[j];
+        if (a1 < 0 || a2 < 0 || b1 < 0 || b2 < 0 || a1 >= kk || a2 >= kk || b1 >= kk || b2 >= kk) *bad = 1;
+        agree = ((a1 == a2) && (b1 == b2)) || ((a1 != a2) && (b1 != b2));
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, agree);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&stab[blockIdx.y], (unsigned)__popc(m));
+}
+__global__ void ari_mc_final_kernel(const AriPair* pairs, int kk, const unsigned long long* tables, const unsigned int* stab, double* out) {
+    const int p = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const unsigned long long* t = tables + (size_t)p * kk * kk;
+    const double size = (double)pairs[p].n;
+    double a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+    for (int c = 0; c < kk; ++c) {
+        unsigned long long r = 0, q = 0;
+        for (int b = 0; b < kk; ++b) { r += t[(size_t)c * kk + b]; q += t[(size_t)b * kk + c]; }
+        const double p1 = (double)r / size, p2 = (double)q / size;
+        a1 += p1 * (p1 - 1.0 / size) * (size / (size - 1));
+        a2 += p2 * (p2 - 1.0 / size) * (size / (size - 1));
+        b1 += p1 * (1 - (p1 - 1.0 / size) * (size / (size - 1)));
+        b2 += p2 * (1 - (p2 - 1.0 / size) * (size / (size - 1)));
+    }
+    const double f = a1 * a2 + b1 * b2;
+    out[p] = (((double)stab[p] / 10000.0) - f) / (1 - f);
+}
+
+// n_used_clusters (src/Clusterer.cpp:323-332): distinct labels
+__global__ void label_presence_kernel(const int32_t* labels, int64_t n, int kk, int32_t* present, int32_t* bad) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = labels[i];
+        if (l < 0 || l >= kk) *bad = 1;
+        else if (!present[l]) present[l] = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// synthetic cells (bench): group g = Philox % G, x = centre[g][j] + N(0,1)  (generateSparseData shape,
+// R/simulateData.R:47-80, generalised), then / global sd (depecheLogCenterSd.R:102-106) by scale_kernel.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+    const float u1 = ((float)a + 1.0f) * 2.3283064e-10f, u2 = (float)b * 2.3283064e-10f;
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincosf(6.2831853f * u2, &s, &c);
+    return make_float2(r * c, r * s);
+}
+__global__ void synth_kernel(float* x, int64_t ld, int64_t n, int d, const float* __restrict__ centres, int groups, uint64_t seed,
+                             double* sum_out, double* sumsq_out) {
+    double s = 0.0, ss = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(dpr_rng_draw(seed, 11, (uint32_t)i, (uint32_t)(i >> 32), 0).w[0] % (uint32_t)groups);
+        for (int j0 = 0; j0 < d; j0 += 4) {
+            const dpr_u32x4 w = dpr_rng_draw(seed, 12, (uint32_t)i, (uint32_t)(i >> 32), (uint32_t)j0);
+            const float2 n0 = box_muller(w.w[0], w.w[1]), n1 = box_muller(w.w[2], w.w[3]);
+            const float z[4] = {n0.x, n0.y, n1.x, n1.y};
+            for (int q = 0; q < 4 && j0 + q < d; ++q) {
+                const float v = centres[g * d + j0 + q] + z[q];
+                x[(int64_t)(j0 + q) * ld + i] = v;
+                s += v;
+                ss += (double)v * v;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(sum_out, s);
+        atomicAdd(sumsq_out, ss);
+    }
+}
+__global__ void scale_kernel(float* x, int64_t ld, int64_t n, int d, float inv_sd) {
+    const int64_t total = n * d;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = t / n, i = t - j * n;
+        x[j * ld + i] *= inv_sd;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------
+static inline int blocks_for(int64_t n, int per = 256, int cap = 148 * 16) {
+    int64_t b = (n + per - 1) / per;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+int launch_f64_to_cols(const double* src, int64_t e0, int64_t count, int64_t n, int64_t ld, float* dst, cudaStream_t st) {
+    f64_to_f32_cols_kernel<<<blocks_for(count), 256, 0, st>>>(src, e0, count, n, ld, dst);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_f32_to_cols(const float* src, int64_t e0, int64_t count, int64_t n, int64_t ld, float* dst, cudaStream_t st) {
+    f32_to_f32_cols_kernel<<<blocks_for(count), 256, 0, st>>>(src, e0, count, n, ld, dst);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_cols_to_f64(const float* x, int64_t ld, int64_t row0, int64_t rows, int d, double* out, cudaStream_t st) {
+    cols_to_f64_kernel<<<blocks_for(rows * d), 256, 0, st>>>(x, ld, row0, rows, d, out);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_gather(const float* x, int64_t ld, int64_t n, int d, const int64_t* rows, uint64_t seed, uint32_t fit0, int64_t m,
+                  int64_t ld_out, float* out, int n_fits, int64_t fit_stride, cudaStream_t st) {
+    gather_rows_kernel<<<blocks_for(m * n_fits), 256, 0, st>>>(x, ld, n, d, rows, seed, fit0, m, ld_out, out, n_fits, fit_stride);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_bootstrap_rows(int64_t n, uint32_t boot_n, uint64_t seed, uint32_t fit, int64_t* rows, cudaStream_t st) {
+    bootstrap_rows_kernel<<<blocks_for(boot_n), 256, 0, st>>>(n, boot_n, seed, fit, rows);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_seeding(SeedFit* d_fits, int n_fits, int64_t n_max, int d, int k, uint64_t seed, cudaStream_t st) {
+    seed_first_kernel<<<n_fits, 64, 0, st>>>(d_fits, d, seed);
+    count_launch();
+    const int nb = (int)((n_max + kSeedBlock - 1) / kSeedBlock);
+    const int gx = std::max(1, std::min(nb, (148 * 8 + n_fits - 1) / n_fits));
+    for (int c = 1; c < k; ++c) {
+        seed_dist_kernel<<<dim3(gx, n_fits), kSeedBlock, sizeof(double) * d, st>>>(d_fits, d, c, c == 1);
+        seed_pick_kernel<<<n_fits, 64, 0, st>>>(d_fits, d, c, seed);
+        count_launch(2);
+    }
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_ssq(const float* x, int64_t ld, int64_t n, int d, const double* mu, int k, const int32_t* labels, double* block_out,
+               int blocks, cudaStream_t st) {
+    const size_t shm = sizeof(double) * k * d;
+    if (shm > 200 * 1024) return fail(DPR_ERR_INVALID, "cluster_norm: k * d too large for the shared-memory centre table");
+    static size_t configured = 48 * 1024;
+    if (shm > configured) {
+        DPR_CUDA(cudaFuncSetAttribute(ssq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    ssq_kernel<<<blocks, 256, shm, st>>>(x, ld, n, d, mu, k, labels, block_out);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_ari(const AriPair* d_pairs, int n_pairs, int64_t n_max, int kk, int mode, uint64_t seed, unsigned long long* d_tables,
+               unsigned int* d_stab, int32_t* d_bad, double* d_out, cudaStream_t st) {
+    const size_t shm = sizeof(unsigned int) * kk * kk;
+    const int gx = std::max(1, std::min((int)((n_max + 8191) / 8192), std::max(1, 148 * 4 / n_pairs)));
+    if (shm <= 160 * 1024) {
+        static size_t configured = 0;
+        if (shm > 48 * 1024 && shm > configured) {
+            DPR_CUDA(cudaFuncSetAttribute(contingency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            configured = 160 * 1024;
+        }
+        contingency_kernel<<<dim3(gx, n_pairs), 256, shm, st>>>(d_pairs, kk, d_tables, d_bad);
+    } else {
+        contingency_global_kernel<<<dim3(gx, n_pairs), 256, 0, st>>>(d_pairs, kk, d_tables, d_bad);
+    }
+    count_launch();
+    if (mode == DPR_ARI_MONTE_CARLO) {
+        ari_mc_count_kernel<<<dim3((10000 + 255) / 256, n_pairs), 256, 0, st>>>(d_pairs, seed, d_stab, d_bad, kk);
+        ari_mc_final_kernel<<<n_pairs, 32, 0, st>>>(d_pairs, kk, d_tables, d_stab, d_out);
+        count_launch(2);
+    } else {
+        ari_from_tables_kernel<<<n_pairs, 32, 0, st>>>(d_pairs, kk, d_tables, d_out);
+        count_launch();
+    }
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_label_presence(const int32_t* labels, int64_t n, int kk, int32_t* present, int32_t* bad, cudaStream_t st) {
+    label_presence_kernel<<<blocks_for(n), 256, 0, st>>>(labels, n, kk, present, bad);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_synth(float* x, int64_t ld, int64_t n, int d, const float* centres, int groups, uint64_t seed, double* sum, double* sumsq,
+                 cudaStream_t st) {
+    synth_kernel<<<blocks_for(n), 256, 0, st>>>(x, ld, n, d, centres, groups, seed, sum, sumsq);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_scale(float* x, int64_t ld, int64_t n, int d, float inv_sd, cudaStream_t st) {
+    scale_kernel<<<blocks_for(n * d), 256, 0, st>>>(x, ld, n, d, inv_sd);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+
+}  // namespace dpr

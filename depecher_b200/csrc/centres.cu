@@ -1,0 +1,265 @@
+// centres.cu — everything that happens to the K x D centres between two passes over the cells:
+//   reduce_partials_kernel   fixed-order sum of the per-warp partial tables of fused_pass_kernel
+//   finalize_kernel          convergence rule + soft-threshold update + fp32 chunk table
+//   prepare_centres_kernel   chunk table for centres supplied by the caller (allocate_points, scoring)
+//
+// finalize restates the tail of Clusterer::reevaluate_centers (/root/reference/src/Clusterer.cpp:103-107,
+//   mu = min((S+reg/2)/n, max((S-reg/2)/n, 0)) with the x86-64 packet NaN semantics, so an empty cluster
+//   becomes an exact zero row) and the loop control of Clusterer::find_centers (:244-252: stop when the
+//   labels did not change AND i > 20; penalty ramp reg*((float)i/(float)20) capped at reg).
+#include "centres.cuh"
+
+namespace dpr {
+
+// Build header / chunk table / slot map of one problem from its fp64 centres.  One CTA; k, d are small.
+// Active rows: no_zero -> rows with any non-zero coefficient (isZero(0), Clusterer.cpp:41-45; NaN counts as
+// non-zero); otherwise every row, except that all-zero rows after the first are dropped: they are identical,
+// and the reference's first-minimum rule (minCoeff, :64) can only ever pick the first of them.
+__device__ void build_centre_table(const Problem& pr, int no_zero, int table_cap) {
+    __shared__ int s_act[kMaxKC * kMaxChunks];
+    __shared__ int s_nact, s_ref_active, s_bad;
+    const int k = pr.k, d = pr.d;
+    CentreHeader* h = pr.hdr;
+    if (threadIdx.x == 0) {
+        int n = 0, ref_active = 0, bad = 0, seen_zero = 0;
+        for (int c = 0; c < k; ++c) {
+            bool zero = true;
+            for (int t = 0; t < d; ++t) {
+                const double v = pr.mu[(size_t)c * d + t];
+                if (!(fabs(v) <= 0.0)) zero = false;
+                if (!isfinite(v)) bad = 1;
+            }
+            bool use;
+            if (no_zero) {
+                use = !zero;
+                ref_active += use;
+            } else {
+                ref_active += 1;
+                use = !(zero && seen_zero);
+                if (zero) seen_zero = 1;
+            }
+            if (use && n < kMaxKC * kMaxChunks) s_act[n++] = c;
+        }
+        s_nact = n;
+        s_ref_active = ref_active;
+        s_bad = bad;
+        const bool trivial = ref_active < 2 || n < 2;
+        const int n_chunks = trivial ? 0 : (n + kMaxKC - 1) / kMaxKC;
+        h->k = k;
+        h->k_act = n;
+        h->n_chunks = n_chunks;
+        h->trivial = trivial;
+        h->force_exact = bad;
+        int off = 0, base = 0;
+        for (int q = 0; q < n_chunks; ++q) {
+            const int real = n / n_chunks + (q < n % n_chunks ? 1 : 0);
+            const int kc = (real + 1) & ~1;
+            const int kcp = (kc + 3) & ~3;
+            h->chunk_kc[q] = kc;
+            h->chunk_off[q] = off;
+            h->chunk_base[q] = base;
+            off += kcp * (d + 1);
+            base += kc;
+        }
+        h->n_slots = base;
+        h->table_floats = off;
+        if (off > table_cap) {  // cannot happen for shapes admitted by plan_pass; keep the kernel safe anyway
+            h->trivial = 1;
+            h->n_chunks = 0;
+        }
+    }
+    __syncthreads();
+    const int n = s_nact, n_chunks = h->n_chunks;
+    float ccmax = 0.f;
+    int real_before = 0;
+    for (int q = 0; q < n_chunks; ++q) {
+        const int real = n / n_chunks + (q < n % n_chunks ? 1 : 0);
+        const int kc = h->chunk_kc[q], kcp = (kc + 3) & ~3;
+        float* cc = pr.table + h->chunk_off[q];
+        float* w = cc + kcp;
+        for (int t = threadIdx.x; t < kcp; t += blockDim.x) {
+            float v = 3.0e38f;
+            int row = -1;
+            if (t < real) {
+                row = s_act[real_before + t];
+                double s = 0.0;
+                for (int j = 0; j < d; ++j) {
+                    const double c = pr.mu[(size_t)row * d + j];
+                    s += c * c;
+                }
+                v = (float)s;
+            }
+            cc[t] = v;
+            if (t < kc) pr.orig[h->chunk_base[q] + t] = row;
+        }
+        for (int e = threadIdx.x; e < kcp * d; e += blockDim.x) {
+            const int j = e / kcp, t = e % kcp;
+            float v = 0.f;
+            if (t < real) v = (float)(-2.0 * pr.mu[(size_t)s_act[real_before + t] * d + j]);
+            w[e] = v;
+        }
+        real_before += real;
+    }
+    if (threadIdx.x == 0) {
+        for (int a = 0; a < n; ++a) {
+            double s = 0.0;
+            for (int j = 0; j < d; ++j) {
+                const double c = pr.mu[(size_t)s_act[a] * d + j];
+                s += c * c;
+            }
+            ccmax = fmaxf(ccmax, (float)s);
+        }
+        h->cc_max = ccmax * 1.0000002f;
+    }
+}
+
+__global__ void prepare_centres_kernel(Problem* problems, int table_cap) {
+    const Problem pr = problems[blockIdx.x];
+    build_centre_table(pr, pr.no_zero, table_cap);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// reduce: out[p][seg][entry] = sum over the CTAs of segment `seg` (ascending) and their warps (ascending)
+// of the partial tables that belong to problem p; the partials are zeroed on the way for the next pass.
+// entry layout per problem: [k_max*d sums][k_max counts][1 changed]
+// ---------------------------------------------------------------------------------------------------
+__global__ void reduce_partials_kernel(const Problem* problems, const int32_t* cta_tile_start, int grid_ctas, int warps, int k_max, int d,
+                                       double* part_sums, long long* part_counts, long long* part_changed, double* seg_out,
+                                       int n_seg) {
+    const int p = blockIdx.x, seg = blockIdx.y;
+    const Problem pr = problems[p];
+    const int64_t stride = (int64_t)k_max * d;
+    const int64_t entries = stride + k_max + 1;
+    double* out = seg_out + ((int64_t)p * n_seg + seg) * entries;
+    const int c0 = (int)((int64_t)grid_ctas * seg / n_seg), c1 = (int)((int64_t)grid_ctas * (seg + 1) / n_seg);
+    const int t0 = pr.first_tile, t1 = pr.first_tile + pr.n_tiles;
+    for (int64_t e = threadIdx.x; e < entries; e += blockDim.x) {
+        double acc = 0.0;
+        if (!pr.done) {
+            for (int c = c0; c < c1; ++c) {
+                if (cta_tile_start[c] >= t1 || cta_tile_start[c + 1] <= t0 || cta_tile_start[c] >= cta_tile_start[c + 1]) continue;
+                const size_t tab0 = (size_t)(c + p) * warps;
+                for (int w = 0; w < warps; ++w) {
+                    if (e < stride) {
+                        double* q = part_sums + (tab0 + w) * stride + e;
+                        acc += *q;
+                        *q = 0.0;
+                    } else if (e < stride + k_max) {
+                        long long* q = part_counts + (tab0 + w) * k_max + (e - stride);
+                        acc += (double)*q;
+                        *q = 0;
+                    } else {
+                        long long* q = part_changed + (tab0 + w);
+                        acc += (double)*q;
+                        *q = 0;
+                    }
+                }
+            }
+        }
+        out[e] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// finalize: one CTA per problem.  iter = index i of the assignment that just ran.
+// ---------------------------------------------------------------------------------------------------
+__global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_seg, int k_max, int iter, int max_iter, int table_cap,
+                                int32_t* n_active_out) {
+    const int p = blockIdx.x;
+    Problem pr = problems[p];
+    if (pr.done) return;
+    const int k = pr.k, d = pr.d;
+    const int64_t stride = (int64_t)k_max * d;
+    const int64_t entries = stride + k_max + 1;
+    const double* in = seg_in + (int64_t)p * n_seg * entries;
+    __shared__ long long s_changed;
+    // totals in fixed segment order
+    for (int64_t e = threadIdx.x; e < entries; e += blockDim.x) {
+        double acc = 0.0;
+        for (int s = 0; s < n_seg; ++s) acc += in[(int64_t)s * entries + e];
+        if (e < stride) {
+            const int c = (int)(e / d), j = (int)(e % d);
+            if (c < k) pr.sums[(size_t)c * d + j] = acc;
+        } else if (e < stride + k_max) {
+            const int c = (int)(e - stride);
+            if (c < k) pr.counts[c] = (long long)acc;
+        } else {
+            s_changed = (long long)acc;
+        }
+    }
+    __syncthreads();
+    const long long changed = s_changed;
+    const bool converged = (changed == 0 && iter > 20);
+    if (threadIdx.x == 0) {
+        problems[p].changed = changed;
+        problems[p].n_assign = iter + 1;
+    }
+    if (converged || iter + 1 >= max_iter) {
+        // Clusterer.cpp:247-249: break BEFORE the update: centres stay those of the previous iteration.
+        // (at the iteration cap the reference has just run its last update, so apply it below first)
+        if (threadIdx.x == 0) problems[p].done = 1;
+        if (converged) return;
+    }
+    // reg_i = min(reg, reg * ((float)i / (float)20))   (Clusterer.cpp:251)
+    const double ramp = pr.reg * (double)((float)iter / (float)20);
+    const double reg_i = pr.reg < ramp ? pr.reg : ramp;
+    for (int e = threadIdx.x; e < k * d; e += blockDim.x) {
+        const int c = e / d;
+        const double S = pr.sums[e];
+        const double nn = (double)pr.counts[c];
+        const double lo = (S - reg_i / 2) / nn;
+        const double hi = (S + reg_i / 2) / nn;
+        const double m0 = lo > 0.0 ? lo : 0.0;  // _mm_max_pd(lo, 0): second operand when lo is NaN
+        pr.mu[e] = hi < m0 ? hi : m0;           // _mm_min_pd(hi, m0)
+    }
+    __threadfence_block();
+    __syncthreads();
+    build_centre_table(pr, pr.no_zero, table_cap);
+    if (threadIdx.x == 0 && n_active_out && !(iter + 1 >= max_iter)) atomicAdd(n_active_out, 1);
+}
+
+// one update from given sums/counts (reevaluate_centers for explicit labels): mu only
+__global__ void soft_threshold_kernel(const double* sums, const long long* counts, int k, int d, double reg, double* mu) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < k * d; e += gridDim.x * blockDim.x) {
+        const double S = sums[e], nn = (double)counts[e / d];
+        const double lo = (S - reg / 2) / nn, hi = (S + reg / 2) / nn;
+        const double m0 = lo > 0.0 ? lo : 0.0;
+        mu[e] = hi < m0 ? hi : m0;
+    }
+}
+
+int launch_prepare_centres(Problem* d_problems, int n_problems, int table_cap, cudaStream_t st) {
+    prepare_centres_kernel<<<n_problems, 128, 0, st>>>(d_problems, table_cap);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+
+int launch_reduce_partials(const Problem* d_problems, int n_problems, const int32_t* cta_tile_start, int grid_ctas, int warps, int k_max,
+                           int d,
+                           double* part_sums, long long* part_counts, long long* part_changed, double* seg_out, int n_seg,
+                           cudaStream_t st) {
+    dim3 g(n_problems, n_seg);
+    reduce_partials_kernel<<<g, 256, 0, st>>>(d_problems, cta_tile_start, grid_ctas, warps, k_max, d, part_sums, part_counts, part_changed,
+                                              seg_out, n_seg);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+
+int launch_finalize(Problem* d_problems, int n_problems, const double* seg_in, int n_seg, int k_max, int iter, int max_iter,
+                    int table_cap, int32_t* n_active_out, cudaStream_t st) {
+    finalize_kernel<<<n_problems, 256, 0, st>>>(d_problems, seg_in, n_seg, k_max, iter, max_iter, table_cap, n_active_out);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+
+int launch_soft_threshold(const double* sums, const long long* counts, int k, int d, double reg, double* mu, cudaStream_t st) {
+    soft_threshold_kernel<<<(k * d + 255) / 256, 256, 0, st>>>(sums, counts, k, d, reg, mu);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+
+}  // namespace dpr

@@ -1,0 +1,37 @@
+// fused_pass.cuh — launch interface of the fused assignment / Lloyd pass (fused_pass.cu).
+#pragma once
+#include "common.cuh"
+
+namespace dpr {
+
+constexpr int kPassAssign = 0;  // labels only           (allocate_clusters, Clusterer.cpp:34-87)
+constexpr int kPassLloyd = 1;   // labels + sums/counts   (+ the scatter-add of reevaluate_centers, :99-102)
+constexpr int kPassSums = 2;    // sums/counts of the labels already stored (reevaluate_centers for given labels)
+
+struct PassParams {
+    const Problem* problems;
+    int32_t n_problems;
+    const int32_t* cta_tile_start;  // [grid + 1]: contiguous tile range of each CTA in the global tile order
+    int32_t mode;
+    int32_t compare_old;            // count labels that differ from the previous ones
+    int32_t k_max;                  // rows of the widest centre matrix (table strides)
+    int64_t part_stride;            // doubles per partial-sum table (k_max * d)
+    double* part_sums;              // [(grid + n_problems) * warps][k_max * d]   (Lloyd mode)
+    long long* part_counts;         // [(grid + n_problems) * warps][k_max]
+    long long* part_changed;        // [(grid + n_problems) * warps]
+    unsigned long long* recheck_count;  // diagnostics: cells decided by the fp64 path (nullable)
+    // filled from the plan
+    int32_t warps, slots_per_warp, slot_floats, off_hdr, off_table, off_orig, off_scratch, scratch_bytes, off_slots;
+};
+
+struct PassPlan {
+    int32_t warps, slots_per_warp, slot_floats, off_hdr, off_table, off_orig, off_scratch, scratch_bytes, off_slots;
+    int32_t table_floats_cap;
+    size_t smem_bytes;
+};
+
+// returns 1 and fills the plan when a d-marker slot per warp fits in shared memory, 0 otherwise
+int plan_pass(int d, int k_max, PassPlan* plan);
+int launch_fused_pass(const PassPlan& plan, PassParams P, int grid, cudaStream_t stream);
+
+}  // namespace dpr

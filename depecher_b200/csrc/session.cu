@@ -1,0 +1,172 @@
+// session.cu — see session.cuh
+#include "session.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+#include "comm.cuh"
+
+namespace dpr {
+
+Session::~Session() {
+    for (void* p : owned_) cudaFree(p);
+    if (h_n_active_) cudaFreeHost(h_n_active_);
+}
+
+template <typename T>
+int Session::alloc(T** p, size_t count, bool zero) {
+    void* q = nullptr;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    DPR_CUDA(cudaMalloc(&q, bytes));
+    owned_.push_back(q);
+    if (zero) DPR_CUDA(cudaMemsetAsync(q, 0, bytes, ctx().stream));
+    *p = reinterpret_cast<T*>(q);
+    return DPR_OK;
+}
+
+int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) {
+    DPR_TRY(ensure_ready());
+    if (specs.empty()) return fail(DPR_ERR_INVALID, "no problems");
+    d_ = d;
+    want_sums_ = want_sums;
+    k_max_ = 0;
+    for (const auto& s : specs) {
+        if (s.k < 1 || s.n < 1) return fail(DPR_ERR_INVALID, "problem with k < 1 or n < 1");
+        k_max_ = std::max(k_max_, (int)s.k);
+    }
+    if (!plan_pass(d, k_max_, &plan))
+        return fail(DPR_ERR_INVALID, "shape not supported by the sm_100a kernels: d = " + std::to_string(d) + ", k = " +
+                                         std::to_string(k_max_) + " (one 128-cell slot of d markers plus the centre table must fit in 227 KB)");
+    const int P = (int)specs.size();
+    h_problems.assign(P, Problem{});
+    // pooled per-problem storage
+    const size_t mu_sz = (size_t)k_max_ * d, tab_sz = (size_t)plan.table_floats_cap, orig_sz = (size_t)k_max_ + 2 * kMaxChunks;
+    double *mu_pool, *sums_pool;
+    long long* cnt_pool;
+    CentreHeader* hdr_pool;
+    float* tab_pool;
+    int32_t* orig_pool;
+    DPR_TRY(alloc(&mu_pool, mu_sz * P, true));
+    DPR_TRY(alloc(&sums_pool, mu_sz * P, true));
+    DPR_TRY(alloc(&cnt_pool, (size_t)k_max_ * P, true));
+    DPR_TRY(alloc(&hdr_pool, (size_t)P, true));
+    DPR_TRY(alloc(&tab_pool, tab_sz * P, true));
+    DPR_TRY(alloc(&orig_pool, orig_sz * P, true));
+    int tile = 0;
+    for (int p = 0; p < P; ++p) {
+        Problem& pr = h_problems[p];
+        const ProblemSpec& s = specs[p];
+        pr.x = s.x;
+        pr.ld = s.ld;
+        pr.n = s.n;
+        pr.d = d;
+        pr.k = s.k;
+        pr.labels = s.labels;
+        pr.mu = mu_pool + mu_sz * p;
+        pr.hdr = hdr_pool + p;
+        pr.table = tab_pool + tab_sz * p;
+        pr.orig = orig_pool + orig_sz * p;
+        pr.first_tile = tile;
+        pr.n_tiles = (int)((s.n + kSlotCells - 1) / kSlotCells);
+        tile += pr.n_tiles;
+        pr.reg = s.reg;
+        pr.no_zero = s.no_zero;
+        pr.sums = sums_pool + mu_sz * p;
+        pr.counts = cnt_pool + (size_t)k_max_ * p;
+    }
+    total_tiles_ = tile;
+    DPR_TRY(alloc(&d_problems, (size_t)P, false));
+    DPR_CUDA(cudaMemcpyAsync(d_problems, h_problems.data(), sizeof(Problem) * P, cudaMemcpyHostToDevice, ctx().stream));
+    // static partition: contiguous, equal tile counts per CTA
+    const int per_cta_min = plan.warps;  // at least one tile per warp before using another CTA
+    grid = std::min(ctx().sms, std::max(1, (total_tiles_ + per_cta_min - 1) / per_cta_min));
+    std::vector<int32_t> start(grid + 1);
+    for (int c = 0; c <= grid; ++c) start[c] = (int32_t)((int64_t)total_tiles_ * c / grid);
+    DPR_TRY(alloc(&d_cta_start_, (size_t)grid + 1, false));
+    DPR_CUDA(cudaMemcpyAsync(d_cta_start_, start.data(), sizeof(int32_t) * (grid + 1), cudaMemcpyHostToDevice, ctx().stream));
+    DPR_TRY(alloc(&d_recheck, (size_t)1, true));
+    const size_t tables = (size_t)(grid + P) * plan.warps;
+    DPR_TRY(alloc(&part_changed_, tables, true));
+    n_seg = std::min(8, grid);
+    seg_entries = (int64_t)k_max_ * d + k_max_ + 1;
+    if (want_sums) {
+        DPR_TRY(alloc(&part_sums_, tables * mu_sz, true));
+        DPR_TRY(alloc(&part_counts_, tables * k_max_, true));
+        DPR_TRY(alloc(&seg, (size_t)P * n_seg * seg_entries, true));
+        DPR_TRY(alloc(&d_n_active_, (size_t)1, true));
+        DPR_CUDA(cudaMallocHost(&h_n_active_, sizeof(int32_t)));
+    }
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));  // `start`/h_problems are stack/heap temporaries of this call
+    return DPR_OK;
+}
+
+int Session::set_centres(int p, const double* mu) {
+    DPR_CUDA(cudaMemcpyAsync(h_problems[p].mu, mu, sizeof(double) * h_problems[p].k * d_, cudaMemcpyHostToDevice, ctx().stream));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    return DPR_OK;
+}
+int Session::set_centres_device(int p, const double* mu) {
+    DPR_CUDA(cudaMemcpyAsync(h_problems[p].mu, mu, sizeof(double) * h_problems[p].k * d_, cudaMemcpyDeviceToDevice, ctx().stream));
+    return DPR_OK;
+}
+int Session::get_centres(int p, double* mu) {
+    DPR_CUDA(cudaMemcpyAsync(mu, h_problems[p].mu, sizeof(double) * h_problems[p].k * d_, cudaMemcpyDeviceToHost, ctx().stream));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    return DPR_OK;
+}
+
+int Session::prepare() { return launch_prepare_centres(d_problems, n_problems(), plan.table_floats_cap, ctx().stream); }
+
+int Session::pass(int mode, bool compare_old) {
+    if (mode != kPassAssign && !want_sums_) return fail(DPR_ERR_STATE, "session was created without sum tables");
+    PassParams P{};
+    P.problems = d_problems;
+    P.n_problems = n_problems();
+    P.cta_tile_start = d_cta_start_;
+    P.mode = mode;
+    P.compare_old = compare_old ? 1 : 0;
+    P.k_max = k_max_;
+    P.part_stride = (int64_t)k_max_ * d_;
+    P.part_sums = part_sums_;
+    P.part_counts = part_counts_;
+    P.part_changed = part_changed_;
+    P.recheck_count = d_recheck;
+    return launch_fused_pass(plan, P, grid, ctx().stream);
+}
+
+int Session::reduce_and_finalize(int iter, int max_iter) {
+    DPR_TRY(launch_reduce_partials(d_problems, n_problems(), d_cta_start_, grid, plan.warps, k_max_, d_, part_sums_, part_counts_,
+                                   part_changed_, seg, n_seg, ctx().stream));
+    if (ctx().world > 1) DPR_TRY(comm_allreduce_sum_f64(seg, (size_t)n_problems() * n_seg * seg_entries));
+    DPR_CUDA(cudaMemsetAsync(d_n_active_, 0, sizeof(int32_t), ctx().stream));
+    return launch_finalize(d_problems, n_problems(), seg, n_seg, k_max_, iter, max_iter, plan.table_floats_cap, d_n_active_, ctx().stream);
+}
+
+int Session::zero_labels() {
+    for (auto& pr : h_problems)
+        if (pr.labels) DPR_CUDA(cudaMemsetAsync(pr.labels, 0, sizeof(int32_t) * pr.n, ctx().stream));
+    return DPR_OK;
+}
+
+int Session::lloyd(int max_iter) {
+    // The convergence rule needs i > 20 (Clusterer.cpp:247): iterations 0..20 run back to back without
+    // touching the host; after that the host looks at the active-problem counter once per iteration.
+    for (int i = 0; i < max_iter; ++i) {
+        DPR_TRY(pass(kPassLloyd, true));
+        DPR_TRY(reduce_and_finalize(i, max_iter));
+        if (i > 20) {
+            DPR_CUDA(cudaMemcpyAsync(h_n_active_, d_n_active_, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx().stream));
+            DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+            if (*h_n_active_ == 0) break;
+        }
+    }
+    return DPR_OK;
+}
+
+int Session::fetch_state() {
+    DPR_CUDA(cudaMemcpyAsync(h_problems.data(), d_problems, sizeof(Problem) * h_problems.size(), cudaMemcpyDeviceToHost, ctx().stream));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    return DPR_OK;
+}
+
+}  // namespace dpr

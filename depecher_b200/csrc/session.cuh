@@ -1,0 +1,72 @@
+// session.cuh — host-side owner of everything one batch of problems needs on the device.
+//
+// A Session holds P problems (data pointer + centre set each), the partition of their tiles over the
+// persistent CTAs, the partial-sum tables and the Lloyd-loop state.  It is the B200 counterpart of one
+// `Clusterer` instance of the reference (src/Clusterer.h:43-73), batched: the reference runs one fit at a
+// time per R worker process (R/depechePenaltyOpt.R:50-54), here every concurrent fit shares each launch.
+#pragma once
+#include <vector>
+
+#include "centres.cuh"
+#include "common.cuh"
+#include "fused_pass.cuh"
+
+namespace dpr {
+
+struct ProblemSpec {
+    const float* x;
+    int64_t ld, n;
+    int32_t k;
+    double reg;
+    int32_t no_zero;
+    int32_t* labels;   // device, >= n ints (nullable: session allocates when want_labels)
+};
+
+class Session {
+public:
+    Session() = default;
+    ~Session();
+    Session(const Session&) = delete;
+    Session& operator=(const Session&) = delete;
+
+    // d is common to all problems.  want_sums: allocate the Lloyd partial tables.
+    int init(const std::vector<ProblemSpec>& specs, int d, bool want_sums);
+    int set_centres(int p, const double* mu_rowmajor_host);        // H2D of one centre matrix
+    int set_centres_device(int p, const double* mu_rowmajor_dev);   // D2D
+    int get_centres(int p, double* mu_rowmajor_host);
+    int prepare();                                                   // chunk tables for the current centres
+    int pass(int mode, bool compare_old);                            // one fused pass over every problem
+    int reduce_and_finalize(int iter, int max_iter);                 // sums -> centres (+ convergence)
+    // find_centers loop (Clusterer.cpp:244-252) for all problems; labels must be zeroed by the caller
+    int lloyd(int max_iter);
+    int fetch_state();                                               // d_problems -> h_problems (synchronises)
+    int zero_labels();
+
+    int n_problems() const { return (int)h_problems.size(); }
+    int d() const { return d_; }
+    int k_max() const { return k_max_; }
+    std::vector<Problem> h_problems;
+    Problem* d_problems = nullptr;
+    unsigned long long* d_recheck = nullptr;   // cells decided by the fp64 path (diagnostics)
+    int grid = 0;
+    PassPlan plan{};
+
+    // raw device buffers (exposed for the multi-GPU allreduce between reduce and finalize)
+    double* seg = nullptr;
+    int n_seg = 1;
+    int64_t seg_entries = 0;   // per problem per segment
+
+private:
+    int d_ = 0, k_max_ = 0, total_tiles_ = 0;
+    bool want_sums_ = false;
+    std::vector<void*> owned_;
+    int32_t* d_cta_start_ = nullptr;
+    double* part_sums_ = nullptr;
+    long long* part_counts_ = nullptr;
+    long long* part_changed_ = nullptr;
+    int32_t* d_n_active_ = nullptr;
+    int32_t* h_n_active_ = nullptr;  // pinned
+    template <typename T> int alloc(T** p, size_t count, bool zero);
+};
+
+}  // namespace dpr

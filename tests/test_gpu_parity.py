@@ -1,0 +1,217 @@
+"""GPU parity: the CUDA library through its C ABI against the CPU oracle on the same seeded inputs.
+
+Bars: labels bit-exact on fp32-representable inputs; on arbitrary doubles only cells whose
+oracle top-2 margin is below 1e-6 may differ; centres within 1e-5 relative (abs floor 1e-5 * data sd — in
+practice they agree to ~1e-12 because the sums are accumulated in fp64); identical iteration counts.
+"""
+import numpy as np
+import pytest
+
+from oracle.oracle import RNG_PHILOX
+
+pytestmark = pytest.mark.gpu
+
+
+def blobs(rng, n, d, g, amp=3.0, f32=True):
+    cent = rng.choice([-amp, 0.0, amp], size=(g, d))
+    X = cent[rng.integers(0, g, n)] + rng.normal(size=(n, d))
+    X /= X.std()
+    return X.astype(np.float32).astype(np.float64) if f32 else X
+
+
+def centres_close(a, b, sd=1.0):
+    assert a.shape == b.shape
+    assert np.array_equal(a == 0, b == 0), "zero pattern differs"
+    np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-5 * sd)
+
+
+# ---------------------------------------------------------------------------------------------- allocate_points
+def test_allocate_points_golden(engine, ref_vectors):
+    v = ref_vectors
+    assert np.array_equal(engine.allocate_points(v["ap_X"], v["ap_mu"], False)["i"], v["ap_idx"])
+    assert np.array_equal(engine.allocate_points(v["ap_X"], v["ap_mu"], True)["i"], v["ap_idx_nz"])
+    assert np.array_equal(engine.allocate_points(v["ap_X"], v["ap_mu_one"], True)["i"], v["ap_idx_one_nz"])
+    assert np.array_equal(engine.allocate_points(v["ap_X"], v["ap_mu_one"], False)["i"], v["ap_idx_one"])
+
+
+@pytest.mark.parametrize("n,d,k", [(1, 3, 2), (127, 5, 2), (128, 14, 30), (129, 15, 20), (5000, 40, 30), (3333, 50, 30),
+                                   (2000, 7, 33), (1500, 20, 90), (700, 100, 12), (64, 150, 2)])
+def test_allocate_points_shapes(engine, oracle, n, d, k):
+    rng = np.random.default_rng(n * 1000 + d * 10 + k)
+    X = blobs(rng, n, d, min(k, 8))
+    mu = blobs(rng, k, d, min(k, 8))
+    if k > 4:
+        mu[[1, k - 2]] = 0.0
+    for nz in (False, True):
+        got = engine.allocate_points(X, mu, nz)["i"]
+        want = oracle.allocate_points(X, mu, nz)
+        assert np.array_equal(got, want), f"{(got != want).sum()} of {n} labels differ (no_zero={nz})"
+
+
+def test_allocate_points_exact_ties_and_duplicates(engine, oracle):
+    """identical centres and cells equidistant from two centres: first minimum wins (minCoeff, Clusterer.cpp:64)"""
+    rng = np.random.default_rng(5)
+    d = 6
+    mu = rng.integers(-3, 4, size=(8, d)).astype(np.float64)
+    mu[5] = mu[2]                       # duplicate row: the lower index must win
+    X = np.concatenate([mu[rng.integers(0, 8, 500)],                     # cells on centres
+                        (mu[0] + mu[1])[None, :].repeat(50, 0) / 2.0,    # exactly between two centres
+                        rng.integers(-3, 4, size=(1000, d)).astype(np.float64)])
+    got = engine.allocate_points(X, mu, False)["i"]
+    assert np.array_equal(got, oracle.allocate_points(X, mu, False))
+    assert not (got == 5).any()
+
+
+def test_allocate_points_arbitrary_doubles(engine, oracle):
+    """inputs that are NOT fp32-representable: only documented near-ties (oracle margin < 1e-6) may differ"""
+    rng = np.random.default_rng(11)
+    X = blobs(rng, 20000, 15, 12, f32=False)
+    mu = blobs(rng, 20, 15, 12, f32=False)
+    got = engine.allocate_points(X, mu, False)["i"]
+    want = oracle.allocate_points(X, mu, False)
+    diff = np.flatnonzero(got != want)
+    margin = oracle.assignment_margin(X, mu, False)
+    assert (margin[diff] < 1e-6).all(), f"{len(diff)} differ, worst margin {margin[diff].max() if len(diff) else 0}"
+
+
+def test_allocate_points_nan_and_errors(engine, oracle):
+    import depecher_b200 as dp
+    rng = np.random.default_rng(2)
+    X = blobs(rng, 300, 4, 3)
+    mu = blobs(rng, 5, 4, 3)
+    X[7, 2] = np.nan
+    assert np.array_equal(engine.allocate_points(X, mu, False)["i"], oracle.allocate_points(X, mu, False))
+    with pytest.raises(dp.DepecherError):
+        engine.allocate_points(X, np.zeros((0, 4)), False)
+
+
+# ---------------------------------------------------------------------------------------------- centre update
+@pytest.mark.parametrize("n,d,k,reg", [(3000, 14, 7, 0.0), (3000, 14, 7, 37.5), (10000, 40, 30, 120.0), (999, 33, 90, 5.0)])
+def test_reevaluate_centers(engine, oracle, n, d, k, reg):
+    rng = np.random.default_rng(n + d + k)
+    X = blobs(rng, n, d, 6)
+    idx = rng.integers(0, k, n).astype(np.int32)
+    idx[idx == 3] = 4   # an empty cluster: exact zero row (SURVEY A-6/A-7)
+    got, cnt = engine.reevaluate_centers(X, idx, k, reg)
+    want, wcnt = oracle.reevaluate_centers(X, idx, k, reg)
+    assert np.array_equal(cnt, wcnt)
+    assert (got[3] == 0).all()
+    centres_close(got, want)
+    np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-13)
+
+
+def test_golden_reevaluate(engine, ref_vectors):
+    v = ref_vectors
+    got0, _ = engine.reevaluate_centers(v["ap_X"], v["rc_idx"], 7, 0.0)
+    got1, _ = engine.reevaluate_centers(v["ap_X"], v["rc_idx"], 7, 37.5)
+    centres_close(got0, v["rc_mu_reg0"])
+    centres_close(got1, v["rc_mu_reg"])
+
+
+# ---------------------------------------------------------------------------------------------- Lloyd loop
+@pytest.mark.parametrize("n,d,k,pen", [(3000, 14, 10, 0.0), (3000, 14, 10, 8.0), (10000, 14, 30, 16.0), (5000, 40, 30, 4.0),
+                                       (500, 100, 90, 8.0)])
+def test_find_centers_from_same_trajectory(engine, oracle, n, d, k, pen):
+    """identical initial centres -> identical labels, iteration count and zero pattern; centres to 1e-5"""
+    rng = np.random.default_rng(n + 7 * d + k)
+    X = blobs(rng, n, d, 6, amp=2.5)
+    reg = pen * n * np.sqrt(d) / 1450.0          # R/depecheAllData.R:15-16
+    oracle.set_rng(RNG_PHILOX, 31)
+    mu0, _ = oracle.initialize_mu(X, k, fit_id=2)
+    want = oracle.find_centers_from(X, mu0, reg, True)
+    got = engine.find_centers_from(X, mu0, reg, True)
+    assert got["n_iter"] == want["n_iter"]
+    assert np.array_equal(got["i"], want["i"])
+    centres_close(got["c"], want["c"])
+    assert abs(got["n"] - want["n"]) <= 1e-9 * abs(want["n"])
+
+
+def test_kmeanspp_seeding_matches_oracle(engine, oracle):
+    rng = np.random.default_rng(3)
+    X = blobs(rng, 7000, 14, 8)
+    oracle.set_rng(RNG_PHILOX, 77)
+    for fit in (0, 5):
+        want_mu, want_rows = oracle.initialize_mu(X, 30, fit_id=fit)
+        got_mu, got_rows = engine.initialize_mu(X, 30, seed=77, fit_id=fit)
+        assert np.array_equal(got_rows, want_rows)
+        assert np.array_equal(got_mu, want_mu)
+
+
+def test_bootstrap_rows_match_oracle(engine, oracle):
+    oracle.set_rng(RNG_PHILOX, 123)
+    assert np.array_equal(engine.bootstrap_rows(20000, 10000, seed=123, fit_id=9), oracle.bootstrap_rows(20000, 10000, 9))
+
+
+def test_sparse_k_means_matches_oracle(engine, oracle):
+    rng = np.random.default_rng(8)
+    X = blobs(rng, 4000, 15, 7, amp=2.5)
+    for pen in (0.0, 4.0, 22.6):
+        reg = pen * 4000 * np.sqrt(15) / 1450.0
+        oracle.set_rng(RNG_PHILOX, 5)
+        want = oracle.sparse_k_means(X, 20, reg, True, fit_id=0)
+        got = engine.sparse_k_means(X, 20, reg, True, seed_off_set=5)
+        assert got["n_iter"] == want["n_iter"]
+        assert np.array_equal(got["i"], want["i"])
+        centres_close(got["c"], want["c"])
+        assert abs(got["n"] - want["n"]) <= 1e-9 * abs(want["n"])
+
+
+# ---------------------------------------------------------------------------------------------- ARI
+def test_rand_index(engine, oracle, ref_vectors):
+    import depecher_b200 as dp
+    v = ref_vectors
+    a, b = v["ri_a"], v["ri_b"]
+    exact = engine.rand_index(a, b, 6)
+    assert abs(exact - oracle.rand_index_exact(a, b, 6)) < 1e-12
+    # the reference's Monte-Carlo value (golden, libc stream) scatters around it: 4 sigma of 10 000 Bernoulli pairs
+    assert abs(exact - float(v["ri_val"])) < 0.03
+    assert engine.rand_index(a + 1, a + 1, 100) == 1.0           # test_dAllocate.R:20
+    assert np.isnan(engine.rand_index(np.zeros(40, int), np.zeros(40, int), 3))
+    engine.set_ari_mode(dp.ARI_MONTE_CARLO)
+    try:
+        oracle.set_rng(RNG_PHILOX, 0)
+        mc = engine.rand_index(a, b, 6)
+        assert abs(mc - oracle.rand_index(a, b, 6, pair_id=0)) < 1e-9   # same Philox pairs -> same estimate
+        assert engine.rand_index(a, a, 6) == 1.0
+    finally:
+        engine.set_ari_mode(dp.ARI_EXACT)
+    with pytest.raises(dp.DepecherError):
+        engine.rand_index(a + 10, b, 6)
+
+
+def test_n_used_and_cluster_norm(engine, oracle, ref_vectors):
+    v = ref_vectors
+    assert engine.n_used_clusters(v["rc_idx"], 7) == int(v["nu_val"])
+    got = engine.cluster_norm(v["ap_X"], v["rc_mu_reg"], v["rc_idx"], 37.5)
+    assert abs(got - float(v["cn_val"])) <= 1e-10 * abs(float(v["cn_val"]))
+
+
+# ---------------------------------------------------------------------------------------------- grid_search
+def test_grid_search_matches_oracle(engine, oracle):
+    rng = np.random.default_rng(21)
+    X = blobs(rng, 6000, 14, 6, amp=2.5)
+    regs = np.array([0.0, 2.0, 8.0, 32.0]) * 1500 * np.sqrt(14) / 1450.0
+    oracle.set_rng(RNG_PHILOX, 99)
+    oracle.set_dead_work(False)
+    want = oracle.grid_search(X, [12], regs, 2, 1500)
+    got = engine.grid_search(X, [12], regs, 2, 1500, seed_off_set=99)
+    assert np.array_equal(got["n"], want["n"])
+    for p, q in zip(got["c"], want["c"]):
+        centres_close(p[0], q[0])
+        centres_close(p[1], q[1])
+    # exact ARI vs the oracle's Monte-Carlo estimate of the same pairs of partitions: 2 iterations averaged
+    assert np.all(np.abs(got["d"] - want["d"]) < 0.04)
+
+
+def test_allocate_many_matches_single(engine, oracle):
+    rng = np.random.default_rng(4)
+    X = blobs(rng, 5000, 14, 6)
+    mus = [blobs(rng, 9, 14, 6) for _ in range(5)]
+    mus[2][[3, 4]] = 0
+    lab, ari = engine.allocate_many(X, mus, True)
+    for s, mu in enumerate(mus):
+        assert np.array_equal(lab[s], oracle.allocate_points(X, mu, True))
+    for i in range(5):
+        for j in range(5):
+            assert abs(ari[i, j] - oracle.rand_index_exact(lab[j] + 1, lab[i] + 1, 9)) < 1e-12
+    assert np.allclose(np.diag(ari), 1.0)

@@ -116,6 +116,12 @@ class Engine:
     def set_ari_mode(self, mode: int) -> None:
         self._chk(self.lib.dpr_set_ari_mode(C.c_int32(mode)))
 
+    def pass_timing(self, enable: bool):
+        """(summed ms, launches) of the fused pass since the last call; enable/disable further timing"""
+        ms, cnt = C.c_double(), C.c_int64()
+        self._chk(self.lib.dpr_pass_timing(C.c_int32(int(enable)), C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
+
     def kernel_launches(self, reset: bool = False) -> int:
         out = C.c_int64()
         self._chk(self.lib.dpr_kernel_launches(C.byref(out), C.c_int32(int(reset))))
@@ -133,11 +139,14 @@ class Engine:
             self._chk(self.lib.dpr_dataset_create(_ptr(Xf, _dp), C.c_int64(X.shape[0]), C.c_int32(X.shape[1]), C.byref(h)))
         return Dataset(self, h, X.shape[0], X.shape[1])
 
-    def synthetic(self, n: int, d: int, groups: int, amplitude: float, seed: int) -> Dataset:
+    def synthetic(self, n: int, d: int, groups: int, amplitude: float, seed: int, row0: int = 0, scale: float = 0.0) -> Dataset:
         h = C.c_void_p()
+        used = C.c_double()
         self._chk(self.lib.dpr_dataset_create_synthetic(C.c_int64(n), C.c_int32(d), C.c_int32(groups), C.c_double(amplitude),
-                                                        C.c_uint64(seed), C.byref(h)))
-        return Dataset(self, h, n, d)
+                                                        C.c_uint64(seed), C.c_int64(row0), C.c_double(scale), C.byref(used), C.byref(h)))
+        ds = Dataset(self, h, n, d)
+        ds.scale = used.value
+        return ds
 
     def read(self, ds: Dataset, row0: int, rows: int) -> np.ndarray:
         out = np.empty((rows, ds.d), np.float64, order="F")

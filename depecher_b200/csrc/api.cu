@@ -76,15 +76,15 @@ static int dataset_alloc(int64_t n, int32_t d, dpr_dataset** out) {
     std::unique_ptr<dpr_dataset> ds(new dpr_dataset());
     ds->n = n;
     ds->d = d;
-    ds->ld = (n + kSlotCells - 1) / kSlotCells * kSlotCells;
-    const size_t bytes = sizeof(float) * (size_t)ds->ld * d;
+    ds->n_pad = (n + kSlotCells - 1) / kSlotCells * kSlotCells;
+    const size_t bytes = sizeof(float) * (size_t)ds->n_pad * d;
     DPR_CUDA(cudaMalloc(&ds->x, bytes));
     DPR_CUDA(cudaMemsetAsync(ds->x, 0, bytes, ctx().stream));
     *out = ds.release();
     return DPR_OK;
 }
 static int dataset_labels(dpr_dataset* ds) {
-    if (!ds->labels) DPR_CUDA(cudaMalloc(&ds->labels, sizeof(int32_t) * (size_t)ds->ld));
+    if (!ds->labels) DPR_CUDA(cudaMalloc(&ds->labels, sizeof(int32_t) * (size_t)ds->n_pad));
     return DPR_OK;
 }
 
@@ -103,8 +103,8 @@ static int dataset_upload(dpr_dataset* ds, const T* X) {
         const int64_t cnt = std::min(chunk, total - e0);
         DPR_CUDA(cudaEventSynchronize(freed[b]));
         DPR_CUDA(cudaMemcpyAsync(stage[b].p, X + e0, sizeof(T) * cnt, cudaMemcpyHostToDevice, ctx().stream));
-        if (sizeof(T) == 8) DPR_TRY(launch_f64_to_cols(stage[b].as<double>(), e0, cnt, ds->n, ds->ld, ds->x, ctx().stream));
-        else DPR_TRY(launch_f32_to_cols(stage[b].as<float>(), e0, cnt, ds->n, ds->ld, ds->x, ctx().stream));
+        if (sizeof(T) == 8) DPR_TRY(launch_f64_to_cols(stage[b].as<double>(), e0, cnt, ds->n, ds->d, ds->x, ctx().stream));
+        else DPR_TRY(launch_f32_to_cols(stage[b].as<float>(), e0, cnt, ds->n, ds->d, ds->x, ctx().stream));
         DPR_CUDA(cudaEventRecord(freed[b], ctx().stream));
     }
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -116,7 +116,7 @@ static int dataset_upload(dpr_dataset* ds, const T* X) {
 static int single_session(dpr_dataset* ds, int k, double reg, int no_zero, bool want_sums, Session& s) {
     DPR_TRY(dataset_labels(ds));
     std::vector<ProblemSpec> specs(1);
-    specs[0] = ProblemSpec{ds->x, ds->ld, ds->n, k, reg, no_zero, ds->labels};
+    specs[0] = ProblemSpec{ds->x, ds->n, k, reg, no_zero, ds->labels};
     return s.init(specs, ds->d, want_sums);
 }
 
@@ -132,7 +132,7 @@ static int cluster_norm_dev(const Problem& pr, int d, double reg, double* out) {
     const int blocks = (int)std::min<int64_t>(148 * 4, (pr.n + 255) / 256);
     DevBuf part;
     DPR_TRY(part.alloc(sizeof(double) * blocks));
-    DPR_TRY(launch_ssq(pr.x, pr.ld, pr.n, d, pr.mu, pr.k, pr.labels, part.as<double>(), blocks, ctx().stream));
+    DPR_TRY(launch_ssq(pr.x, pr.n, d, pr.mu, pr.k, pr.labels, part.as<double>(), blocks, ctx().stream));
     std::vector<double> hp(blocks), mu((size_t)pr.k * d);
     DPR_CUDA(cudaMemcpyAsync(hp.data(), part.p, sizeof(double) * blocks, cudaMemcpyDeviceToHost, ctx().stream));
     DPR_CUDA(cudaMemcpyAsync(mu.data(), pr.mu, sizeof(double) * mu.size(), cudaMemcpyDeviceToHost, ctx().stream));
@@ -148,7 +148,7 @@ static int cluster_norm_dev(const Problem& pr, int d, double reg, double* out) {
 // k-means++ for a list of fits (data pointers may differ); mus[f] = device k x d row-major
 struct SeedJob {
     const float* x;
-    int64_t ld, n;
+    int64_t n;
     uint32_t fit_id;
     double* mu;
     long long* rows;
@@ -168,7 +168,7 @@ static int run_seeding(const std::vector<SeedJob>& jobs, int d, int k, uint64_t 
     std::vector<SeedFit> h(F);
     int64_t wo = 0, bo = 0;
     for (int f = 0; f < F; ++f) {
-        h[f] = SeedFit{jobs[f].x, jobs[f].ld, jobs[f].n, jobs[f].fit_id, 0, jobs[f].mu, w.as<double>() + wo, bs.as<double>() + bo, jobs[f].rows};
+        h[f] = SeedFit{jobs[f].x, jobs[f].n, jobs[f].fit_id, 0, jobs[f].mu, w.as<double>() + wo, bs.as<double>() + bo, jobs[f].rows};
         wo += jobs[f].n;
         bo += (jobs[f].n + kSeedBlock - 1) / kSeedBlock;
     }
@@ -228,7 +228,7 @@ static int find_centers_dev(dpr_dataset* ds, const double* init_mu_colmajor, uin
         DPR_TRY(s.set_centres(0, rm.data()));
     } else {
         std::vector<SeedJob> jobs(1);
-        jobs[0] = SeedJob{ds->x, ds->ld, ds->n, fit_id, s.h_problems[0].mu, nullptr};
+        jobs[0] = SeedJob{ds->x, ds->n, fit_id, s.h_problems[0].mu, nullptr};
         DPR_TRY(run_seeding(jobs, ds->d, (int)k, seed));
     }
     DPR_TRY(s.prepare());
@@ -291,6 +291,25 @@ int dpr_set_ari_mode(int32_t mode) {
     ctx().ari_mode = mode;
     return DPR_OK;
 }
+int dpr_pass_timing(int32_t enable, double* ms_sum_out, int64_t* launches_out) {
+    DPR_TRY(ensure_ready());
+    double sum = 0.0;
+    int64_t cnt = 0;
+    for (auto& ev : ctx().pass_events) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+            sum += ms;
+            ++cnt;
+        }
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    ctx().pass_events.clear();
+    ctx().time_passes = enable != 0;
+    if (ms_sum_out) *ms_sum_out = sum;
+    if (launches_out) *launches_out = cnt;
+    return DPR_OK;
+}
 int dpr_kernel_launches(int64_t* out, int32_t reset) {
     if (out) *out = ctx().launches;
     if (reset) ctx().launches = 0;
@@ -316,7 +335,8 @@ int dpr_dataset_create_f32(const float* X, int64_t n, int32_t d, dpr_dataset_t* 
     *out = ds;
     return DPR_OK;
 }
-int dpr_dataset_create_synthetic(int64_t n, int32_t d, int32_t groups, double amplitude, uint64_t seed, dpr_dataset_t* out) {
+int dpr_dataset_create_synthetic(int64_t n, int32_t d, int32_t groups, double amplitude, uint64_t seed, int64_t row0, double scale,
+                                 double* scale_out, dpr_dataset_t* out) {
     if (groups < 1) return fail(DPR_ERR_INVALID, "groups must be >= 1");
     dpr_dataset* ds = nullptr;
     DPR_TRY(dataset_alloc(n, d, &ds));
@@ -335,13 +355,15 @@ int dpr_dataset_create_synthetic(int64_t n, int32_t d, int32_t groups, double am
     if (rc == DPR_OK) rc = acc.alloc(sizeof(double) * 2, true);
     if (rc != DPR_OK) { dpr_dataset_destroy(ds); return rc; }
     cudaMemcpyAsync(dc.p, cen.data(), sizeof(float) * cen.size(), cudaMemcpyHostToDevice, ctx().stream);
-    rc = launch_synth(ds->x, ds->ld, n, d, dc.as<float>(), groups, seed, acc.as<double>(), acc.as<double>() + 1, ctx().stream);
+    rc = launch_synth(ds->x, n, d, dc.as<float>(), groups, seed, row0, acc.as<double>(), acc.as<double>() + 1, ctx().stream);
     double h[2] = {0, 0};
     cudaMemcpyAsync(h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, ctx().stream);
     cudaStreamSynchronize(ctx().stream);
     const double cnt = (double)n * d, mean = h[0] / cnt;
     const double var = (h[1] - cnt * mean * mean) / (cnt - 1);
-    if (rc == DPR_OK) rc = launch_scale(ds->x, ds->ld, n, d, (float)(1.0 / std::sqrt(var)), ctx().stream);
+    const double used = scale > 0 ? scale : std::sqrt(var);
+    if (scale_out) *scale_out = used;
+    if (rc == DPR_OK) rc = launch_scale(ds->x, ds->n_pad, d, (float)(1.0 / used), ctx().stream);
     if (rc == DPR_OK && cudaStreamSynchronize(ctx().stream) != cudaSuccess) rc = fail(DPR_ERR_CUDA, "synthetic generation failed");
     if (rc != DPR_OK) { dpr_dataset_destroy(ds); return rc; }
     *out = ds;
@@ -365,7 +387,7 @@ int dpr_dataset_read(dpr_dataset_t ds, int64_t row0, int64_t rows, double* out) 
     if (!ds || !out || row0 < 0 || rows < 1 || row0 + rows > ds->n) return fail(DPR_ERR_INVALID, "bad row range");
     DevBuf tmp;
     DPR_TRY(tmp.alloc(sizeof(double) * rows * ds->d));
-    DPR_TRY(launch_cols_to_f64(ds->x, ds->ld, row0, rows, ds->d, tmp.as<double>(), ctx().stream));
+    DPR_TRY(launch_cols_to_f64(ds->x, row0, rows, ds->d, tmp.as<double>(), ctx().stream));
     DPR_CUDA(cudaMemcpyAsync(out, tmp.p, sizeof(double) * rows * ds->d, cudaMemcpyDeviceToHost, ctx().stream));
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));
     return DPR_OK;
@@ -380,7 +402,7 @@ int dpr_dataset_gather(dpr_dataset_t ds, const int64_t* rows, int64_t m, dpr_dat
     int rc = dr.alloc(sizeof(int64_t) * m);
     if (rc == DPR_OK && cudaMemcpyAsync(dr.p, rows, sizeof(int64_t) * m, cudaMemcpyHostToDevice, ctx().stream) != cudaSuccess)
         rc = fail(DPR_ERR_CUDA, "copy of row indices failed");
-    if (rc == DPR_OK) rc = launch_gather(ds->x, ds->ld, ds->n, ds->d, dr.as<int64_t>(), 0, 0, m, g->ld, g->x, 1, 0, ctx().stream);
+    if (rc == DPR_OK) rc = launch_gather(ds->x, ds->n, ds->d, dr.as<int64_t>(), 0, 0, m, g->x, 1, 0, ctx().stream);
     if (rc == DPR_OK && cudaStreamSynchronize(ctx().stream) != cudaSuccess) rc = fail(DPR_ERR_CUDA, "gather failed");
     if (rc != DPR_OK) { dpr_dataset_destroy(g); return rc; }
     *out = g;
@@ -434,7 +456,7 @@ int dpr_dataset_initialize_mu(dpr_dataset_t ds, uint32_t k, uint64_t seed, uint3
     DPR_TRY(mu.alloc(sizeof(double) * k * ds->d, true));
     DPR_TRY(rows.alloc(sizeof(long long) * k, true));
     std::vector<SeedJob> jobs(1);
-    jobs[0] = SeedJob{ds->x, ds->ld, ds->n, fit_id, mu.as<double>(), rows.as<long long>()};
+    jobs[0] = SeedJob{ds->x, ds->n, fit_id, mu.as<double>(), rows.as<long long>()};
     DPR_TRY(run_seeding(jobs, ds->d, (int)k, seed));
     std::vector<double> rm((size_t)k * ds->d);
     std::vector<long long> hr(k);
@@ -496,7 +518,6 @@ int dpr_dataset_cluster_norm(dpr_dataset_t ds, const double* mu, uint32_t k, con
     DPR_CUDA(cudaMemcpyAsync(ds->labels, idx, sizeof(int32_t) * ds->n, cudaMemcpyHostToDevice, ctx().stream));
     Problem pr{};
     pr.x = ds->x;
-    pr.ld = ds->ld;
     pr.n = ds->n;
     pr.k = (int)k;
     pr.mu = dmu.as<double>();
@@ -559,7 +580,7 @@ int dpr_dataset_grid_search(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
     DevBuf xb, lab_b;
     DPR_TRY(xb.alloc(sizeof(float) * (size_t)F * ldb * d, true));
     DPR_TRY(lab_b.alloc(sizeof(int32_t) * (size_t)F * ldb, true));
-    DPR_TRY(launch_gather(ds->x, ds->ld, ds->n, d, nullptr, seed, 0, boot_n, ldb, xb.as<float>(), F, ldb * d, ctx().stream));
+    DPR_TRY(launch_gather(ds->x, ds->n, d, nullptr, seed, 0, boot_n, xb.as<float>(), F, ldb * d, ctx().stream));
     // 2. the fits (find_centers with zero-centre removal, :361-362)
     std::vector<ProblemSpec> specs(F);
     auto cell_of = [&](int f, int& it, int& j, int& l) {
@@ -571,13 +592,13 @@ int dpr_dataset_grid_search(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
     for (int f = 0; f < F; ++f) {
         int it, j, l;
         cell_of(f, it, j, l);
-        specs[f] = ProblemSpec{xb.as<float>() + (size_t)f * ldb * d, ldb, (int64_t)boot_n, k[j], reg[l], 1, lab_b.as<int32_t>() + (size_t)f * ldb};
+        specs[f] = ProblemSpec{xb.as<float>() + (size_t)f * ldb * d, (int64_t)boot_n, k[j], reg[l], 1, lab_b.as<int32_t>() + (size_t)f * ldb};
     }
     Session fits;
     DPR_TRY(fits.init(specs, d, true));
     {
         std::vector<SeedJob> jobs(F);
-        for (int f = 0; f < F; ++f) jobs[f] = SeedJob{specs[f].x, ldb, (int64_t)boot_n, (uint32_t)f, fits.h_problems[f].mu, nullptr};
+        for (int f = 0; f < F; ++f) jobs[f] = SeedJob{specs[f].x, (int64_t)boot_n, (uint32_t)f, fits.h_problems[f].mu, nullptr};
         // seeding rounds are batched per k (the number of rounds is k - 1)
         for (int j = 0; j < nk; ++j) {
             std::vector<SeedJob> sub;
@@ -597,10 +618,10 @@ int dpr_dataset_grid_search(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
     DPR_CUDA(cudaMemcpyAsync(counts.data(), fits.h_problems[0].counts, sizeof(long long) * counts.size(), cudaMemcpyDeviceToHost, ctx().stream));
     // 3. score on the full data, no_zero = false (:370-371)
     DevBuf lab_full;
-    DPR_TRY(lab_full.alloc(sizeof(int32_t) * (size_t)F * ds->ld));
+    DPR_TRY(lab_full.alloc(sizeof(int32_t) * (size_t)F * ds->n_pad));
     std::vector<ProblemSpec> sspecs(F);
     for (int f = 0; f < F; ++f)
-        sspecs[f] = ProblemSpec{ds->x, ds->ld, ds->n, specs[f].k, 0.0, 0, lab_full.as<int32_t>() + (size_t)f * ds->ld};
+        sspecs[f] = ProblemSpec{ds->x, ds->n, specs[f].k, 0.0, 0, lab_full.as<int32_t>() + (size_t)f * ds->n_pad};
     Session score;
     DPR_TRY(score.init(sspecs, d, false));
     for (int f = 0; f < F; ++f) DPR_TRY(score.set_centres_device(f, fits.h_problems[f].mu));
@@ -654,9 +675,9 @@ int dpr_dataset_allocate_many(dpr_dataset_t ds, const double* mus, int32_t m, in
     DPR_TRY(ensure_ready());
     const int d = ds->d;
     DevBuf lab;
-    DPR_TRY(lab.alloc(sizeof(int32_t) * (size_t)m * ds->ld));
+    DPR_TRY(lab.alloc(sizeof(int32_t) * (size_t)m * ds->n_pad));
     std::vector<ProblemSpec> specs(m);
-    for (int s = 0; s < m; ++s) specs[s] = ProblemSpec{ds->x, ds->ld, ds->n, k, 0.0, no_zero, lab.as<int32_t>() + (size_t)s * ds->ld};
+    for (int s = 0; s < m; ++s) specs[s] = ProblemSpec{ds->x, ds->n, k, 0.0, no_zero, lab.as<int32_t>() + (size_t)s * ds->n_pad};
     Session sess;
     DPR_TRY(sess.init(specs, d, false));
     std::vector<double> rm;

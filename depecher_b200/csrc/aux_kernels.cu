@@ -12,27 +12,27 @@ namespace dpr {
 // dimension ld.  Replaces numeric_to_eigen (src/InterfaceUtils.cpp:23-33), which transposes; here R's
 // layout is already the one the kernels want.
 // ---------------------------------------------------------------------------------------------------
-__global__ void f64_to_f32_cols_kernel(const double* __restrict__ src, int64_t e0, int64_t count, int64_t n, int64_t ld,
+__global__ void f64_to_f32_cols_kernel(const double* __restrict__ src, int64_t e0, int64_t count, int64_t n, int d,
                                        float* __restrict__ dst) {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t e = e0 + t;
         const int64_t j = e / n, i = e - j * n;
-        dst[j * ld + i] = (float)src[t];
+        dst[x_index(i, (int)j, d)] = (float)src[t];
     }
 }
-__global__ void f32_to_f32_cols_kernel(const float* __restrict__ src, int64_t e0, int64_t count, int64_t n, int64_t ld,
+__global__ void f32_to_f32_cols_kernel(const float* __restrict__ src, int64_t e0, int64_t count, int64_t n, int d,
                                        float* __restrict__ dst) {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t e = e0 + t;
         const int64_t j = e / n, i = e - j * n;
-        dst[j * ld + i] = src[t];
+        dst[x_index(i, (int)j, d)] = src[t];
     }
 }
-__global__ void cols_to_f64_kernel(const float* __restrict__ x, int64_t ld, int64_t row0, int64_t rows, int d, double* __restrict__ out) {
+__global__ void cols_to_f64_kernel(const float* __restrict__ x, int64_t row0, int64_t rows, int d, double* __restrict__ out) {
     const int64_t total = rows * d;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t j = t / rows, i = t - j * rows;
-        out[t] = (double)x[j * ld + row0 + i];
+        out[t] = (double)x[x_index(row0 + i, (int)j, d)];
     }
 }
 
@@ -40,8 +40,8 @@ __global__ void cols_to_f64_kernel(const float* __restrict__ x, int64_t ld, int6
 // bootstrap_data (src/Clusterer.cpp:308-321): rows drawn with replacement, gathered into a new matrix.
 // rows_explicit == nullptr -> row = Philox(seed, BOOT, fit, i) % n   (include/dpr_philox.h)
 // ---------------------------------------------------------------------------------------------------
-__global__ void gather_rows_kernel(const float* __restrict__ x, int64_t ld, int64_t n, int d, const int64_t* __restrict__ rows_explicit,
-                                   uint64_t seed, uint32_t fit0, int64_t m, int64_t ld_out, float* __restrict__ out, int n_fits,
+__global__ void gather_rows_kernel(const float* __restrict__ x, int64_t n, int d, const int64_t* __restrict__ rows_explicit,
+                                   uint64_t seed, uint32_t fit0, int64_t m, float* __restrict__ out, int n_fits,
                                    int64_t fit_stride) {
     const int64_t total = m * n_fits;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -50,8 +50,8 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, int64_t ld, int6
         int64_t row;
         if (rows_explicit) row = rows_explicit[t];
         else row = (int64_t)(dpr_rng_draw(seed, DPR_RNG_BOOT, fit0 + (uint32_t)f, (uint32_t)i, 0).w[0] % (uint64_t)n);
-        float* o = out + (int64_t)f * fit_stride + i;
-        for (int j = 0; j < d; ++j) o[(int64_t)j * ld_out] = x[(int64_t)j * ld + row];
+        float* o = out + (int64_t)f * fit_stride;
+        for (int j = 0; j < d; ++j) o[x_index(i, j, d)] = x[x_index(row, j, d)];
     }
 }
 __global__ void bootstrap_rows_kernel(int64_t n, uint32_t boot_n, uint64_t seed, uint32_t fit, int64_t* rows) {
@@ -69,7 +69,7 @@ __global__ void bootstrap_rows_kernel(int64_t n, uint32_t boot_n, uint64_t seed,
 __global__ void seed_first_kernel(SeedFit* fits, int d, uint64_t seed) {
     SeedFit f = fits[blockIdx.x];
     const int64_t row = (int64_t)(dpr_rng_draw(seed, DPR_RNG_SEED, f.fit_id, 0, 0).w[0] % (uint64_t)f.n);
-    for (int j = threadIdx.x; j < d; j += blockDim.x) f.mu[j] = (double)f.x[(int64_t)j * f.ld + row];
+    for (int j = threadIdx.x; j < d; j += blockDim.x) f.mu[j] = (double)f.x[x_index(row, j, d)];
     if (threadIdx.x == 0 && f.rows) f.rows[0] = row;
 }
 
@@ -86,7 +86,7 @@ __global__ void seed_dist_kernel(const SeedFit* fits, int d, int c /* centre jus
         if (i < f.n) {
             double s = 0.0;
             for (int j = 0; j < d; ++j) {
-                const double diff = __dadd_rn(-(double)f.x[(int64_t)j * f.ld + i], s_mu[j]);
+                const double diff = __dadd_rn(-(double)f.x[x_index(i, j, d)], s_mu[j]);
                 s = __dadd_rn(s, __dmul_rn(diff, diff));
             }
             if (!first) {
@@ -149,13 +149,13 @@ __global__ void seed_pick_kernel(SeedFit* fits, int d, int c, uint64_t seed) {
     }
     __syncthreads();
     const long long row = s_row;
-    for (int j = threadIdx.x; j < d; j += blockDim.x) f.mu[(size_t)c * d + j] = (double)f.x[(int64_t)j * f.ld + row];
+    for (int j = threadIdx.x; j < d; j += blockDim.x) f.mu[(size_t)c * d + j] = (double)f.x[x_index(row, j, d)];
 }
 
 // ---------------------------------------------------------------------------------------------------
 // cluster_norm (src/Clusterer.cpp:198-211): sum_i ||x_i - mu_{l_i}||^2  (+ reg * sum(mu), added by the host)
 // ---------------------------------------------------------------------------------------------------
-__global__ void ssq_kernel(const float* __restrict__ x, int64_t ld, int64_t n, int d, const double* __restrict__ mu, int k,
+__global__ void ssq_kernel(const float* __restrict__ x, int64_t n, int d, const double* __restrict__ mu, int k,
                            const int32_t* __restrict__ labels, double* __restrict__ block_out) {
     extern __shared__ double s_mu[];
     for (int e = threadIdx.x; e < k * d; e += blockDim.x) s_mu[e] = mu[e];
@@ -165,7 +165,7 @@ __global__ void ssq_kernel(const float* __restrict__ x, int64_t ld, int64_t n, i
         const double* m = s_mu + (size_t)labels[i] * d;
         double s = 0.0;
         for (int j = 0; j < d; ++j) {
-            const double diff = (double)x[(int64_t)j * ld + i] - m[j];
+            const double diff = (double)x[x_index(i, j, d)] - m[j];
             s += diff * diff;
         }
         acc += s;
@@ -309,18 +309,19 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
     sincosf(6.2831853f * u2, &s, &c);
     return make_float2(r * c, r * s);
 }
-__global__ void synth_kernel(float* x, int64_t ld, int64_t n, int d, const float* __restrict__ centres, int groups, uint64_t seed,
-                             double* sum_out, double* sumsq_out) {
+__global__ void synth_kernel(float* x, int64_t n, int d, const float* __restrict__ centres, int groups, uint64_t seed,
+                             int64_t row0, double* sum_out, double* sumsq_out) {
     double s = 0.0, ss = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int g = (int)(dpr_rng_draw(seed, 11, (uint32_t)i, (uint32_t)(i >> 32), 0).w[0] % (uint32_t)groups);
+        const int64_t gi = row0 + i;  // global cell number: shards of one virtual matrix never repeat a cell
+        const int g = (int)(dpr_rng_draw(seed, 11, (uint32_t)gi, (uint32_t)(gi >> 32), 0).w[0] % (uint32_t)groups);
         for (int j0 = 0; j0 < d; j0 += 4) {
-            const dpr_u32x4 w = dpr_rng_draw(seed, 12, (uint32_t)i, (uint32_t)(i >> 32), (uint32_t)j0);
+            const dpr_u32x4 w = dpr_rng_draw(seed, 12, (uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)j0);
             const float2 n0 = box_muller(w.w[0], w.w[1]), n1 = box_muller(w.w[2], w.w[3]);
             const float z[4] = {n0.x, n0.y, n1.x, n1.y};
             for (int q = 0; q < 4 && j0 + q < d; ++q) {
                 const float v = centres[g * d + j0 + q] + z[q];
-                x[(int64_t)(j0 + q) * ld + i] = v;
+                x[x_index(i, j0 + q, d)] = v;
                 s += v;
                 ss += (double)v * v;
             }
@@ -335,12 +336,9 @@ __global__ void synth_kernel(float* x, int64_t ld, int64_t n, int d, const float
         atomicAdd(sumsq_out, ss);
     }
 }
-__global__ void scale_kernel(float* x, int64_t ld, int64_t n, int d, float inv_sd) {
-    const int64_t total = n * d;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t j = t / n, i = t - j * n;
-        x[j * ld + i] *= inv_sd;
-    }
+__global__ void scale_kernel(float* x, int64_t n_pad, int d, float inv_sd) {
+    const int64_t total = n_pad * d;   // padding cells are zero and stay zero
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) x[t] *= inv_sd;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -351,27 +349,27 @@ static inline int blocks_for(int64_t n, int per = 256, int cap = 148 * 16) {
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-int launch_f64_to_cols(const double* src, int64_t e0, int64_t count, int64_t n, int64_t ld, float* dst, cudaStream_t st) {
-    f64_to_f32_cols_kernel<<<blocks_for(count), 256, 0, st>>>(src, e0, count, n, ld, dst);
+int launch_f64_to_cols(const double* src, int64_t e0, int64_t count, int64_t n, int d, float* dst, cudaStream_t st) {
+    f64_to_f32_cols_kernel<<<blocks_for(count), 256, 0, st>>>(src, e0, count, n, d, dst);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
 }
-int launch_f32_to_cols(const float* src, int64_t e0, int64_t count, int64_t n, int64_t ld, float* dst, cudaStream_t st) {
-    f32_to_f32_cols_kernel<<<blocks_for(count), 256, 0, st>>>(src, e0, count, n, ld, dst);
+int launch_f32_to_cols(const float* src, int64_t e0, int64_t count, int64_t n, int d, float* dst, cudaStream_t st) {
+    f32_to_f32_cols_kernel<<<blocks_for(count), 256, 0, st>>>(src, e0, count, n, d, dst);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
 }
-int launch_cols_to_f64(const float* x, int64_t ld, int64_t row0, int64_t rows, int d, double* out, cudaStream_t st) {
-    cols_to_f64_kernel<<<blocks_for(rows * d), 256, 0, st>>>(x, ld, row0, rows, d, out);
+int launch_cols_to_f64(const float* x, int64_t row0, int64_t rows, int d, double* out, cudaStream_t st) {
+    cols_to_f64_kernel<<<blocks_for(rows * d), 256, 0, st>>>(x, row0, rows, d, out);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
 }
-int launch_gather(const float* x, int64_t ld, int64_t n, int d, const int64_t* rows, uint64_t seed, uint32_t fit0, int64_t m,
-                  int64_t ld_out, float* out, int n_fits, int64_t fit_stride, cudaStream_t st) {
-    gather_rows_kernel<<<blocks_for(m * n_fits), 256, 0, st>>>(x, ld, n, d, rows, seed, fit0, m, ld_out, out, n_fits, fit_stride);
+int launch_gather(const float* x, int64_t n, int d, const int64_t* rows, uint64_t seed, uint32_t fit0, int64_t m, float* out, int n_fits,
+                  int64_t fit_stride, cudaStream_t st) {
+    gather_rows_kernel<<<blocks_for(m * n_fits), 256, 0, st>>>(x, n, d, rows, seed, fit0, m, out, n_fits, fit_stride);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
@@ -395,8 +393,8 @@ int launch_seeding(SeedFit* d_fits, int n_fits, int64_t n_max, int d, int k, uin
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
 }
-int launch_ssq(const float* x, int64_t ld, int64_t n, int d, const double* mu, int k, const int32_t* labels, double* block_out,
-               int blocks, cudaStream_t st) {
+int launch_ssq(const float* x, int64_t n, int d, const double* mu, int k, const int32_t* labels, double* block_out, int blocks,
+               cudaStream_t st) {
     const size_t shm = sizeof(double) * k * d;
     if (shm > 200 * 1024) return fail(DPR_ERR_INVALID, "cluster_norm: k * d too large for the shared-memory centre table");
     static size_t configured = 48 * 1024;
@@ -404,7 +402,7 @@ int launch_ssq(const float* x, int64_t ld, int64_t n, int d, const double* mu, i
         DPR_CUDA(cudaFuncSetAttribute(ssq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = 200 * 1024;
     }
-    ssq_kernel<<<blocks, 256, shm, st>>>(x, ld, n, d, mu, k, labels, block_out);
+    ssq_kernel<<<blocks, 256, shm, st>>>(x, n, d, mu, k, labels, block_out);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
@@ -441,15 +439,15 @@ int launch_label_presence(const int32_t* labels, int64_t n, int kk, int32_t* pre
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
 }
-int launch_synth(float* x, int64_t ld, int64_t n, int d, const float* centres, int groups, uint64_t seed, double* sum, double* sumsq,
+int launch_synth(float* x, int64_t n, int d, const float* centres, int groups, uint64_t seed, int64_t row0, double* sum, double* sumsq,
                  cudaStream_t st) {
-    synth_kernel<<<blocks_for(n), 256, 0, st>>>(x, ld, n, d, centres, groups, seed, sum, sumsq);
+    synth_kernel<<<blocks_for(n), 256, 0, st>>>(x, n, d, centres, groups, seed, row0, sum, sumsq);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
 }
-int launch_scale(float* x, int64_t ld, int64_t n, int d, float inv_sd, cudaStream_t st) {
-    scale_kernel<<<blocks_for(n * d), 256, 0, st>>>(x, ld, n, d, inv_sd);
+int launch_scale(float* x, int64_t n_pad, int d, float inv_sd, cudaStream_t st) {
+    scale_kernel<<<blocks_for(n_pad * d), 256, 0, st>>>(x, n_pad, d, inv_sd);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;

@@ -119,43 +119,26 @@ __global__ void prepare_centres_kernel(Problem* problems, int table_cap) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// reduce: out[p][seg][entry] = sum over the CTAs of segment `seg` (ascending) and their warps (ascending)
-// of the partial tables that belong to problem p; the partials are zeroed on the way for the next pass.
-// entry layout per problem: [k_max*d sums][k_max counts][1 changed]
+// reduce: out[p][seg][entry] = sum, in ascending CTA order, of the (CTA, problem) tables written by the
+// fused pass for the CTAs of segment `seg` whose tile range touches problem p.
+// entry layout: [k_max*d sums][k_max counts][1 changed]
 // ---------------------------------------------------------------------------------------------------
-__global__ void reduce_partials_kernel(const Problem* problems, const int32_t* cta_tile_start, int grid_ctas, int warps, int k_max, int d,
-                                       double* part_sums, long long* part_counts, long long* part_changed, double* seg_out,
-                                       int n_seg) {
+__global__ void reduce_partials_kernel(const Problem* problems, const int32_t* cta_tile_start, int grid_ctas, int k_max, int d,
+                                       const double* cta_tables, double* seg_out, int n_seg) {
     const int p = blockIdx.x, seg = blockIdx.y;
     const Problem pr = problems[p];
-    const int64_t stride = (int64_t)k_max * d;
-    const int64_t entries = stride + k_max + 1;
+    const int64_t entries = (int64_t)k_max * d + k_max + 1;
     double* out = seg_out + ((int64_t)p * n_seg + seg) * entries;
     const int c0 = (int)((int64_t)grid_ctas * seg / n_seg), c1 = (int)((int64_t)grid_ctas * (seg + 1) / n_seg);
     const int t0 = pr.first_tile, t1 = pr.first_tile + pr.n_tiles;
     for (int64_t e = threadIdx.x; e < entries; e += blockDim.x) {
         double acc = 0.0;
-        if (!pr.done) {
+        if (!pr.done)
             for (int c = c0; c < c1; ++c) {
-                if (cta_tile_start[c] >= t1 || cta_tile_start[c + 1] <= t0 || cta_tile_start[c] >= cta_tile_start[c + 1]) continue;
-                const size_t tab0 = (size_t)(c + p) * warps;
-                for (int w = 0; w < warps; ++w) {
-                    if (e < stride) {
-                        double* q = part_sums + (tab0 + w) * stride + e;
-                        acc += *q;
-                        *q = 0.0;
-                    } else if (e < stride + k_max) {
-                        long long* q = part_counts + (tab0 + w) * k_max + (e - stride);
-                        acc += (double)*q;
-                        *q = 0;
-                    } else {
-                        long long* q = part_changed + (tab0 + w);
-                        acc += (double)*q;
-                        *q = 0;
-                    }
-                }
+                const int a = cta_tile_start[c], b = cta_tile_start[c + 1];
+                if (a >= t1 || b <= t0 || a >= b) continue;
+                acc += cta_tables[(size_t)(c + p) * entries + e];
             }
-        }
         out[e] = acc;
     }
 }
@@ -164,7 +147,7 @@ __global__ void reduce_partials_kernel(const Problem* problems, const int32_t* c
 // finalize: one CTA per problem.  iter = index i of the assignment that just ran.
 // ---------------------------------------------------------------------------------------------------
 __global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_seg, int k_max, int iter, int max_iter, int table_cap,
-                                int32_t* n_active_out) {
+                                int allow_delta, int32_t* n_active_out) {
     const int p = blockIdx.x;
     Problem pr = problems[p];
     if (pr.done) return;
@@ -179,10 +162,10 @@ __global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_s
         for (int s = 0; s < n_seg; ++s) acc += in[(int64_t)s * entries + e];
         if (e < stride) {
             const int c = (int)(e / d), j = (int)(e % d);
-            if (c < k) pr.sums[(size_t)c * d + j] = acc;
+            if (c < k) pr.sums[(size_t)c * d + j] = (pr.delta ? pr.sums[(size_t)c * d + j] : 0.0) + acc;
         } else if (e < stride + k_max) {
             const int c = (int)(e - stride);
-            if (c < k) pr.counts[c] = (long long)acc;
+            if (c < k) pr.counts[c] = (pr.delta ? pr.counts[c] : 0LL) + (long long)acc;
         } else {
             s_changed = (long long)acc;
         }
@@ -193,6 +176,8 @@ __global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_s
     if (threadIdx.x == 0) {
         problems[p].changed = changed;
         problems[p].n_assign = iter + 1;
+        // next pass: scatter only the cells that change label once few of them do (sums += delta)
+        problems[p].delta = (allow_delta && changed * 8 < pr.n) ? 1 : 0;
     }
     if (converged || iter + 1 >= max_iter) {
         // Clusterer.cpp:247-249: break BEFORE the update: centres stay those of the previous iteration.
@@ -235,21 +220,18 @@ int launch_prepare_centres(Problem* d_problems, int n_problems, int table_cap, c
     return DPR_OK;
 }
 
-int launch_reduce_partials(const Problem* d_problems, int n_problems, const int32_t* cta_tile_start, int grid_ctas, int warps, int k_max,
-                           int d,
-                           double* part_sums, long long* part_counts, long long* part_changed, double* seg_out, int n_seg,
-                           cudaStream_t st) {
+int launch_reduce_partials(const Problem* d_problems, int n_problems, const int32_t* cta_tile_start, int grid_ctas, int k_max, int d,
+                           const double* cta_tables, double* seg_out, int n_seg, cudaStream_t st) {
     dim3 g(n_problems, n_seg);
-    reduce_partials_kernel<<<g, 256, 0, st>>>(d_problems, cta_tile_start, grid_ctas, warps, k_max, d, part_sums, part_counts, part_changed,
-                                              seg_out, n_seg);
+    reduce_partials_kernel<<<g, 256, 0, st>>>(d_problems, cta_tile_start, grid_ctas, k_max, d, cta_tables, seg_out, n_seg);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
 }
 
 int launch_finalize(Problem* d_problems, int n_problems, const double* seg_in, int n_seg, int k_max, int iter, int max_iter,
-                    int table_cap, int32_t* n_active_out, cudaStream_t st) {
-    finalize_kernel<<<n_problems, 256, 0, st>>>(d_problems, seg_in, n_seg, k_max, iter, max_iter, table_cap, n_active_out);
+                    int table_cap, int allow_delta, int32_t* n_active_out, cudaStream_t st) {
+    finalize_kernel<<<n_problems, 256, 0, st>>>(d_problems, seg_in, n_seg, k_max, iter, max_iter, table_cap, allow_delta, n_active_out);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;

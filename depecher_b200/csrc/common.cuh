@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/depecher_b200.h"
@@ -26,13 +27,25 @@ int fail(int code, const std::string& msg);
     } while (0)
 
 // ---- geometry of the fused pass --------------------------------------------------------------
-constexpr int kSlotCells = 128;   // cells per warp slot (32 lanes x 4 cells, one LDS.128 per marker)
-constexpr int kRowStride = 132;   // floats per marker row of a slot (528 B: 16 B aligned, bank-skewed)
-constexpr int kMaxKC = 32;        // centres per register-tile chunk (4 cells x 32 centres = 128 accumulators)
-constexpr int kWarpsPerCta = 8;
+constexpr int kSlotCells = 64;    // cells per warp slot (32 lanes x 2 cells, one LDS.64 per marker)
+constexpr int kRowStride = 64;    // floats per marker row of a slot: rows are dense, cells are XOR-swizzled inside a row
+constexpr int kMaxKC = 32;        // centres per register-tile chunk (2 cells x 32 centres = 64 accumulators)
+constexpr int kWarpsPerCta = 16;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kMaxChunks = 8;     // => fast path handles up to 256 active centres
 constexpr int kSmemBudget = 227 * 1024;
+
+// Resident layout of a cell matrix ("tile-major"): cells are grouped in tiles of kSlotCells = 64 consecutive
+// cells; a tile holds its d marker rows back to back (d * 64 floats, contiguous in HBM, so one bulk-async
+// copy moves a whole slot), and inside marker row j the cell c sits at c ^ (2 * (j & 15)).  The XOR keeps
+// the (2c, 2c+1) pair of a lane adjacent (one LDS.64 per marker in the distance loop, conflict-free) and
+// spreads the marker rows of one cell over 16 banks for the transposed reads of the sum phase.
+__host__ __device__ __forceinline__ size_t x_index(int64_t cell, int j, int d) {
+    return (size_t)(cell >> 6) * (size_t)(d * kSlotCells) + (size_t)j * kSlotCells + (size_t)((cell & 63) ^ ((j & 15) << 1));
+}
+__host__ __device__ __forceinline__ int x_slot_index(int cell_in_slot, int j) {
+    return j * kSlotCells + (cell_in_slot ^ ((j & 15) << 1));
+}
 
 // Centre table of one problem as the fused pass reads it (global memory, built on device by
 // finalize_kernel / prepare_centres_kernel).  Floats are laid out per chunk:
@@ -54,8 +67,7 @@ struct CentreHeader {
 
 // One problem = one data matrix + one centre set (+ the state of its Lloyd loop).  Device-resident array.
 struct Problem {
-    const float* x;       // column-major fp32, column j at x + j*ld
-    int64_t ld;           // floats per column (multiple of kSlotCells)
+    const float* x;       // resident fp32 cells, tile-major (see x_index)
     int64_t n;            // cells
     int32_t d;
     int32_t k;
@@ -71,7 +83,7 @@ struct Problem {
     int32_t no_zero;
     int32_t done;         // converged (labels unchanged and i > 20) or iteration cap reached
     int32_t n_assign;     // assignments performed so far
-    int32_t pad_;
+    int32_t delta;        // next Lloyd pass accumulates only the cells whose label changes (sums += delta)
     long long changed;    // labels changed in the last assignment
     double* sums;         // k x d  (this rank's, then all ranks')
     long long* counts;    // k
@@ -86,6 +98,9 @@ struct Context {
     cudaStream_t own_stream = nullptr;
     int ari_mode = DPR_ARI_EXACT;
     int64_t launches = 0;
+    // optional per-launch timing of the fused pass (dpr_pass_timing)
+    bool time_passes = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pass_events;
     // multi-GPU
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
@@ -100,7 +115,7 @@ inline void count_launch(int n = 1) { ctx().launches += n; }
 struct dpr_dataset {
     int64_t n = 0;
     int32_t d = 0;
-    int64_t ld = 0;
-    float* x = nullptr;        // device
-    int32_t* labels = nullptr; // device, ld entries (lazily allocated)
+    int64_t n_pad = 0;         // n rounded up to whole tiles
+    float* x = nullptr;        // device, tile-major (dpr::x_index), n_pad * d floats
+    int32_t* labels = nullptr; // device, n_pad entries (lazily allocated)
 };

@@ -4,21 +4,25 @@
 // half of Clusterer::reevaluate_centers (:99-102) with ONE pass over the cells.
 //
 // Shape of the work:
-//   * X lives in HBM as column-major fp32 (R's own layout, so every marker column is a contiguous
-//     stream).  A warp owns a "slot" of 128 consecutive cells x d markers in shared memory, filled by
-//     d bulk-async copies (TMA, cp.async.bulk + mbarrier complete_tx) of 512 B each.
-//   * Distance micro-kernel: each lane holds 4 cells x up to 32 centres = 128 fp32 accumulators as
-//     packed pairs and issues FFMA2 (fma.rn.f32x2): s_k = ||c_k||^2 - 2 x.c_k.  One LDS.128 brings the
-//     lane's 4 cells of a marker, one broadcast LDS.128 brings 4 centres.  Measured on B200: this tile
-//     shape runs at 98 % of the FP32 pipe, scalar FFMA or narrower tiles lose 10-30 %
-//     (profiles/microbench/r01_pipes_b200.log).
-//   * Argmin in registers with the centre index packed into the 5 low mantissa bits; cells whose two
-//     best fp32 scores are closer than a proven error bound are re-decided in fp64 exactly as the
-//     reference does (sqrt of the left-to-right sum, strict <), so labels are bit-exact for
+//   * X lives in HBM as fp32 in tile-major order (common.cuh: x_index): the d marker rows of 64 consecutive
+//     cells are contiguous and pre-swizzled, so a warp fills its "slot" (64 cells x d markers of shared
+//     memory) with ONE bulk-async copy (TMA, cp.async.bulk + mbarrier complete_tx) of d * 256 bytes;
+//     16 warps per SM keep 16 slots (up to 3 per warp when d is small) in flight or in use.
+//   * Distance micro-kernel: each lane holds 2 cells x up to 32 centres = 64 fp32 accumulators as
+//     packed pairs and issues FFMA2 (fma.rn.f32x2): s_k = ||c_k||^2 - 2 x.c_k.  One LDS.64 brings the
+//     lane's 2 cells of a marker, one broadcast LDS.128 brings 4 centres.  (Measured on B200: packed
+//     FFMA2 with >= 32-wide centre tiles reaches 88-98 % of the FP32 pipe, scalar FFMA or narrower tiles
+//     lose 10-30 %: profiles/microbench/r01_pipes_b200.log.)
+//   * Argmin in registers with the centre index packed into the 5 low mantissa bits (FMNMX/FMNMX3);
+//     cells whose two best fp32 scores are closer than a proven error bound are re-decided in fp64 exactly
+//     as the reference does (sqrt of the left-to-right sum, strict <), so labels are bit-exact for
 //     fp32-representable data.
-//   * Lloyd mode: the warp counting-sorts its 128 labels (match.any, no atomics), then lanes switch to
-//     marker ownership and add each label's run in fp64 registers before one read-modify-write of the
-//     warp's PRIVATE partial table.  Fixed tile->warp map + private tables => bit-reproducible sums.
+//   * Lloyd mode: the warp counting-sorts its contributions by label (match.any, no atomics), then lanes
+//     switch to marker ownership and add each label's run in fp64 registers before one read-modify-write
+//     of the warp's PRIVATE table.  Full mode contributes every cell (+x to its label); delta mode only
+//     the cells whose label changed (+x to the new, -x to the old label), which after the first few
+//     iterations is a fraction of a percent of the cells.  Fixed tile->warp map + private tables + fixed
+//     combine order => bit-reproducible sums.
 #include "common.cuh"
 #include "fused_pass.cuh"
 
@@ -48,14 +52,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
                  : "memory");
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// distance micro-kernel for one chunk of KC centres
+// distance micro-kernel for one chunk of KC centres: 2 cells per lane
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float pack_idx(float s, int idx) {
     return __uint_as_float((__float_as_uint(s) & 0xFFFFFFE0u) | (unsigned)idx);
@@ -63,57 +72,57 @@ __device__ __forceinline__ float pack_idx(float s, int idx) {
 
 template <int KC, bool FIRST>
 __device__ __forceinline__ void dist_chunk(const float* __restrict__ slot, const float* __restrict__ tab, int d, int lane,
-                                           float (&xx)[4], float (&best)[4], float (&second)[4]) {
+                                           float (&xx)[2], float (&best)[2], float (&second)[2]) {
     constexpr int NP = KC / 2;
     constexpr int KCP = (KC + 3) & ~3;
-    float2 acc[4][NP];
+    float2 acc[2][NP];
     {
         const float2* cc = reinterpret_cast<const float2*>(tab);
 #pragma unroll
         for (int t = 0; t < NP; ++t) {
-            float2 c = cc[t];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r][t] = c;
+            const float2 c = cc[t];
+            acc[0][t] = c;
+            acc[1][t] = c;
         }
     }
-    const float4* xs = reinterpret_cast<const float4*>(slot) + lane;
+    const float2* xs = reinterpret_cast<const float2*>(slot);
     const float4* cw = reinterpret_cast<const float4*>(tab + KCP);
 #pragma unroll 2
     for (int j = 0; j < d; ++j) {
-        const float4 xv = xs[j * (kRowStride / 4)];
-        const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+        const float2 xv = xs[j * (kRowStride / 2) + (lane ^ (j & 15))];   // cells (2*lane, 2*lane+1) of marker j, swizzled
+        const float2 x0 = make_float2(xv.x, xv.x), x1 = make_float2(xv.y, xv.y);
 #pragma unroll
         for (int q = 0; q < KCP / 4; ++q) {
             const float4 c = cw[j * (KCP / 4) + q];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const float2 xr = make_float2(x[r], x[r]);
-                acc[r][2 * q] = __ffma2_rn(xr, make_float2(c.x, c.y), acc[r][2 * q]);
-                if (2 * q + 1 < NP) acc[r][2 * q + 1] = __ffma2_rn(xr, make_float2(c.z, c.w), acc[r][2 * q + 1]);
+            acc[0][2 * q] = __ffma2_rn(x0, make_float2(c.x, c.y), acc[0][2 * q]);
+            acc[1][2 * q] = __ffma2_rn(x1, make_float2(c.x, c.y), acc[1][2 * q]);
+            if (2 * q + 1 < NP) {
+                acc[0][2 * q + 1] = __ffma2_rn(x0, make_float2(c.z, c.w), acc[0][2 * q + 1]);
+                acc[1][2 * q + 1] = __ffma2_rn(x1, make_float2(c.z, c.w), acc[1][2 * q + 1]);
             }
         }
         if (FIRST) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) xx[r] = fmaf(x[r], x[r], xx[r]);
+            xx[0] = fmaf(xv.x, xv.x, xx[0]);
+            xx[1] = fmaf(xv.y, xv.y, xx[1]);
         }
     }
+    // two smallest packed scores per cell: merge the sorted pair (lo, hi) of each accumulator pair
 #pragma unroll
     for (int t = 0; t < NP; ++t) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < 2; ++r) {
             const float a = pack_idx(acc[r][t].x, 2 * t);
             const float b = pack_idx(acc[r][t].y, 2 * t + 1);
-            second[r] = fminf(second[r], fmaxf(a, best[r]));
-            best[r] = fminf(best[r], a);
-            second[r] = fminf(second[r], fmaxf(b, best[r]));
-            best[r] = fminf(best[r], b);
+            const float lo = fminf(a, b), hi = fmaxf(a, b);
+            second[r] = fmin3(fmaxf(best[r], lo), second[r], hi);
+            best[r] = fminf(best[r], lo);
         }
     }
 }
 
 template <bool FIRST>
-__device__ __forceinline__ void dist_chunk_dispatch(int kc, const float* slot, const float* tab, int d, int lane, float (&xx)[4],
-                                                    float (&best)[4], float (&second)[4]) {
+__device__ __forceinline__ void dist_chunk_dispatch(int kc, const float* slot, const float* tab, int d, int lane, float (&xx)[2],
+                                                    float (&best)[2], float (&second)[2]) {
     switch (kc) {
 #define DPR_CASE(KC)                                                \
     case KC:                                                        \
@@ -127,48 +136,65 @@ __device__ __forceinline__ void dist_chunk_dispatch(int kc, const float* slot, c
 }
 
 // ---------------------------------------------------------------------------------------------------
-// exact decision for one cell: the reference's arithmetic (Clusterer.cpp:56-66) in fp64 —
-// d_k = sqrt(sum_t ((-x_t) + mu_kt)^2), separate multiply and add (no contraction: the reference is
-// built for baseline x86-64, which has no FMA), strict-< first minimum over the active rows in order.
+// exact decision for one cell, by the whole warp: the reference's arithmetic (Clusterer.cpp:56-66) in fp64 —
+// d_k = sqrt(sum_t ((-x_t) + mu_kt)^2), separate multiply and add (no contraction: the reference is built
+// for baseline x86-64, which has no FMA), strict-< first minimum over the active rows in order.  Lane a
+// takes active slots a, a+32, ...; the (distance, slot) pairs are then reduced lexicographically, which is
+// the sequential first-minimum scan (a NaN distance is never chosen unless it is the first one, like there).
 // ---------------------------------------------------------------------------------------------------
-__device__ __noinline__ int exact_label(const float* __restrict__ slot, int cell, int d, const double* __restrict__ mu,
-                                        const int32_t* __restrict__ orig, int n_slots) {
-    int best = -1;
-    double bv = 0.0;
-    for (int a = 0; a < n_slots; ++a) {
+__device__ __noinline__ int exact_label_warp(const float* __restrict__ slot, int cell, int d, const double* __restrict__ mu,
+                                             const int32_t* __restrict__ orig, int n_slots, int lane) {
+    double bv = INFINITY;
+    int bi = 0x7fffffff;
+    bool first_nan = false;
+    for (int a = lane; a < n_slots; a += 32) {
         const int row = orig[a];
         if (row < 0) continue;
         const double* m = mu + (size_t)row * d;
         double s = 0.0;
         for (int t = 0; t < d; ++t) {
-            const double diff = __dadd_rn(-(double)slot[t * kRowStride + cell], m[t]);
+            const double diff = __dadd_rn(-(double)slot[x_slot_index(cell, t)], m[t]);
             s = __dadd_rn(s, __dmul_rn(diff, diff));
         }
         const double dist = sqrt(s);
-        if (best < 0) {
-            best = row;
+        if (a == 0 && dist != dist) first_nan = true;
+        if (dist < bv) {
             bv = dist;
-        } else if (dist < bv) {
-            bv = dist;
-            best = row;
+            bi = a;
         }
     }
-    return best < 0 ? 0 : best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov < bv || (ov == bv && oi < bi)) {
+            bv = ov;
+            bi = oi;
+        }
+    }
+    first_nan = __shfl_sync(0xffffffffu, (int)first_nan, 0) != 0;
+    if (first_nan || bi == 0x7fffffff) bi = 0;   // nothing compares below a NaN / every distance is NaN or +inf: the first row stays
+    return n_slots > 0 ? orig[bi] : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Lloyd mode: sums/counts of one slot into the warp's private partial table
+// Lloyd mode: signed contributions of one slot into the warp's private table.
+// Each lane brings up to 4 entries: (cell, label, sign); key = 2*label + (sign < 0).  off[0..2k] ints and
+// perm[0..127] bytes are the warp's scratch.  No atomics: one leader per key per instruction.
 // ---------------------------------------------------------------------------------------------------
-// off[0..k] (ints) and perm[0..127] (bytes) are the warp's scratch in shared memory.
-__device__ __forceinline__ void slot_sums(const float* __restrict__ slot, const int (&lab)[4], int d, int k, int lane, int* off,
-                                          unsigned char* perm, double* __restrict__ sums, long long* __restrict__ counts) {
+__device__ __forceinline__ void slot_contributions(const float* __restrict__ slot, const int (&key)[4], const int (&cell)[4], int d,
+                                                   int k, int lane, int* off, unsigned char* perm, double* __restrict__ sums,
+                                                   long long* __restrict__ counts) {
     const unsigned full = 0xffffffffu;
-    for (int i = lane; i <= k; i += 32) off[i] = 0;
+    const int nk = 2 * k;
+    const bool any = (key[0] >= 0) | (key[1] >= 0) | (key[2] >= 0) | (key[3] >= 0);
+    if (!__any_sync(full, any)) return;
+    for (int i = lane; i <= nk; i += 32) off[i] = 0;
     __syncwarp();
     int pos[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const int L = lab[r];
+        const int L = key[r];
         const unsigned m = __match_any_sync(full, L);
         const int leader = __ffs(m) - 1;
         int base = 0;
@@ -180,52 +206,53 @@ __device__ __forceinline__ void slot_sums(const float* __restrict__ slot, const 
         pos[r] = base + __popc(m & ((1u << lane) - 1u));
         __syncwarp();
     }
-    // counts -> exclusive offsets (off[L] = first position of label L, off[k] = valid cells)
+    // inclusive scan: off[i] = number of entries with key < i   (entry i held the count of key i-1)
     int carry = 0;
-    for (int b = 0; b <= k; b += 32) {
+    for (int b = 0; b <= nk; b += 32) {
         const int i = b + lane;
-        int v = (i <= k) ? off[i] : 0;
-        int s = v;
+        int s = (i <= nk) ? off[i] : 0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(full, s, o);
             if (lane >= o) s += t;
         }
-        if (i <= k) off[i] = carry + s;  // inclusive over entries 0..i  (entry 0 is 0)
+        if (i <= nk) off[i] = carry + s;
         carry += __shfl_sync(full, s, 31);
     }
     __syncwarp();
-    // off[i] now = number of cells with label < i  (entry i held the count of label i-1)
 #pragma unroll
     for (int r = 0; r < 4; ++r)
-        if (lab[r] >= 0) perm[off[lab[r]] + pos[r]] = (unsigned char)(4 * lane + r);
+        if (key[r] >= 0) perm[off[key[r]] + pos[r]] = (unsigned char)cell[r];
     __syncwarp();
     for (int L = lane; L < k; L += 32) {
-        const int c = off[L + 1] - off[L];
-        if (c) counts[L] += c;
+        const int c = (off[2 * L + 1] - off[2 * L]) - (off[2 * L + 2] - off[2 * L + 1]);
+        if (c) __stcg(&counts[L], __ldcg(&counts[L]) + c);
     }
     for (int jb = 0; jb < d; jb += 32) {
         const int j = jb + lane;
         const bool on = j < d;
         const float* row = slot + (on ? j : 0) * kRowStride;
+        const int xo = ((on ? j : 0) & 15) << 1;   // swizzle of this lane's marker row
         for (int Lb = 0; Lb < k; Lb += 32) {
             const int Li = Lb + lane;
-            const bool present = (Li < k) && (off[Li + 1] > off[Li]);
+            const bool present = (Li < k) && (off[2 * Li + 2] > off[2 * Li]);
             unsigned pm = __ballot_sync(full, present);
             while (pm) {
                 const int L = Lb + __ffs(pm) - 1;
                 pm &= pm - 1;
-                const int s = off[L], e = off[L + 1];
-                double* cell = sums + (size_t)L * d + j;
-                const double old = on ? *cell : 0.0;
+                const int s = off[2 * L], mid = off[2 * L + 1], e = off[2 * L + 2];
+                double* tcell = sums + (size_t)L * d + j;
+                const double old = on ? __ldcg(tcell) : 0.0;
                 double a0 = 0.0, a1 = 0.0;
                 int p = s;
-                for (; p + 1 < e; p += 2) {
-                    a0 += (double)row[perm[p]];
-                    a1 += (double)row[perm[p + 1]];
+                for (; p + 1 < mid; p += 2) {
+                    a0 += (double)row[perm[p] ^ xo];
+                    a1 += (double)row[perm[p + 1] ^ xo];
                 }
-                if (p < e) a0 += (double)row[perm[p]];
-                if (on) *cell = old + (a0 + a1);
+                if (p < mid) a0 += (double)row[perm[p] ^ xo];
+                double m0 = 0.0;
+                for (p = mid; p < e; ++p) m0 += (double)row[perm[p] ^ xo];
+                if (on) __stcg(tcell, old + ((a0 + a1) - m0));
             }
         }
     }
@@ -242,12 +269,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
     const int t_begin = P.cta_tile_start[blockIdx.x], t_end = P.cta_tile_start[blockIdx.x + 1];
     if (t_begin >= t_end) return;
 
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);                                   // [W][S]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [W][S]
     CentreHeader* hdr = reinterpret_cast<CentreHeader*>(smem + P.off_hdr);
     float* table = reinterpret_cast<float*>(smem + P.off_table);
     int32_t* orig = reinterpret_cast<int32_t*>(smem + P.off_orig);
     int* wscr = reinterpret_cast<int*>(smem + P.off_scratch + (size_t)warp * P.scratch_bytes);
-    unsigned char* perm = reinterpret_cast<unsigned char*>(wscr + P.k_max + 2);
+    unsigned char* perm = reinterpret_cast<unsigned char*>(wscr + 2 * P.k_max + 2);
     float* slots = reinterpret_cast<float*>(smem + P.off_slots) + (size_t)warp * P.slots_per_warp * P.slot_floats;
     const int S = P.slots_per_warp;
 
@@ -258,7 +285,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
     __syncthreads();
     uint32_t phase = 0;  // bit s = parity the next wait on slot s expects
 
-    // problem containing the first tile
+    // this warp's private tables (global, L2-resident)
+    const size_t wtab = (size_t)blockIdx.x * W + warp;
+    double* my_sums = P.warp_sums ? P.warp_sums + wtab * P.part_stride : nullptr;
+    long long* my_counts = P.warp_counts ? P.warp_counts + wtab * P.k_max : nullptr;
+
     int p = 0;
     {
         int lo = 0, hi = P.n_problems - 1;
@@ -297,100 +328,134 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
         const bool trivial = hdr->trivial != 0, force_exact = hdr->force_exact != 0;
         const float tau_c = (2.5f * (float)(d + 4)) * 5.9604645e-8f + 7.6293945e-6f;  // fp32 dot bound + 5 masked bits (2*2^-18)
         const float cc2 = 2.0f * hdr->cc_max;
+        const int chunk0_kc = hdr->chunk_kc[0], chunk0_off = hdr->chunk_off[0];
         const uint32_t slot_bytes_tx = (uint32_t)d * (kSlotCells * 4);
-
-        // partial tables of this (cta, problem, warp)
-        const size_t tab = ((size_t)(blockIdx.x + p) * W + warp);
-        double* my_sums = P.part_sums ? P.part_sums + tab * P.part_stride : nullptr;
-        long long* my_counts = P.part_counts ? P.part_counts + tab * P.k_max : nullptr;
+        const bool delta = P.mode == kPassLloyd && pr.delta;
+        const bool need_old = (P.compare_old || P.mode == kPassSums || delta) && pr.labels;
         long long changed = 0;
 
         const int first = tile + warp;
         const int count = first < p_end ? (p_end - first + W - 1) / W : 0;
-        auto issue = [&](int i) {
-            const int s = i % S;
-            const int64_t cell0 = (int64_t)(first + i * W - pr.first_tile) * kSlotCells;
-            float* dst = slots + (size_t)s * P.slot_floats;
-            uint64_t* bar = &bars[warp * S + s];
-            if (lane == 0) mbar_expect_tx(bar, slot_bytes_tx);
-            __syncwarp();
-            for (int j = lane; j < d; j += 32) bulk_g2s(dst + j * kRowStride, pr.x + (size_t)j * pr.ld + cell0, kSlotCells * 4, bar);
+        auto issue = [&](int i) {   // ONE bulk-async copy: a tile is contiguous (and already swizzled) in HBM
+            if (lane == 0) {
+                const int s = i % S;
+                const size_t t_idx = (size_t)(first + i * W - pr.first_tile);
+                mbar_expect_tx(&bars[warp * S + s], slot_bytes_tx);
+                bulk_g2s(smem_u32(slots + (size_t)s * P.slot_floats), pr.x + t_idx * (size_t)(d * kSlotCells), slot_bytes_tx,
+                         smem_u32(&bars[warp * S + s]));
+            }
         };
         for (int i = 0; i < min(S, count); ++i) issue(i);
 
         for (int i = 0; i < count; ++i) {
             const int s = i % S;
             const int64_t cell0 = (int64_t)(first + i * W - pr.first_tile) * kSlotCells;
-            const int64_t mycell = cell0 + 4 * lane;
+            const int64_t mycell = cell0 + 2 * lane;
             const float* slot = slots + (size_t)s * P.slot_floats;
             // previous labels (the reference compares against the previous assignment, Clusterer.cpp:247)
-            int4 oldl = make_int4(0, 0, 0, 0);
-            const bool full4 = mycell + 3 < pr.n;
-            if ((P.compare_old || P.mode == kPassSums) && pr.labels) {
-                if (full4) oldl = *reinterpret_cast<const int4*>(pr.labels + mycell);
-                else {
-                    if (mycell + 0 < pr.n) oldl.x = pr.labels[mycell + 0];
-                    if (mycell + 1 < pr.n) oldl.y = pr.labels[mycell + 1];
-                    if (mycell + 2 < pr.n) oldl.z = pr.labels[mycell + 2];
-                }
+            int2 oldl = make_int2(0, 0);
+            const bool full2 = mycell + 1 < pr.n;
+            if (need_old) {
+                if (full2) oldl = *reinterpret_cast<const int2*>(pr.labels + mycell);
+                else if (mycell < pr.n) oldl.x = pr.labels[mycell];
             }
             mbar_wait(&bars[warp * S + s], (phase >> s) & 1u);
             phase ^= (1u << s);
 
-            int lab[4] = {0, 0, 0, 0};
+            int lab[2] = {0, 0};
             if (P.mode == kPassSums) {
-                lab[0] = oldl.x; lab[1] = oldl.y; lab[2] = oldl.z; lab[3] = oldl.w;
+                lab[0] = oldl.x;
+                lab[1] = oldl.y;
             } else if (!trivial) {
-                float xx[4] = {0.f, 0.f, 0.f, 0.f};
-                float best[4], second[4];
-                int bchunk[4] = {0, 0, 0, 0};
-#pragma unroll
-                for (int r = 0; r < 4; ++r) best[r] = second[r] = 3.3e38f;
-                dist_chunk_dispatch<true>(hdr->chunk_kc[0], slot, table + hdr->chunk_off[0], d, lane, xx, best, second);
+                float xx[2] = {0.f, 0.f};
+                float best[2] = {3.3e38f, 3.3e38f}, second[2] = {3.3e38f, 3.3e38f};
+                int bchunk[2] = {0, 0};
+                dist_chunk_dispatch<true>(chunk0_kc, slot, table + chunk0_off, d, lane, xx, best, second);
                 for (int q = 1; q < n_chunks; ++q) {
-                    float prev[4];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) prev[r] = best[r];
+                    const float prev0 = best[0], prev1 = best[1];
                     dist_chunk_dispatch<false>(hdr->chunk_kc[q], slot, table + hdr->chunk_off[q], d, lane, xx, best, second);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        if (best[r] < prev[r]) bchunk[r] = q;
+                    if (best[0] < prev0) bchunk[0] = q;
+                    if (best[1] < prev1) bchunk[1] = q;
                 }
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
+                for (int r = 0; r < 2; ++r) {
                     const int a = hdr->chunk_base[bchunk[r]] + (int)(__float_as_uint(best[r]) & 31u);
                     const float tau = tau_c * (xx[r] + cc2);
                     const bool sure = (second[r] - best[r] > tau) && !force_exact;
-                    if (sure) lab[r] = orig[a];
-                    else if (mycell + r < pr.n) {
-                        lab[r] = exact_label(slot, 4 * lane + r, d, pr.mu, orig, n_slots);
-                        if (P.recheck_count) atomicAdd(P.recheck_count, 1ULL);
+                    lab[r] = orig[a < n_slots ? a : 0];
+                    unsigned redo = __ballot_sync(0xffffffffu, !sure && (mycell + r < pr.n));
+                    if (redo && P.recheck_count && lane == 0) atomicAdd(P.recheck_count, (unsigned long long)__popc(redo));
+                    while (redo) {   // the whole warp re-decides each doubtful cell in fp64
+                        const int src = __ffs(redo) - 1;
+                        redo &= redo - 1;
+                        const int v = exact_label_warp(slot, 2 * src + r, d, pr.mu, orig, n_slots, lane);
+                        if (lane == src) lab[r] = v;
                     }
                 }
             }
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                if (mycell + r >= pr.n) lab[r] = -1;
-            if (P.compare_old) {
-                changed += (lab[0] >= 0 && lab[0] != oldl.x) + (lab[1] >= 0 && lab[1] != oldl.y) + (lab[2] >= 0 && lab[2] != oldl.z) +
-                           (lab[3] >= 0 && lab[3] != oldl.w);
-            }
+            if (mycell >= pr.n) lab[0] = -1;
+            if (mycell + 1 >= pr.n) lab[1] = -1;
+            const bool ch0 = lab[0] >= 0 && lab[0] != oldl.x, ch1 = lab[1] >= 0 && lab[1] != oldl.y;
+            if (P.compare_old) changed += (int)ch0 + (int)ch1;
             if (pr.labels && P.mode != kPassSums) {
-                if (full4) *reinterpret_cast<int4*>(pr.labels + mycell) = make_int4(lab[0], lab[1], lab[2], lab[3]);
-                else {
-                    if (lab[0] >= 0) pr.labels[mycell + 0] = lab[0];
-                    if (lab[1] >= 0) pr.labels[mycell + 1] = lab[1];
-                    if (lab[2] >= 0) pr.labels[mycell + 2] = lab[2];
-                }
+                if (full2) *reinterpret_cast<int2*>(pr.labels + mycell) = make_int2(lab[0], lab[1]);
+                else if (lab[0] >= 0) pr.labels[mycell] = lab[0];
             }
-            if (P.mode != kPassAssign) slot_sums(slot, lab, d, pr.k, lane, wscr, perm, my_sums, my_counts);
+            if (P.mode != kPassAssign) {
+                int key[4], cell[4];
+                cell[0] = cell[2] = 2 * lane;
+                cell[1] = cell[3] = 2 * lane + 1;
+                if (delta) {
+                    key[0] = ch0 ? 2 * lab[0] : -1;
+                    key[1] = ch1 ? 2 * lab[1] : -1;
+                    key[2] = ch0 ? 2 * oldl.x + 1 : -1;
+                    key[3] = ch1 ? 2 * oldl.y + 1 : -1;
+                } else {
+                    key[0] = lab[0] >= 0 ? 2 * lab[0] : -1;
+                    key[1] = lab[1] >= 0 ? 2 * lab[1] : -1;
+                    key[2] = key[3] = -1;
+                }
+                slot_contributions(slot, key, cell, d, pr.k, lane, wscr, perm, my_sums, my_counts);
+            }
             __syncwarp();
             if (i + S < count) issue(i + S);
         }
-        if (P.part_changed) {
+        // ---- combine the warps' tables of this (CTA, problem) in fixed order; reset them for the next range
+        if (P.cta_tables) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
-            if (lane == 0) P.part_changed[tab] = changed;
+            long long* s_changed = reinterpret_cast<long long*>(smem + P.off_hdr);  // header no longer needed
+            __threadfence();   // the warps' table updates are visible to the whole CTA
+            __syncthreads();
+            if (lane == 0) s_changed[warp] = changed;
+            __syncthreads();
+            const int64_t stride = P.part_stride;
+            const int64_t entries = stride + P.k_max + 1;
+            double* out = P.cta_tables + (size_t)(blockIdx.x + p) * entries;
+            const size_t wbase = (size_t)blockIdx.x * W;
+            for (int64_t e = threadIdx.x; e < entries; e += nthreads) {
+                double acc = 0.0;
+                if (e < stride) {
+                    if (P.warp_sums)
+                        for (int w = 0; w < W; ++w) {
+                            double* q = P.warp_sums + (wbase + w) * stride + e;
+                            acc += __ldcg(q);
+                            __stcg(q, 0.0);
+                        }
+                } else if (e < stride + P.k_max) {
+                    if (P.warp_counts)
+                        for (int w = 0; w < W; ++w) {
+                            long long* q = P.warp_counts + (wbase + w) * P.k_max + (e - stride);
+                            acc += (double)__ldcg(q);
+                            __stcg(q, 0LL);
+                        }
+                } else {
+                    long long t = 0;
+                    for (int w = 0; w < W; ++w) t += s_changed[w];
+                    acc = (double)t;
+                }
+                out[e] = acc;
+            }
         }
         tile = p_end;
         ++p;
@@ -400,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
 // ---------------------------------------------------------------------------------------------------
 // host side: shared-memory plan + launch
 // ---------------------------------------------------------------------------------------------------
-constexpr size_t kBarBytes = 256;  // kWarpsPerCta * 3 slots * 8 B mbarriers, rounded up
+constexpr size_t kBarBytes = 512;  // kWarpsPerCta * 3 slots * 8 B mbarriers, rounded up
 
 int plan_pass(int d, int k_max, PassPlan* plan) {
     if (d < 1 || k_max < 1 || k_max > kMaxKC * kMaxChunks - 2 * kMaxChunks) return 0;
@@ -409,8 +474,8 @@ int plan_pass(int d, int k_max, PassPlan* plan) {
     const int n_chunks = (k_max + kMaxKC - 1) / kMaxKC;
     const size_t table_bytes = ((size_t)(d + 1) * (k_max + 3 * n_chunks) * 4 + 127) & ~(size_t)127;
     const size_t orig_bytes = ((size_t)(k_max + 2 * n_chunks) * 4 + 127) & ~(size_t)127;
-    const size_t scratch = (((size_t)(k_max + 2) * 4 + kSlotCells) + 127) & ~(size_t)127;
-    const size_t hdr_bytes = (sizeof(CentreHeader) + 127) & ~(size_t)127;
+    const size_t scratch = (((size_t)(2 * k_max + 2) * 4 + 2 * kSlotCells) + 127) & ~(size_t)127;
+    const size_t hdr_bytes = std::max<size_t>((sizeof(CentreHeader) + 127) & ~(size_t)127, 8 * kWarpsPerCta);
     int W = kWarpsPerCta;
     for (; W >= 1; --W)
         if (kBarBytes + hdr_bytes + table_bytes + orig_bytes + (scratch + slot_bytes) * W <= (size_t)kSmemBudget) break;
@@ -442,13 +507,23 @@ int launch_fused_pass(const PassPlan& plan, PassParams P, int grid, cudaStream_t
     P.off_scratch = plan.off_scratch;
     P.scratch_bytes = plan.scratch_bytes;
     P.off_slots = plan.off_slots;
-    static size_t configured = 0;
-    if (plan.smem_bytes > configured) {
+    static bool configured = false;
+    if (!configured) {
         DPR_CUDA(cudaFuncSetAttribute(fused_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-        configured = kSmemBudget;
+        configured = true;
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx().time_passes) {
+        DPR_CUDA(cudaEventCreate(&e0));
+        DPR_CUDA(cudaEventCreate(&e1));
+        DPR_CUDA(cudaEventRecord(e0, stream));
     }
     fused_pass_kernel<<<grid, plan.warps * 32, plan.smem_bytes, stream>>>(P);
     count_launch();
+    if (e0) {
+        DPR_CUDA(cudaEventRecord(e1, stream));
+        ctx().pass_events.emplace_back(e0, e1);
+    }
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
 }

@@ -15,10 +15,10 @@ struct PassParams {
     int32_t mode;
     int32_t compare_old;            // count labels that differ from the previous ones
     int32_t k_max;                  // rows of the widest centre matrix (table strides)
-    int64_t part_stride;            // doubles per partial-sum table (k_max * d)
-    double* part_sums;              // [(grid + n_problems) * warps][k_max * d]   (Lloyd mode)
-    long long* part_counts;         // [(grid + n_problems) * warps][k_max]
-    long long* part_changed;        // [(grid + n_problems) * warps]
+    int64_t part_stride;            // doubles per sum table (k_max * d)
+    double* warp_sums;              // [grid * warps][k_max * d]   private per-warp tables (Lloyd / sums modes)
+    long long* warp_counts;         // [grid * warps][k_max]
+    double* cta_tables;             // [(grid + n_problems)][k_max*d + k_max + 1]: sums, counts, changed of each (CTA, problem)
     unsigned long long* recheck_count;  // diagnostics: cells decided by the fp64 path (nullable)
     // filled from the plan
     int32_t warps, slots_per_warp, slot_floats, off_hdr, off_table, off_orig, off_scratch, scratch_bytes, off_slots;

@@ -57,7 +57,6 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
         Problem& pr = h_problems[p];
         const ProblemSpec& s = specs[p];
         pr.x = s.x;
-        pr.ld = s.ld;
         pr.n = s.n;
         pr.d = d;
         pr.k = s.k;
@@ -85,13 +84,13 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
     DPR_TRY(alloc(&d_cta_start_, (size_t)grid + 1, false));
     DPR_CUDA(cudaMemcpyAsync(d_cta_start_, start.data(), sizeof(int32_t) * (grid + 1), cudaMemcpyHostToDevice, ctx().stream));
     DPR_TRY(alloc(&d_recheck, (size_t)1, true));
-    const size_t tables = (size_t)(grid + P) * plan.warps;
-    DPR_TRY(alloc(&part_changed_, tables, true));
-    n_seg = std::min(8, grid);
+    n_seg = std::min(16, grid);
     seg_entries = (int64_t)k_max_ * d + k_max_ + 1;
     if (want_sums) {
-        DPR_TRY(alloc(&part_sums_, tables * mu_sz, true));
-        DPR_TRY(alloc(&part_counts_, tables * k_max_, true));
+        const size_t wtabs = (size_t)grid * plan.warps;
+        DPR_TRY(alloc(&warp_sums_, wtabs * mu_sz, true));
+        DPR_TRY(alloc(&warp_counts_, wtabs * k_max_, true));
+        DPR_TRY(alloc(&cta_tables_, (size_t)(grid + P) * seg_entries, true));
         DPR_TRY(alloc(&seg, (size_t)P * n_seg * seg_entries, true));
         DPR_TRY(alloc(&d_n_active_, (size_t)1, true));
         DPR_CUDA(cudaMallocHost(&h_n_active_, sizeof(int32_t)));
@@ -127,19 +126,19 @@ int Session::pass(int mode, bool compare_old) {
     P.compare_old = compare_old ? 1 : 0;
     P.k_max = k_max_;
     P.part_stride = (int64_t)k_max_ * d_;
-    P.part_sums = part_sums_;
-    P.part_counts = part_counts_;
-    P.part_changed = part_changed_;
+    P.warp_sums = warp_sums_;
+    P.warp_counts = warp_counts_;
+    P.cta_tables = cta_tables_;
     P.recheck_count = d_recheck;
     return launch_fused_pass(plan, P, grid, ctx().stream);
 }
 
 int Session::reduce_and_finalize(int iter, int max_iter) {
-    DPR_TRY(launch_reduce_partials(d_problems, n_problems(), d_cta_start_, grid, plan.warps, k_max_, d_, part_sums_, part_counts_,
-                                   part_changed_, seg, n_seg, ctx().stream));
+    DPR_TRY(launch_reduce_partials(d_problems, n_problems(), d_cta_start_, grid, k_max_, d_, cta_tables_, seg, n_seg, ctx().stream));
     if (ctx().world > 1) DPR_TRY(comm_allreduce_sum_f64(seg, (size_t)n_problems() * n_seg * seg_entries));
     DPR_CUDA(cudaMemsetAsync(d_n_active_, 0, sizeof(int32_t), ctx().stream));
-    return launch_finalize(d_problems, n_problems(), seg, n_seg, k_max_, iter, max_iter, plan.table_floats_cap, d_n_active_, ctx().stream);
+    return launch_finalize(d_problems, n_problems(), seg, n_seg, k_max_, iter, max_iter, plan.table_floats_cap, allow_delta ? 1 : 0, d_n_active_,
+                           ctx().stream);
 }
 
 int Session::zero_labels() {

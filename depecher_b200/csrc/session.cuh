@@ -14,8 +14,8 @@
 namespace dpr {
 
 struct ProblemSpec {
-    const float* x;
-    int64_t ld, n;
+    const float* x;    // tile-major resident cells
+    int64_t n;
     int32_t k;
     double reg;
     int32_t no_zero;
@@ -50,6 +50,7 @@ public:
     unsigned long long* d_recheck = nullptr;   // cells decided by the fp64 path (diagnostics)
     int grid = 0;
     PassPlan plan{};
+    bool allow_delta = true;   // let finalize switch a problem to delta accumulation when few labels change
 
     // raw device buffers (exposed for the multi-GPU allreduce between reduce and finalize)
     double* seg = nullptr;
@@ -61,9 +62,9 @@ private:
     bool want_sums_ = false;
     std::vector<void*> owned_;
     int32_t* d_cta_start_ = nullptr;
-    double* part_sums_ = nullptr;
-    long long* part_counts_ = nullptr;
-    long long* part_changed_ = nullptr;
+    double* warp_sums_ = nullptr;
+    long long* warp_counts_ = nullptr;
+    double* cta_tables_ = nullptr;
     int32_t* d_n_active_ = nullptr;
     int32_t* h_n_active_ = nullptr;  // pinned
     template <typename T> int alloc(T** p, size_t count, bool zero);

@@ -53,6 +53,9 @@ int dpr_synchronize(void);
 int dpr_set_ari_mode(int32_t mode);      /* DPR_ARI_EXACT (default) | DPR_ARI_MONTE_CARLO */
 /* counters for bench/test evidence: kernels launched by this library since the last reset */
 int dpr_kernel_launches(int64_t* out, int32_t reset);
+/* bench evidence: with enable != 0 every launch of the fused pass is bracketed by CUDA events on the
+ * launching stream; the call returns (and resets) the summed duration and the number of launches. */
+int dpr_pass_timing(int32_t enable, double* ms_sum_out, int64_t* launches_out);
 
 /* ---- the four drop-in entry points (host buffers in, host buffers out) ------------------ */
 
@@ -88,8 +91,11 @@ int dpr_rand_index(const int32_t* a, const int32_t* b, int64_t n, uint32_t k, do
 int dpr_dataset_create(const double* X, int64_t n, int32_t d, dpr_dataset_t* out);
 int dpr_dataset_create_f32(const float* X, int64_t n, int32_t d, dpr_dataset_t* out);
 /* synthetic generator on device (bench only): G blobs, centre coords in {-a,0,a}, unit noise, / sd. */
+/* row0: global index of the first cell (row shards of one virtual matrix draw disjoint cells from the
+ * same mixture); scale: divisor applied to every value, 0 = this shard's own standard deviation; the
+ * divisor actually used is returned in *scale_out (nullable). */
 int dpr_dataset_create_synthetic(int64_t n, int32_t d, int32_t groups, double amplitude, uint64_t seed,
-                                 dpr_dataset_t* out);
+                                 int64_t row0, double scale, double* scale_out, dpr_dataset_t* out);
 int dpr_dataset_destroy(dpr_dataset_t ds);
 int dpr_dataset_shape(dpr_dataset_t ds, int64_t* n, int32_t* d);
 /* copy rows [row0, row0+rows) back as column-major doubles (tests / CPU baseline sample) */

@@ -171,9 +171,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        ids = [eng.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        eng.comm_init(rank, world, ids[0])
+        from depecher_b200 import shard
+        shard.init_comm(eng, dist, device=torch.device("cuda", local_rank))
 
     n_local = N_CELLS
     ds = eng.synthetic(n_local, D, GROUPS, AMP, SEED, row0=rank * n_local, scale=0.0)

@@ -227,6 +227,39 @@ class Engine:
         ari, ncl = np.array(ari), np.array(ncl)
         return {"d": ari, "z": ari, "n": ncl, "m": ncl, "c": centers}
 
+    def grid_search_each(self, X, k, reg, iterations, bootstrapSamples, seed_off_set=0) -> dict:
+        """`iterations` workers' grid_search(X, k, reg, 1, bootstrapSamples, .) results as one batch (R/depechePenaltyOpt.R:50-55):
+        z, m: lists (one per worker) of nk x nreg matrices; c: per worker, per (k, penalty) the list [ret1, ret2, ret1, ret2]."""
+        k = _i32(np.atleast_1d(k))
+        reg = np.ascontiguousarray(np.atleast_1d(reg), dtype=np.float64)
+        nk, nreg, iterations = len(k), len(reg), int(iterations)
+        ari = np.empty((iterations, nreg, nk), np.float64)
+        ncl = np.empty((iterations, nreg, nk), np.float64)
+        ds, own = self._as_ds(X)
+        try:
+            cen = np.empty(iterations * nreg * 2 * ds.d * int(k.sum()), np.float64)
+            self._chk(self.lib.dpr_dataset_grid_search_each(ds.handle, _ptr(k, _ip), C.c_int32(nk), _ptr(reg, _dp), C.c_int32(nreg),
+                                                            C.c_uint32(iterations), C.c_uint32(bootstrapSamples), C.c_uint64(seed_off_set),
+                                                            _ptr(ari, _dp), _ptr(ncl, _dp), _ptr(cen, _dp)))
+            d = ds.d
+        finally:
+            if own:
+                ds.close()
+        z = [ari[w].T.copy() for w in range(iterations)]
+        m = [ncl[w].T.copy() for w in range(iterations)]
+        c, off = [], 0
+        for _w in range(iterations):
+            per = []
+            for kj in k:
+                for _l in range(nreg):
+                    mats = []
+                    for _q in range(2):
+                        mats.append(np.array(cen[off:off + kj * d].reshape((kj, d), order="F")))
+                        off += kj * d
+                    per.append(mats + mats)
+            c.append(per)
+        return {"d": z, "z": z, "n": m, "m": m, "c": c}
+
     def rand_index(self, inds1, inds2, k) -> float:
         """rand_index(inds1, inds2, k) -> double   (src/InterfaceUtils.cpp:151-161)"""
         a, b = _i32(inds1), _i32(inds2)

@@ -565,9 +565,11 @@ int dpr_rand_index(const int32_t* a, const int32_t* b, int64_t n, uint32_t k, do
 // batch of problems (every launch serves all of them), then the 2 * ... scoring assignments of the full data
 // run as one batch, then one batched ARI launch.  The two extra allocations of the reference whose results
 // are discarded (:373-374) are not performed.
-int dpr_dataset_grid_search(dpr_dataset_t ds, const int32_t* k, int32_t nk, const double* reg, int32_t nreg, uint32_t iterations,
-                            uint32_t boot_n, uint64_t seed, double* ari_out, double* nclust_out, double* centers_out) {
-    if (!ds || !k || !reg || !ari_out || !nclust_out || nk < 1 || nreg < 1 || iterations < 1 || boot_n < 1)
+}  // extern "C"
+
+static int grid_search_impl(dpr_dataset_t ds, const int32_t* k, int32_t nk, const double* reg, int32_t nreg, uint32_t iterations,
+                            uint32_t boot_n, uint64_t seed, double* ari_each, double* nclust_each, double* centers_out) {
+    if (!ds || !k || !reg || !ari_each || !nclust_each || nk < 1 || nreg < 1 || iterations < 1 || boot_n < 1)
         return fail(DPR_ERR_INVALID, "grid_search: bad arguments");
     for (int j = 0; j < nk; ++j)
         if (k[j] < 2) return fail(DPR_ERR_INVALID, "grid_search: every k must be >= 2");
@@ -635,16 +637,15 @@ int dpr_dataset_grid_search(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
         pairs[c] = PairJob{sspecs[2 * c].labels, sspecs[2 * c + 1].labels, ds->n, (uint32_t)c};
     std::vector<double> ari(cells);
     DPR_TRY(run_ari(pairs, (uint32_t)kmax, seed, ari.data()));
-    // 5. reduce over iterations like the reference (:387-390)
-    for (int e = 0; e < nk * nreg; ++e) ari_out[e] = nclust_out[e] = 0.0;
+    // 5. per-iteration results: ARI of the cell and the mean number of used clusters of its two fits
     size_t coff = 0;
     for (int c = 0; c < cells; ++c) {
-        const int l = c % nreg, j = (c / nreg) % nk;
-        ari_out[(size_t)l * nk + j] += ari[c];
+        const int l = c % nreg, j = (c / nreg) % nk, it = c / (nreg * nk);
+        const size_t o = (size_t)it * nk * nreg + (size_t)l * nk + j;
+        ari_each[o] = ari[c];
+        int used = 0;
         for (int w = 0; w < 2; ++w) {
-            int used = 0;
             for (int q = 0; q < k[j]; ++q) used += counts[(size_t)(2 * c + w) * fits.k_max() + q] > 0;
-            nclust_out[(size_t)l * nk + j] += used;
             if (centers_out) {
                 std::vector<double> rm((size_t)k[j] * d);
                 DPR_TRY(fits.get_centres(2 * c + w, rm.data()));
@@ -652,12 +653,36 @@ int dpr_dataset_grid_search(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
                 coff += (size_t)k[j] * d;
             }
         }
-    }
-    for (int e = 0; e < nk * nreg; ++e) {
-        ari_out[e] /= iterations;
-        nclust_out[e] /= (iterations * 2);
+        nclust_each[o] = used / 2.0;
     }
     return DPR_OK;
+}
+
+extern "C" {
+
+// reference-shaped result: the mean over iterations (distances/iterations, found_cluster/(iterations*2), :387-390)
+int dpr_dataset_grid_search(dpr_dataset_t ds, const int32_t* k, int32_t nk, const double* reg, int32_t nreg, uint32_t iterations,
+                            uint32_t boot_n, uint64_t seed, double* ari_out, double* nclust_out, double* centers_out) {
+    if (!ari_out || !nclust_out || nk < 1 || nreg < 1 || iterations < 1) return fail(DPR_ERR_INVALID, "grid_search: bad arguments");
+    const size_t m = (size_t)nk * nreg;
+    std::vector<double> a(m * iterations), c(m * iterations);
+    DPR_TRY(grid_search_impl(ds, k, nk, reg, nreg, iterations, boot_n, seed, a.data(), c.data(), centers_out));
+    for (size_t e = 0; e < m; ++e) {
+        double sa = 0.0, sc = 0.0;
+        for (uint32_t it = 0; it < iterations; ++it) {
+            sa += a[it * m + e];
+            sc += 2.0 * c[it * m + e];
+        }
+        ari_out[e] = sa / iterations;
+        nclust_out[e] = sc / (iterations * 2);
+    }
+    return DPR_OK;
+}
+// one result per iteration: what the reference obtains from `iterations` separate worker processes that each
+// call grid_search(..., iterations = 1, ...) (R/depechePenaltyOpt.R:50-55), computed as one batch
+int dpr_dataset_grid_search_each(dpr_dataset_t ds, const int32_t* k, int32_t nk, const double* reg, int32_t nreg, uint32_t iterations,
+                                 uint32_t boot_n, uint64_t seed, double* ari_each, double* nclust_each, double* centers_out) {
+    return grid_search_impl(ds, k, nk, reg, nreg, iterations, boot_n, seed, ari_each, nclust_each, centers_out);
 }
 int dpr_grid_search(const double* X, int64_t n, int32_t d, const int32_t* k, int32_t nk, const double* reg, int32_t nreg,
                     uint32_t iterations, uint32_t boot_n, uint64_t seed, double* ari_out, double* nclust_out, double* centers_out) {

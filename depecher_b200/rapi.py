@@ -1,0 +1,408 @@
+"""Host-side mirror of the reference's R callers of the hot path (names, arguments and results as in R).
+
+The reference drives its C++ engine from R (`depeche()` -> `depechePenaltyOpt()` -> `grid_search`,
+`depecheAllData()` -> `sparse_k_means`, `depecheClusterCenterSelection()` / `dAllocate()` ->
+`allocate_points`, `rand_index`).  R is not part of this image, so the same control flow is restated here
+in Python over the C ABI; every function cites the R lines it follows.  The state machine is unchanged;
+what changes is the fan-out: the reference starts `nCores` SOCK worker processes per set and ships the data
+matrix to each (R/depechePenaltyOpt.R:37-38,50-54) — here one call runs all workers' fits as one batch on
+the GPU from a matrix that stays resident in HBM.
+
+`engine` is anything with the four entry points of the reference (`grid_search`, `sparse_k_means`,
+`allocate_points`, `rand_index`, results keyed like the Rcpp lists).  The default is the CUDA engine
+(`depecher_b200.Engine`), which fails loudly without a B200; tests inject a CPU oracle engine to check the
+host logic on machines without a GPU.
+"""
+from __future__ import annotations
+
+import math
+import os
+import warnings
+
+import numpy as np
+
+__all__ = ["depeche", "dAllocate", "depechePenaltyOpt", "dOptPenalty", "depecheAllData", "depecheClusterCenterSelection",
+           "depecheLogCenterSd", "depecheGroundCenters", "generateBimodalData", "generateSparseData", "default_ncores"]
+
+
+# --------------------------------------------------------------------------------------------------------
+# fixtures: R/simulateData.R
+# --------------------------------------------------------------------------------------------------------
+def generateBimodalData(centers=None, prop=0.3, dataCols=5, observations=10000, rng=None):
+    """R/simulateData.R:8-36: two unit-variance blobs at runif+50 / runif-50, `prop` of the rows in the first."""
+    rng = rng or np.random.default_rng()
+    if centers is None:
+        centers = np.vstack([rng.random(dataCols) + 50, rng.random(dataCols) - 50])
+    centers = np.asarray(centers, float)
+    dataCols = centers.shape[1]
+    n1 = int(math.floor(prop * observations))
+    ids = np.r_[np.full(n1, 1), np.full(observations - n1, 2)]
+    rands = rng.normal(size=(observations, dataCols))
+    samples = np.vstack([rands[:n1] + centers[0], rands[n1:] + centers[1]])
+    return {"samples": samples, "ids": ids}
+
+
+def generateSparseData(modeN=5, dataCols=100, observations=10000, rng=None):
+    """R/simulateData.R:47-80: modeN blobs at +-50 per coordinate, blob i has i coordinates set to 0."""
+    rng = rng or np.random.default_rng()
+    if observations % modeN:
+        raise ValueError("Observations has to be divisible by modeN")
+    per = observations // modeN
+    centers = rng.choice([-50.0, 50.0], size=(modeN, dataCols))
+    for i in range(modeN):
+        centers[i, rng.choice(dataCols, size=i + 1, replace=False)] = 0.0
+    samples = np.zeros((observations, dataCols))
+    ids = np.zeros(observations, int)
+    for i in range(modeN):
+        samples[i * per:(i + 1) * per] = rng.normal(size=(per, dataCols)) + centers[i]
+        ids[i * per:(i + 1) * per] = i + 1
+    return {"samples": samples, "ids": ids, "centers": centers}
+
+
+# --------------------------------------------------------------------------------------------------------
+# pre-scaling: R/depecheLogCenterSd.R, R/dScaleCoFunction.R:74-99
+# --------------------------------------------------------------------------------------------------------
+def _r_pretty(lo: float, hi: float, n: int, min_n: int = 1):
+    """R's pretty.default(c(lo, hi), n, min.n): 'nice' breakpoints (1, 2, 5 x 10^k) covering [lo, hi]."""
+    h, h5, eps = 1.5, 0.5 + 1.5 * 1.5, 1e-10
+    dx = hi - lo
+    if dx == 0 and hi == 0:
+        cell, i_small = 1.0, True
+    else:
+        cell = max(abs(lo), abs(hi))
+        U = 1 + (1 / (1 + h) if h5 >= 1.5 * h + 0.5 else 1.5 / (1 + h5))
+        U *= max(1, n) * np.finfo(float).eps
+        i_small = dx < cell * U * 3
+    if i_small:
+        if cell > 10:
+            cell = 9 + cell / 10
+        cell *= 1e-7 * 3     # shrink_sml default
+        if min_n > 1:
+            cell /= min_n
+    else:
+        cell = dx
+        if n > 1:
+            cell /= n
+    cell = max(cell, 20 * np.finfo(float).tiny)
+    base = 10.0 ** math.floor(math.log10(cell))
+    unit = base
+    if 2 * base - cell < h * (cell - unit):
+        unit = 2 * base
+        if 5 * base - cell < h5 * (cell - unit):
+            unit = 5 * base
+            if 10 * base - cell < h * (cell - unit):
+                unit = 10 * base
+    ns, nu = math.floor(lo / unit + 1e-7), math.ceil(hi / unit - 1e-7)
+    while ns * unit > lo + eps * unit:
+        ns -= 1
+    while nu * unit < hi - eps * unit:
+        nu += 1
+    k = int(0.5 + nu - ns)
+    if k < min_n:
+        k = min_n - k
+        if ns >= 0:
+            nu += k // 2
+            ns -= k // 2 + k % 2
+        else:
+            ns -= k // 2
+            nu += k // 2 + k % 2
+    return np.arange(ns, nu + 1) * unit
+
+
+def _peak_center(x: np.ndarray) -> float:
+    """dScaleCoFunction.R:74-88: mid of the fullest bin of hist(x, breaks = n/50 (10 below 500 rows))."""
+    n_breaks = 10 if len(x) < 500 else len(x) / 50
+    br = _r_pretty(float(x.min()), float(x.max()), int(n_breaks), 1)
+    # hist.default: right-closed bins, lowest value included in the first
+    idx = np.searchsorted(br, x, side="left") - 1
+    idx[idx < 0] = 0
+    counts = np.bincount(idx, minlength=len(br) - 1)[:len(br) - 1]
+    b = int(np.argmax(counts))          # match(max(counts), counts): first maximum
+    return float((br[b] + br[b + 1]) / 2)
+
+
+def depecheLogCenterSd(X, log2Off=False, center="default", scale=True):
+    """R/depecheLogCenterSd.R:6-115 -> (scaled matrix, [log2 applied, centres | False, sd])."""
+    X = np.array(X, dtype=np.float64)
+    info = [False, False, 1]
+    flat = X.ravel()
+    kurt = len(flat) * np.sum((flat - flat.mean()) ** 4) / np.sum((flat - flat.mean()) ** 2) ** 2   # moments::kurtosis
+    if not log2Off and kurt > 100:                                                            # :11-45
+        if X.min() >= 0:
+            X = np.log2(X + 1)
+        else:
+            X = np.log2(X - X.min(axis=0) + 1)
+            X[np.isnan(X)] = 0
+        info[0] = True
+    d = X.shape[1]
+    if isinstance(center, str):
+        if center == "peak" or (center == "default" and d <= 100):                             # :49-63
+            c = np.array([_peak_center(X[:, j]) for j in range(d)])
+        elif center == "mean" or (center == "default" and d > 100):                            # :64-78
+            c = X.mean(axis=0)
+        else:
+            raise ValueError("center must be 'default', 'peak', 'mean', False or a vector")
+        X = X - c
+        info[1] = c
+    elif center is False:                                                                      # :95-98
+        pass
+    else:                                                                                      # :79-94
+        c = np.asarray(center, float)
+        if len(c) != d:
+            raise ValueError("Mismatch between the number of columns and the length of the centering vector")
+        X = X - c
+        info[1] = c
+    if scale is True:                                                                          # :102-106
+        sd = float(np.std(X, ddof=1))
+        X = X / sd
+        info[2] = sd
+    elif scale is not False:
+        X = X / float(scale)
+        info[2] = float(scale)
+    return X, info
+
+
+def depecheGroundCenters(reduced, logCenterSd):
+    """R/depecheGroundCenters.R:7-28: un-scale the centres (x sd, + centre); exact zeros stay zero."""
+    reduced = np.asarray(reduced, float)
+    out = reduced * logCenterSd[2]
+    if logCenterSd[1] is not False:
+        out = out + np.asarray(logCenterSd[1], float)[None, :]
+        out[reduced == 0] = 0
+    return out
+
+
+def default_ncores() -> int:
+    """R/depeche.R:169-174"""
+    return max(1, min(10, int(math.floor((os.cpu_count() or 1) * 0.875))))
+
+
+def _engine(engine):
+    if engine is not None:
+        return engine
+    from . import Engine
+    return Engine()
+
+
+# --------------------------------------------------------------------------------------------------------
+# dAllocate: R/dAllocate.R:62-137
+# --------------------------------------------------------------------------------------------------------
+def _reduce_centres(cc):
+    """rows with rowSums != 0, columns with colSums != 0 (R/dAllocate.R:99-103)"""
+    rows = np.flatnonzero(cc.sum(axis=1) != 0)
+    cols = np.flatnonzero(cc.sum(axis=0) != 0)
+    return rows, cols
+
+
+def dAllocate(inDataFrame, depModel, engine=None, columns=None):
+    """Allocate cells to a fitted model; returns 1-based labels into the reduced centre matrix.
+
+    `columns`: when the centre matrix carries column names in R (model from depeche()), the data keeps
+    exactly those columns (:112-114); pass their indices.  Otherwise zero-sum columns are dropped (:115-118)."""
+    eng = _engine(engine)
+    cc = np.asarray(depModel["clusterCenters"], float)
+    lcs = depModel.get("logCenterSd", False)
+    X = inDataFrame
+    if isinstance(lcs, (list, tuple)):
+        if lcs[0]:
+            raise ValueError("dAllocate does not work well with data that has been internally log-transformed")   # :71-79
+        X, _ = depecheLogCenterSd(np.asarray(X, float), True, lcs[1] if lcs[1] is not False else False, lcs[2])  # :81-85
+        ccs, _ = depecheLogCenterSd(cc, True, lcs[1] if lcs[1] is not False else False, lcs[2])                  # :86-90
+        ccs[cc == 0] = 0
+        cc = ccs
+    rows, cols = _reduce_centres(cc)
+    red = cc[np.ix_(rows, cols)]
+    if columns is not None:
+        Xr = np.asarray(X)[:, columns] if not hasattr(X, "handle") else X
+    elif hasattr(X, "handle"):
+        Xr = X                                    # resident dataset: zero-sum columns stay (they add the same to every distance)
+        red = cc[rows]
+    else:
+        Xr = np.asarray(X)[:, cols]
+    if red.ndim == 1:
+        red = red[None, :]
+    return eng.allocate_points(Xr, red, 1)["i"].astype(np.int64) + 1             # :127-134
+
+
+# --------------------------------------------------------------------------------------------------------
+# depechePenaltyOpt (and its legacy twin dOptPenalty): R/depechePenaltyOpt.R:14-265
+# --------------------------------------------------------------------------------------------------------
+def _sd(v):
+    v = np.asarray(v, float)
+    return float(np.std(v, ddof=1)) if len(v) > 1 else float("nan")
+
+
+def depechePenaltyOpt(inDataFrameUsed, k, maxIter, minARIImprovement, sampleSize, penalties, createOutput=False, disableWarnings=False,
+                      optimARI=0.95, nCores=None, plotDir=".", engine=None, seed=0, verbose=False):
+    eng = _engine(engine)
+    nCores = nCores or default_ncores()
+    X = inDataFrameUsed
+    d = X.d if hasattr(X, "handle") else np.asarray(X).shape[1]
+    penalties = np.asarray(penalties, float)
+    penaltyConstant = sampleSize * math.sqrt(d) / 1450.0                                       # :22
+    realPenalties = penalties * penaltyConstant
+    roundPenalties = np.round(penalties, 1)
+    it, lastStd, stdChange, iterTimesNCores = 1, 1.0, 1.0, 1
+    usedPos = np.arange(len(penalties))
+    full = []          # one entry per worker-iteration: {penalty position -> (ARI, nClust, [ret1 centres, ret2 centres])}
+    while iterTimesNCores < 20 or (iterTimesNCores < maxIter and stdChange >= minARIImprovement):     # :47-48
+        # nCores workers x grid_search(dataMat, k, usedPenalties, 1, sampleSize, i)  (:50-55) as ONE batched call
+        res = eng.grid_search_each(X, [k], realPenalties[usedPos], nCores, sampleSize, seed + 7919 * it)
+        for w in range(nCores):
+            ari = np.array(res["z"][w]).ravel()
+            ncl = np.array(res["m"][w]).ravel()
+            ari = np.where(ncl == 1, 0.0, ari)                                                 # :75-78
+            full.append({int(p): (ari[q], ncl[q], res["c"][w][q][:2]) for q, p in enumerate(usedPos)})
+        ariVecs = [[e[p][0] for e in full if p in e] for p in range(len(penalties))]           # :89-97 (keyed by position)
+        meanARI = np.array([np.mean(v) if v else np.nan for v in ariVecs])
+        stdOpt = np.array([_sd(v) if v else np.nan for v in ariVecs])
+        maxPos = int(np.nanargmax(meanARI))                                                    # :103
+        meanMinus2StdMax = meanARI[maxPos] - 2 * stdOpt[maxPos]
+        meanPlus2StdAll = meanARI + 2 * stdOpt
+        localIter = min(it, 3)
+        k1, k2 = (2, 1, 0)[localIter - 1], (4, 3, 2)[localIter - 1]                            # :123-125
+        with np.errstate(invalid="ignore"):
+            keep = (meanPlus2StdAll >= meanMinus2StdMax - k1 * stdOpt[maxPos]) | (meanARI >= np.nanmax(meanARI) - (1 - optimARI) * k2)
+        usedPos = np.array([p for p in usedPos if keep[p]], dtype=int)                         # :126-140
+        if len(usedPos) > 1:                                                                   # :145-154
+            stdChange = ((lastStd - stdOpt[maxPos]) / lastStd) / math.sqrt(it * nCores) if lastStd != 0 else 0.0
+            if np.isnan(stdChange):
+                stdChange = 0.0
+        else:
+            stdChange = 0.0
+        lastStd = stdOpt[maxPos]
+        iterTimesNCores = it * nCores
+        if verbose:
+            print(f"Set {it} with {nCores} iterations completed; {len(usedPos)} penalties kept")
+        it += 1
+    if it * nCores >= maxIter and stdChange > minARIImprovement and not disableWarnings:        # :173-177
+        warnings.warn("The maximum number of iterations was reached before stable optimal solution was found")
+    with np.errstate(invalid="ignore"):
+        optimal = np.flatnonzero(meanARI >= np.nanmax(meanARI) - (1 - optimARI))               # :184-185
+    bestPos = int(optimal[int(round(np.mean(np.arange(1, len(optimal) + 1)))) - 1])            # :192 (R rounds half to even, like Python)
+    bestPenalty = float(roundPenalties[bestPos])
+    if len(penalties) > 1 and not disableWarnings:                                             # :196-207
+        if bestPos == 0:
+            warnings.warn("The lowest penalty was the most optimal in the range.")
+        if bestPos == len(penalties) - 1:
+            warnings.warn("The highest penalty was the most optimal in the range.")
+    meanClust = np.array([np.nanmean([e[p][1] for e in full if p in e]) if any(p in e for e in full) else np.nan
+                          for p in range(len(penalties))])                                     # :242-249
+    bestCenters = [c for e in full if bestPos in e for c in e[bestPos][2]]                     # :255-258
+    return {"bestPenalty": bestPenalty, "bestPenaltyPosition": bestPos,
+            "meanOptimDf": {"penalty": roundPenalties, "ARI": meanARI, "nClust": meanClust},
+            "bestClusterCenters": bestCenters, "workerIterations": (it - 1) * nCores}
+
+
+dOptPenalty = depechePenaltyOpt       # R/dOptPenalty.R is the same function under its old name
+
+
+# --------------------------------------------------------------------------------------------------------
+# depecheAllData: R/depecheAllData.R:14-79   (fewer than 10 000 rows)
+# --------------------------------------------------------------------------------------------------------
+def depecheAllData(inDataFrameUsed, penalty, k, nCores=None, engine=None, seed=0):
+    eng = _engine(engine)
+    X = inDataFrameUsed
+    n, d = (X.n, X.d) if hasattr(X, "handle") else np.asarray(X).shape
+    reg = penalty * (n * math.sqrt(d)) / 1450.0                                               # :15-16
+    runs = [eng.sparse_k_means(X, int(round(k * 3)), reg, 1, seed + i) for i in range(1, 22)]  # :30-31
+    logMaxLik = np.array([r["n"] for r in runs])
+    nClust = np.array([int(((r["c"] != 0).sum(axis=1) != 0).sum()) for r in runs])            # :37-40
+    ok = logMaxLik[nClust > 1]
+    maxN = ok.max()
+    best = runs[int(np.flatnonzero(logMaxLik == maxN)[0])]                                     # :42-44
+    cc = best["c"]
+    rows, cols = _reduce_centres(cc)                                                           # :56-59
+    return {"clusterVector": best["i"].astype(np.int64), "clusterCenters": cc[np.ix_(rows, cols)], "rows": rows, "cols": cols}
+
+
+# --------------------------------------------------------------------------------------------------------
+# depecheClusterCenterSelection: R/depecheClusterCenterSelection.R:7-59   (10 000 rows or more)
+# --------------------------------------------------------------------------------------------------------
+def depecheClusterCenterSelection(allSolutions, selectionDataSet, k, nCores=None, engine=None):
+    eng = _engine(engine)
+    if hasattr(eng, "allocate_many"):
+        # every solution's dAllocate (:11-16) and all rand_index pairs (:24-29) in one pass over the selection set.
+        # dAllocate drops zero-sum rows; the labels it returns index the kept rows, 1-based.
+        masked = []
+        for s in allSolutions:
+            m = np.array(s, float)
+            m[m.sum(axis=1) == 0] = 0.0
+            masked.append(m)
+        _, ari = eng.allocate_many(selectionDataSet, masked, True, want_labels=False, want_ari=True)
+        meanARI = ari.mean(axis=0)
+    else:
+        alloc = [dAllocate(selectionDataSet, {"clusterCenters": s, "logCenterSd": False}, engine=eng) for s in allSolutions]
+        meanARI = np.array([np.mean([eng.rand_index(a, alloc[i], k) for a in alloc]) for i in range(len(alloc))])
+    best = np.asarray(allSolutions[int(np.flatnonzero(meanARI == np.nanmax(meanARI))[0])], float)  # :35-37
+    rows, cols = _reduce_centres(best)                                                         # :41-45
+    return {"clusterCenters": best[np.ix_(rows, cols)], "rows": rows, "cols": cols, "meanARI": meanARI}
+
+
+# --------------------------------------------------------------------------------------------------------
+# depeche: R/depeche.R:127-294
+# --------------------------------------------------------------------------------------------------------
+def depeche(inDataFrame, samplingSubset=None, penalties=None, sampleSize="default", selectionSampleSize="default", k=30,
+            minARIImprovement=0.01, optimARI=0.95, maxIter=100, log2Off=False, center="default", scale=True, nCores="default",
+            plotDir=".", createOutput=False, engine=None, seed=0, verbose=False):
+    eng = _engine(engine)
+    rng = np.random.default_rng(seed)
+    X = np.asarray(inDataFrame, float)
+    if penalties is None:
+        penalties = 2.0 ** np.arange(0, 5.5, 0.5)                                              # :128
+    Xs, logCenterSd = depecheLogCenterSd(X, log2Off, center, scale)                             # :141
+    if samplingSubset is None:
+        samplingSubset = np.arange(len(Xs))
+    if len(samplingSubset) > 1e6:                                                               # :150-156
+        warnings.warn("This dataset is very large; the reference recommends fitting on a sampling subset and allocating the rest with dAllocate")
+    used = Xs[samplingSubset]
+    if sampleSize == "default":
+        sampleSize = len(used) if len(used) <= 10000 else 10000                                 # :161-167
+    if nCores == "default":
+        nCores = default_ncores()                                                               # :169-174
+    use_ds = hasattr(eng, "dataset")
+    ds_used = eng.dataset(used) if use_ds else used                                             # resident for the whole search (SURVEY f-2)
+    try:
+        opt = depechePenaltyOpt(ds_used, k=k, maxIter=maxIter, sampleSize=sampleSize, penalties=penalties, createOutput=createOutput,
+                                minARIImprovement=minARIImprovement, optimARI=optimARI, nCores=nCores, plotDir=plotDir, engine=eng,
+                                seed=seed, verbose=verbose)                                    # :176-184
+        if selectionSampleSize == "default":
+            selectionSampleSize = sampleSize
+        if len(used) < 10000:                                                                   # :207-215
+            r = depecheAllData(ds_used, penalty=opt["bestPenalty"], k=k, nCores=nCores, engine=eng, seed=seed + 104729)
+            clusterVector, reduced, cols = r["clusterVector"], r["clusterCenters"], r["cols"]
+        else:
+            if len(used) <= selectionSampleSize:                                                # :191-199
+                sel = used
+            else:
+                sel = used[rng.integers(0, len(used), selectionSampleSize)]
+            r = depecheClusterCenterSelection(opt["bestClusterCenters"], sel, k, nCores, engine=eng)   # :222-225
+            reduced, cols = r["clusterCenters"], r["cols"]
+            ds_all = ds_used if (use_ds and len(samplingSubset) == len(Xs)) else (eng.dataset(Xs[:, cols]) if use_ds else Xs[:, cols])
+            full_cc = np.zeros((reduced.shape[0], Xs.shape[1]))
+            full_cc[:, cols] = reduced
+            model_cc = full_cc if ds_all is ds_used else reduced
+            clusterVector = dAllocate(ds_all, {"clusterCenters": model_cc, "logCenterSd": False}, engine=eng)   # :228-232
+            if use_ds and ds_all is not ds_used:
+                ds_all.close()
+    finally:
+        if use_ds:
+            ds_used.close()
+    # clusters renumbered by size (:236-252)
+    labels, counts = np.unique(clusterVector, return_counts=True)
+    order = labels[np.argsort(-counts, kind="stable")]
+    newVec = np.zeros_like(clusterVector)
+    rank_of_label = {}
+    for i, lab in enumerate(order, start=1):
+        newVec[clusterVector == lab] = i
+        rank_of_label[lab] = i
+    sortedLabels = np.sort(order)
+    if len(sortedLabels) == reduced.shape[0]:
+        reduced = reduced[np.argsort([rank_of_label[l] for l in sortedLabels])]
+    ground = depecheGroundCenters(reduced, [logCenterSd[0], (np.asarray(logCenterSd[1])[cols] if logCenterSd[1] is not False else False),
+                                            logCenterSd[2]])                                   # :262-263
+    essence = [list(np.asarray(cols)[np.flatnonzero(reduced[i] != 0)]) for i in range(reduced.shape[0])]   # :266-271
+    return {"clusterVector": newVec, "clusterCenters": ground, "scaledClusterCenters": reduced, "columns": np.asarray(cols),
+            "essenceElementList": essence, "penaltyOptList": {"bestPenalty": opt["bestPenalty"], "allPenalties": opt["meanOptimDf"],
+                                                              "workerIterations": opt["workerIterations"]},
+            "logCenterSd": logCenterSd}

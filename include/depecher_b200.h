@@ -109,6 +109,13 @@ int dpr_dataset_sparse_k_means(dpr_dataset_t ds, uint32_t k, double reg, int32_t
 int dpr_dataset_grid_search(dpr_dataset_t ds, const int32_t* k, int32_t nk, const double* reg, int32_t nreg,
                             uint32_t iterations, uint32_t boot_n, uint64_t seed, double* ari_out,
                             double* nclust_out, double* centers_out);
+/* The same work with one result per iteration instead of their mean: ari_each/nclust_each hold `iterations`
+ * matrices (nk x nreg col-major, iteration-major).  This is what the reference gets from `iterations` separate
+ * SOCK worker processes each calling grid_search(..., iterations = 1, ...) (R/depechePenaltyOpt.R:50-55);
+ * here all of them are one batch of problems on the device. */
+int dpr_dataset_grid_search_each(dpr_dataset_t ds, const int32_t* k, int32_t nk, const double* reg, int32_t nreg,
+                                 uint32_t iterations, uint32_t boot_n, uint64_t seed, double* ari_each,
+                                 double* nclust_each, double* centers_out);
 
 /* ---- stage-level entry points (parity hooks; each is one deterministic stage of the reference) ----- */
 

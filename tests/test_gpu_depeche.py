@@ -1,0 +1,75 @@
+"""GPU end-to-end: the reference's hot-path testthat properties and its stored depeche(testData[, 2:15]) result,
+through the Python mirror of the R callers over the CUDA library."""
+import numpy as np
+import pytest
+
+from depecher_b200 import rapi
+
+pytestmark = pytest.mark.gpu
+
+
+def test_depeche_bimodal(engine):
+    """test_depeche.R:4-10"""
+    x = rapi.generateBimodalData(observations=100, dataCols=150, rng=np.random.default_rng(1))
+    out = rapi.depeche(x["samples"], maxIter=8, nCores=2, engine=engine, seed=3)
+    cv = out["clusterVector"]
+    assert cv.max() == 2
+    assert np.array_equal(x["ids"], cv) or np.array_equal(x["ids"] % 2 + 1, cv)
+
+
+def test_depeche_sparsity(engine):
+    """test_depeche.R:14-26 with the reference's own sizes: 500 cells x 100 markers, 5 modes, K = 3k = 90"""
+    x = rapi.generateSparseData(observations=500, rng=np.random.default_rng(2))
+    out = rapi.depeche(x["samples"], maxIter=8, nCores=2, center=False, engine=engine, seed=5)
+    binTruth = x["centers"] == 0
+    binGot = np.ones((out["clusterCenters"].shape[0], 100), bool)
+    binGot[:, out["columns"]] = out["clusterCenters"] == 0
+    for i in range(1, 6):
+        row = np.flatnonzero(binGot.sum(axis=1) == i)
+        assert len(row) == 1 and np.array_equal(binTruth[i - 1], binGot[row[0]])
+
+
+def test_dallocate(engine):
+    """test_dAllocate.R:4-11 and :16-23"""
+    rng = np.random.default_rng(3)
+    x = rapi.generateBimodalData(observations=20, dataCols=150, rng=rng)
+    centers = np.vstack([rng.random(150) + 50, rng.random(150) - 50])
+    assert np.array_equal(rapi.dAllocate(x["samples"], {"clusterCenters": centers, "logCenterSd": False}, engine=engine), x["ids"])
+    dep = rapi.depeche(x["samples"], center=False, nCores=2, engine=engine, seed=1)
+    alloc = rapi.dAllocate(x["samples"][:, dep["columns"]], {"clusterCenters": dep["clusterCenters"],
+                                                             "logCenterSd": [False, False, dep["logCenterSd"][2]]}, engine=engine,
+                           columns=np.arange(len(dep["columns"])))
+    assert engine.rand_index(dep["clusterVector"], alloc, 100) == 1.0
+
+
+def test_doptpenalty(engine):
+    """test_dOptPenalty.R:4-22"""
+    x = rapi.generateBimodalData(observations=200, dataCols=10, rng=np.random.default_rng(6))
+    xs = x["samples"] / np.std(x["samples"], ddof=1)
+    r = rapi.dOptPenalty(xs, k=30, maxIter=20, minARIImprovement=0.01, sampleSize=100, penalties=[0, 2, 4, 8, 16, 32, 128], optimARI=0.95,
+                         nCores=2, engine=engine, seed=2, disableWarnings=True)
+    pos = r["bestPenaltyPosition"]
+    assert r["meanOptimDf"]["nClust"][pos] == 2 and r["meanOptimDf"]["ARI"][pos] == 1
+
+
+def test_testdata_against_stored_depeche_result(engine, testdata):
+    """BASELINE configs[0]: depeche(testData[, 2:15]) with the default penalty grid.  The stored run
+    (data/testDataDepeche.RData) is time-seeded, so the comparison is distributional: same best penalty
+    neighbourhood, 8 clusters, ARI curve and cluster-count curve close to the stored ones, same partition."""
+    out = rapi.depeche(testdata["X"], nCores=7, engine=engine, seed=11)
+    opt = out["penaltyOptList"]
+    pen = opt["allPenalties"]["penalty"]
+    assert np.allclose(pen, testdata["stored_penalties"])
+    ari, ncl = opt["allPenalties"]["ARI"], opt["allPenalties"]["nClust"]
+    assert opt["bestPenalty"] in (11.3, 16.0, 22.6)                                 # stored: 16
+    hi = np.isin(pen, [11.3, 16.0, 22.6])
+    assert np.all(ari[hi] > 0.96) and np.all(np.abs(ncl[hi] - 8) < 0.6)            # stored: .987 .991 .991 / 8.07 8.00 8.00
+    assert ari[0] < 0.75 and ncl[0] > 26                                            # stored: .590 / 29.4 at penalty 1
+    assert np.all(np.diff(ncl) < 0.8)                                               # cluster count falls with the penalty
+    assert out["clusterCenters"].shape[0] == 8
+    from sklearn.metrics import adjusted_rand_score
+    assert adjusted_rand_score(out["clusterVector"], testdata["stored_clusterVector"]) > 0.93
+    sizes = np.bincount(out["clusterVector"])[1:]
+    assert np.all(np.diff(sizes) <= 0)                                              # clusters numbered by size (R/depeche.R:236-249)
+    stored = np.bincount(testdata["stored_clusterVector"])[1:]
+    assert np.all(np.abs(sizes - stored) < 0.05 * 20000)

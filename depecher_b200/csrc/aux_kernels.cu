@@ -110,27 +110,49 @@ __global__ void seed_dist_kernel(const SeedFit* fits, int d, int c /* centre jus
 }
 
 __global__ void seed_pick_kernel(SeedFit* fits, int d, int c, uint64_t seed) {
+    // One CTA per fit.  The cumulative sum the reference keeps in a std::map is evaluated hierarchically:
+    // thread segments of block sums -> the segment holding x -> its blocks -> the cells of one block.  Every level
+    // is summed in ascending order, so the pick only differs from a purely sequential cumsum when x falls within
+    // rounding distance (~1e-16 relative) of a boundary.
     SeedFit f = fits[blockIdx.x];
     const int nb = (int)((f.n + kSeedBlock - 1) / kSeedBlock);
-    __shared__ double s_total, s_before;
-    __shared__ int s_block;
+    const int T = blockDim.x;
+    const int seg = (nb + T - 1) / T;
+    __shared__ double s_seg[256];
     __shared__ long long s_row;
+    {
+        double t = 0.0;
+        const int b0 = threadIdx.x * seg, b1 = min(nb, b0 + seg);
+        for (int b = b0; b < b1; ++b) t += f.block_sums[b];
+        s_seg[threadIdx.x] = t;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         double total = 0.0;
-        for (int b = 0; b < nb; ++b) total += f.block_sums[b];
+        for (int t = 0; t < T; ++t) total += s_seg[t];
         const double u = dpr_rng_unit(dpr_rng_draw(seed, DPR_RNG_SEED, f.fit_id, (uint32_t)c, 0).w[0]);
         const double x = u * total;
         double cum = 0.0;
-        int blk = -1;
-        double before = 0.0;
-        for (int b = 0; b < nb; ++b) {
-            const double nxt = cum + f.block_sums[b];
-            if (nxt > x && f.block_sums[b] > 0) { blk = b; before = cum; break; }
+        int sg = -1;
+        for (int t = 0; t < T; ++t) {
+            const double nxt = cum + s_seg[t];
+            if (nxt > x && s_seg[t] > 0) { sg = t; break; }
             cum = nxt;
         }
         long long row = 0;
-        if (blk >= 0) {
-            double run = before;
+        if (sg >= 0) {
+            int blk = -1;
+            const int b0 = sg * seg, b1 = min(nb, b0 + seg);
+            int last_blk = -1;
+            for (int b = b0; b < b1; ++b) {
+                const double bs = f.block_sums[b];
+                if (bs > 0) last_blk = b;
+                const double nxt = cum + bs;
+                if (nxt > x && bs > 0) { blk = b; break; }
+                cum = nxt;
+            }
+            if (blk < 0) blk = last_blk;   // rounding of the segment sums: take the segment's last non-empty block
+            double run = cum;
             const int64_t i0 = (int64_t)blk * kSeedBlock, i1 = min(f.n, i0 + (int64_t)kSeedBlock);
             long long last_pos = -1;
             row = -1;
@@ -142,7 +164,7 @@ __global__ void seed_pick_kernel(SeedFit* fits, int d, int c, uint64_t seed) {
                     if (run > x) { row = i; break; }
                 }
             }
-            if (row < 0) row = last_pos < 0 ? i0 : last_pos;  // rounding of the block sums: take the block's last positive weight
+            if (row < 0) row = last_pos < 0 ? i0 : last_pos;
         }
         s_row = row;
         if (f.rows) f.rows[c] = row;
@@ -387,7 +409,7 @@ int launch_seeding(SeedFit* d_fits, int n_fits, int64_t n_max, int d, int k, uin
     const int gx = std::max(1, std::min(nb, (148 * 8 + n_fits - 1) / n_fits));
     for (int c = 1; c < k; ++c) {
         seed_dist_kernel<<<dim3(gx, n_fits), kSeedBlock, sizeof(double) * d, st>>>(d_fits, d, c, c == 1);
-        seed_pick_kernel<<<n_fits, 64, 0, st>>>(d_fits, d, c, seed);
+        seed_pick_kernel<<<n_fits, 256, 0, st>>>(d_fits, d, c, seed);
         count_launch(2);
     }
     DPR_CUDA(cudaGetLastError());

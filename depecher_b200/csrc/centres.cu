@@ -16,19 +16,34 @@ namespace dpr {
 // non-zero); otherwise every row, except that all-zero rows after the first are dropped: they are identical,
 // and the reference's first-minimum rule (minCoeff, :64) can only ever pick the first of them.
 __device__ void build_centre_table(const Problem& pr, int no_zero, int table_cap) {
-    __shared__ int s_act[kMaxKC * kMaxChunks];
-    __shared__ int s_nact, s_ref_active, s_bad;
+    constexpr int kMaxRows = kMaxKC * kMaxChunks;
+    __shared__ int s_act[kMaxRows];
+    __shared__ double s_cc[kMaxRows];
+    __shared__ unsigned char s_zero[kMaxRows];
+    __shared__ int s_nact, s_bad;
     const int k = pr.k, d = pr.d;
     CentreHeader* h = pr.hdr;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    // one thread per row: all-zero flag, non-finite flag, ||c||^2 in fp64
+    for (int c = threadIdx.x; c < k && c < kMaxRows; c += blockDim.x) {
+        bool zero = true, bad = false;
+        double s = 0.0;
+        for (int t = 0; t < d; ++t) {
+            const double v = pr.mu[(size_t)c * d + t];
+            if (!(fabs(v) <= 0.0)) zero = false;
+            if (!isfinite(v)) bad = true;
+            s += v * v;
+        }
+        s_zero[c] = zero;
+        s_cc[c] = s;
+        if (bad) s_bad = 1;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        int n = 0, ref_active = 0, bad = 0, seen_zero = 0;
-        for (int c = 0; c < k; ++c) {
-            bool zero = true;
-            for (int t = 0; t < d; ++t) {
-                const double v = pr.mu[(size_t)c * d + t];
-                if (!(fabs(v) <= 0.0)) zero = false;
-                if (!isfinite(v)) bad = 1;
-            }
+        int n = 0, ref_active = 0, seen_zero = 0;
+        for (int c = 0; c < k && c < kMaxRows; ++c) {
+            const bool zero = s_zero[c];
             bool use;
             if (no_zero) {
                 use = !zero;
@@ -38,19 +53,20 @@ __device__ void build_centre_table(const Problem& pr, int no_zero, int table_cap
                 use = !(zero && seen_zero);
                 if (zero) seen_zero = 1;
             }
-            if (use && n < kMaxKC * kMaxChunks) s_act[n++] = c;
+            if (use) s_act[n++] = c;
         }
         s_nact = n;
-        s_ref_active = ref_active;
-        s_bad = bad;
         const bool trivial = ref_active < 2 || n < 2;
         const int n_chunks = trivial ? 0 : (n + kMaxKC - 1) / kMaxKC;
         h->k = k;
         h->k_act = n;
         h->n_chunks = n_chunks;
         h->trivial = trivial;
-        h->force_exact = bad;
+        h->force_exact = s_bad;
         int off = 0, base = 0;
+        float ccmax = 0.f;
+        for (int a = 0; a < n; ++a) ccmax = fmaxf(ccmax, (float)s_cc[s_act[a]]);
+        h->cc_max = ccmax * 1.0000002f;
         for (int q = 0; q < n_chunks; ++q) {
             const int real = n / n_chunks + (q < n % n_chunks ? 1 : 0);
             const int kc = (real + 1) & ~1;
@@ -70,7 +86,6 @@ __device__ void build_centre_table(const Problem& pr, int no_zero, int table_cap
     }
     __syncthreads();
     const int n = s_nact, n_chunks = h->n_chunks;
-    float ccmax = 0.f;
     int real_before = 0;
     for (int q = 0; q < n_chunks; ++q) {
         const int real = n / n_chunks + (q < n % n_chunks ? 1 : 0);
@@ -78,38 +93,15 @@ __device__ void build_centre_table(const Problem& pr, int no_zero, int table_cap
         float* cc = pr.table + h->chunk_off[q];
         float* w = cc + kcp;
         for (int t = threadIdx.x; t < kcp; t += blockDim.x) {
-            float v = 3.0e38f;
-            int row = -1;
-            if (t < real) {
-                row = s_act[real_before + t];
-                double s = 0.0;
-                for (int j = 0; j < d; ++j) {
-                    const double c = pr.mu[(size_t)row * d + j];
-                    s += c * c;
-                }
-                v = (float)s;
-            }
-            cc[t] = v;
+            const int row = t < real ? s_act[real_before + t] : -1;
+            cc[t] = row >= 0 ? (float)s_cc[row] : 3.0e38f;
             if (t < kc) pr.orig[h->chunk_base[q] + t] = row;
         }
         for (int e = threadIdx.x; e < kcp * d; e += blockDim.x) {
             const int j = e / kcp, t = e % kcp;
-            float v = 0.f;
-            if (t < real) v = (float)(-2.0 * pr.mu[(size_t)s_act[real_before + t] * d + j]);
-            w[e] = v;
+            w[e] = t < real ? (float)(-2.0 * pr.mu[(size_t)s_act[real_before + t] * d + j]) : 0.f;
         }
         real_before += real;
-    }
-    if (threadIdx.x == 0) {
-        for (int a = 0; a < n; ++a) {
-            double s = 0.0;
-            for (int j = 0; j < d; ++j) {
-                const double c = pr.mu[(size_t)s_act[a] * d + j];
-                s += c * c;
-            }
-            ccmax = fmaxf(ccmax, (float)s);
-        }
-        h->cc_max = ccmax * 1.0000002f;
     }
 }
 

@@ -436,19 +436,29 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
             for (int64_t e = threadIdx.x; e < entries; e += nthreads) {
                 double acc = 0.0;
                 if (e < stride) {
-                    if (P.warp_sums)
-                        for (int w = 0; w < W; ++w) {
-                            double* q = P.warp_sums + (wbase + w) * stride + e;
-                            acc += __ldcg(q);
-                            __stcg(q, 0.0);
+                    if (P.warp_sums) {
+                        double v[kWarpsPerCta];   // all loads in flight first, then the fixed-order sum
+#pragma unroll
+                        for (int w = 0; w < kWarpsPerCta; ++w) v[w] = w < W ? __ldcg(P.warp_sums + (wbase + w) * stride + e) : 0.0;
+#pragma unroll
+                        for (int w = 0; w < kWarpsPerCta; ++w) {
+                            acc += v[w];
+                            if (w < W && v[w] != 0.0) __stcg(P.warp_sums + (wbase + w) * stride + e, 0.0);
                         }
+                    }
                 } else if (e < stride + P.k_max) {
-                    if (P.warp_counts)
-                        for (int w = 0; w < W; ++w) {
-                            long long* q = P.warp_counts + (wbase + w) * P.k_max + (e - stride);
-                            acc += (double)__ldcg(q);
-                            __stcg(q, 0LL);
+                    if (P.warp_counts) {
+                        long long v[kWarpsPerCta];
+#pragma unroll
+                        for (int w = 0; w < kWarpsPerCta; ++w) v[w] = w < W ? __ldcg(P.warp_counts + (wbase + w) * P.k_max + (e - stride)) : 0LL;
+                        long long t = 0;
+#pragma unroll
+                        for (int w = 0; w < kWarpsPerCta; ++w) {
+                            t += v[w];
+                            if (w < W && v[w] != 0) __stcg(P.warp_counts + (wbase + w) * P.k_max + (e - stride), 0LL);
                         }
+                        acc = (double)t;
+                    }
                 } else {
                     long long t = 0;
                     for (int w = 0; w < W; ++w) t += s_changed[w];

@@ -1,0 +1,43 @@
+// Compile-check stub of the handful of Rcpp names rpkg/src/InterfaceUtils.cpp uses (R/Rcpp are not in this
+// image).  It only has to make `g++ -fsyntax-only` meaningful; it is not a runtime.
+#pragma once
+#include <algorithm>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+namespace Rcpp {
+template <typename T> struct Vec {
+    std::vector<T> v;
+    Vec() {}
+    Vec(long n) : v((size_t)n) {}
+    long size() const { return (long)v.size(); }
+    T& operator[](long i) { return v[(size_t)i]; }
+    T* begin() { return v.data(); }
+};
+typedef Vec<int> IntegerVector;
+typedef Vec<double> NumericVector;
+struct NumericMatrix : Vec<double> {
+    int r, c;
+    NumericMatrix(int rr, int cc) : Vec<double>((long)rr * cc), r(rr), c(cc) {}
+    int nrow() const { return r; }
+    int ncol() const { return c; }
+};
+struct Any {
+    Any() {}
+    template <typename T> Any(const T&) {}
+};
+struct List {
+    std::map<std::string, Any> named;
+    std::vector<Any> pos;
+    List() {}
+    List(size_t n) : pos(n) {}
+    Any& operator[](const char* k) { return named[k]; }
+    Any& operator[](size_t i) { return pos[i]; }
+    Any& operator[](int i) { return pos[(size_t)i]; }
+};
+template <typename T> T clone(const T& x) { return x; }
+inline void stop(const std::string& m) { throw std::runtime_error(m); }
+}  // namespace Rcpp
+inline double* REAL(Rcpp::Vec<double>& x) { return x.v.data(); }
+inline int* INTEGER(Rcpp::Vec<int>& x) { return x.v.data(); }

@@ -177,21 +177,21 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     n_local = N_CELLS
     ds = eng.synthetic(n_local, D, GROUPS, AMP, SEED, row0=rank * n_local, scale=0.0)
     reg = reg_for(n_local * world, D, PENALTY)
-    # initial centres: K cells of rank 0's shard (identical on every rank)
-    head = eng.read(ds, 0, 4096)
+    # initial centres: k-means++ on rank 0's shard (initialize_mu), identical on every rank; untimed like the data upload
+    mu0, _ = eng.initialize_mu(ds, K, seed=SEED, fit_id=0)
     if world > 1:
-        t = torch.from_numpy(np.ascontiguousarray(head)).cuda()
+        t = torch.from_numpy(np.ascontiguousarray(mu0)).cuda()
         dist.broadcast(t, src=0)
-        head = t.cpu().numpy()
-    mu = np.array(head[np.random.default_rng(7).choice(4096, K, replace=False)])
+        mu0 = t.cpu().numpy()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    mu, _ = eng.lloyd_iterations(ds, mu, reg, True, 20, max(args.warmup, 3))      # warm-up (>= 3 steps)
-    k_active0 = int((np.abs(mu).sum(1) > 0).sum())
+    # A step = one fused Lloyd iteration of a FRESH fit (iterations 0, 1, 2, ... of find_centers: all labels change in
+    # iteration 0, the penalty ramps up over the first 20, dying clusters drop out) - not a converged steady state.
+    eng.lloyd_iterations(ds, mu0, reg, True, -1, max(args.warmup, 3))             # warm-up (>= 3 steps)
     eng.pass_timing(True)
     launches0 = eng.kernel_launches(reset=True)
     sampler = ClockSampler(local_rank)
@@ -199,7 +199,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    mu, changed = eng.lloyd_iterations(ds, mu, reg, True, 20, args.steps)
+    mu, changed = eng.lloyd_iterations(ds, mu0, reg, True, -1, args.steps)
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -211,8 +211,21 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    k_eff = min(k_active0, k_active1)
+    k_eff = k_active1          # clusters only ever die during a fit: the count at the end is the smallest of the run
     value = float(n_local) * world * k_eff * args.steps / (ms * 1e-3)
+    # the same loop continued in its steady state (ramp complete, a handful of labels still moving)
+    steady = None
+    if rank == 0 and world == 1:
+        eng.pass_timing(True)
+        t0s, t1s = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0s.record()
+        mu_s, _ = eng.lloyd_iterations(ds, mu, reg, True, 20, 10)
+        t1s.record()
+        torch.cuda.synchronize()
+        sp_ms, sp_cnt = eng.pass_timing(False)
+        k_s = int((np.abs(mu_s).sum(1) > 0).sum())
+        steady = {"ms_per_step": t0s.elapsed_time(t1s) / 10, "fused_pass_ms": sp_ms / max(sp_cnt, 1), "k_active": k_s,
+                  "value": float(n_local) * k_s * 10 / (t0s.elapsed_time(t1s) * 1e-3)}
 
     line = None
     if rank == 0:
@@ -235,10 +248,11 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"synthetic {n_local} cells x {D} markers per GPU, K={K} ({k_eff} active), penalty {PENALTY}, one fused Lloyd iteration per step",
+            "config": {"workload": f"synthetic {n_local} cells x {D} markers per GPU, K={K} ({k_eff} still active at the end), penalty {PENALTY}, "
+                                   f"one fused Lloyd iteration per step: iterations 0..{args.steps - 1} of a fresh fit from k-means++ centres",
                        "cells_per_gpu": n_local, "markers": D, "k": K, "k_active": k_eff, "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
                        "l2": "inputs (1.6 GB per GPU) exceed the 126 MB L2", "labels_changed_last_step": int(changed)},
-            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "steady_state": steady,
         }
     # ---- e2e through the C ABI with host buffers, and the CPU baseline: rank 0 at N=1 only (bounded)
     if rank == 0 and world == 1:
@@ -259,6 +273,16 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         rate, wall, kind = cpu_lloyd_rate(sample, mu_cpu, reg_for(rows, D, PENALTY), 3, workers)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": workers, "kind": kind,
                                 "sample": f"{workers} single-threaded engines x {rows} cells x {D} markers, K={K}, 3 Lloyd iterations each ({wall:.1f} s)"}
+        # the other half of the metric: depeche() on 10M x 40 with the full default penalty sweep (X resident, pre-scaling excluded)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import depeche_c3
+            ds.close()
+            dres = depeche_c3.run(eng, N_CELLS, D, K, 10, GROUPS, AMP, SEED + 1, verbose=False)
+            line["depeche_10Mx40"] = {kk: dres[kk] for kk in ("total_s", "penalty_opt_s", "selection_s", "final_allocate_s", "workerIterations",
+                                                              "bestPenalty", "clusters", "kernel_launches")}
+        except Exception as exc:   # the headline line must still print
+            line["depeche_10Mx40"] = {"error": repr(exc)}
     elif rank == 0:
         line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "measured at N=1 only"}
     if rank == 0:

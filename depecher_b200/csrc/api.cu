@@ -782,6 +782,7 @@ static int bench_session(dpr_dataset_t ds, const double* mu, uint32_t k, double 
     pr.reg = reg;
     pr.no_zero = no_zero;
     pr.done = 0;
+    pr.delta = 0;
     DPR_CUDA(cudaMemcpyAsync(g_bench_session->d_problems, &pr, sizeof(Problem), cudaMemcpyHostToDevice, ctx().stream));
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));
     return g_bench_session->prepare();
@@ -792,9 +793,11 @@ int dpr_dataset_lloyd_iterations(dpr_dataset_t ds, double* mu_inout, uint32_t k,
     if (!ds || !mu_inout || k < 2 || iters < 1) return fail(DPR_ERR_INVALID, "lloyd_iterations: bad arguments");
     DPR_TRY(bench_session(ds, mu_inout, k, reg, no_zero, true));
     Session& s = *g_bench_session;
+    if (ramp_i < 0) DPR_TRY(s.zero_labels());   // a fresh fit: previous labels are all 0 (Clusterer.cpp:226)
     for (int i = 0; i < iters; ++i) {
         DPR_TRY(s.pass(kPassLloyd, true));
-        DPR_TRY(s.reduce_and_finalize(std::min(ramp_i, 20), 1 << 30));  // i <= 20: never "converged", ramp frozen
+        // iteration index <= 20 keeps the convergence exit off; ramp_i < 0 walks the ramp 0, 1, 2, ... of a real fit
+        DPR_TRY(s.reduce_and_finalize(std::min(ramp_i < 0 ? i : ramp_i, 20), 1 << 30));
     }
     DPR_TRY(s.fetch_state());
     if (changed_out) *changed_out = s.h_problems[0].changed;

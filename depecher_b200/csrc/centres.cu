@@ -168,8 +168,9 @@ __global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_s
     if (threadIdx.x == 0) {
         problems[p].changed = changed;
         problems[p].n_assign = iter + 1;
-        // next pass: scatter only the cells that change label once few of them do (sums += delta)
-        problems[p].delta = (allow_delta && changed * 8 < pr.n) ? 1 : 0;
+        // every pass after the first one scatters only the cells whose label changes (sums += delta): the running sums are
+        // valid from here on, and even a slot where every cell moves costs at most two contributions per cell
+        problems[p].delta = allow_delta ? 1 : 0;
     }
     if (converged || iter + 1 >= max_iter) {
         // Clusterer.cpp:247-249: break BEFORE the update: centres stay those of the previous iteration.

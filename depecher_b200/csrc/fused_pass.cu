@@ -76,19 +76,32 @@ __device__ __forceinline__ void dist_chunk(const float* __restrict__ slot, const
     constexpr int NP = KC / 2;
     constexpr int KCP = (KC + 3) & ~3;
     float2 acc[2][NP];
-    {
-        const float2* cc = reinterpret_cast<const float2*>(tab);
-#pragma unroll
-        for (int t = 0; t < NP; ++t) {
-            const float2 c = cc[t];
-            acc[0][t] = c;
-            acc[1][t] = c;
-        }
-    }
     const float2* xs = reinterpret_cast<const float2*>(slot);
     const float4* cw = reinterpret_cast<const float4*>(tab + KCP);
+    {
+        // marker 0 peeled: the accumulators are born as x0 * w0 + ||c||^2 (no register copies of the ||c||^2 row)
+        const float2* cc = reinterpret_cast<const float2*>(tab);
+        const float2 xv = xs[lane];
+        const float2 x0 = make_float2(xv.x, xv.x), x1 = make_float2(xv.y, xv.y);
+#pragma unroll
+        for (int q = 0; q < KCP / 4; ++q) {
+            const float4 c = cw[q];
+            const float2 c0 = cc[2 * q];
+            acc[0][2 * q] = __ffma2_rn(x0, make_float2(c.x, c.y), c0);
+            acc[1][2 * q] = __ffma2_rn(x1, make_float2(c.x, c.y), c0);
+            if (2 * q + 1 < NP) {
+                const float2 c1 = cc[2 * q + 1];
+                acc[0][2 * q + 1] = __ffma2_rn(x0, make_float2(c.z, c.w), c1);
+                acc[1][2 * q + 1] = __ffma2_rn(x1, make_float2(c.z, c.w), c1);
+            }
+        }
+        if (FIRST) {
+            xx[0] = xv.x * xv.x;
+            xx[1] = xv.y * xv.y;
+        }
+    }
 #pragma unroll 2
-    for (int j = 0; j < d; ++j) {
+    for (int j = 1; j < d; ++j) {
         const float2 xv = xs[j * (kRowStride / 2) + (lane ^ (j & 15))];   // cells (2*lane, 2*lane+1) of marker j, swizzled
         const float2 x0 = make_float2(xv.x, xv.x), x1 = make_float2(xv.y, xv.y);
 #pragma unroll
@@ -415,7 +428,38 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
                     key[1] = lab[1] >= 0 ? 2 * lab[1] : -1;
                     key[2] = key[3] = -1;
                 }
-                slot_contributions(slot, key, cell, d, pr.k, lane, wscr, perm, my_sums, my_counts);
+                const unsigned m0 = __ballot_sync(0xffffffffu, ch0), m1 = __ballot_sync(0xffffffffu, ch1);
+                if (delta && __popc(m0) + __popc(m1) <= 16) {
+                    // few cells moved: no sort, each moved cell adds its row to the new label's sums and takes it off the old one's
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        unsigned m = r ? m1 : m0;
+                        while (m) {
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            const int newL = __shfl_sync(0xffffffffu, lab[r], src);
+                            const int oldL = __shfl_sync(0xffffffffu, r ? oldl.y : oldl.x, src);
+                            const int c = 2 * src + r;
+                            for (int jb = 0; jb < d; jb += 32) {
+                                const int j = jb + lane;
+                                if (j < d) {
+                                    const double v = (double)slot[x_slot_index(c, j)];
+                                    double* pa = my_sums + (size_t)newL * d + j;
+                                    double* pb = my_sums + (size_t)oldL * d + j;
+                                    const double a = __ldcg(pa), b = __ldcg(pb);
+                                    __stcg(pa, a + v);
+                                    __stcg(pb, b - v);
+                                }
+                            }
+                            if (lane == 0) {
+                                __stcg(&my_counts[newL], __ldcg(&my_counts[newL]) + 1);
+                                __stcg(&my_counts[oldL], __ldcg(&my_counts[oldL]) - 1);
+                            }
+                        }
+                    }
+                } else {
+                    slot_contributions(slot, key, cell, d, pr.k, lane, wscr, perm, my_sums, my_counts);
+                }
             }
             __syncwarp();
             if (i + S < count) issue(i + S);

@@ -147,8 +147,10 @@ int dpr_dataset_allocate_many(dpr_dataset_t ds, const double* mus, int32_t m, in
                               int32_t* labels_out, double* ari_out);
 
 /* ---- device-resident Lloyd iterations (bench: the timed hot loop, nothing crosses PCIe) --------- */
-/* Runs `iters` fused iterations (assignment + sums/counts + soft-threshold update, ramp frozen at
- * ramp_i) from mu_inout, without convergence exit; changed_out (nullable) = labels changed in the last. */
+/* Runs `iters` fused iterations (assignment + sums/counts + soft-threshold update) from mu_inout without the
+ * convergence exit.  ramp_i >= 0: continue a fit with the penalty ramp frozen at iteration ramp_i (steady state).
+ * ramp_i < 0: a fresh fit — previous labels zeroed, iterations numbered 0, 1, 2, ... like find_centers.
+ * changed_out (nullable) = labels changed in the last iteration. */
 int dpr_dataset_lloyd_iterations(dpr_dataset_t ds, double* mu_inout, uint32_t k, double reg, int32_t no_zero,
                                  int32_t ramp_i, int32_t iters, int64_t* changed_out);
 /* same for the plain assignment pass (dAllocate's kernel), labels stay on device */

@@ -239,7 +239,16 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         launch_ms = pass_ms / max(pass_cnt, 1)
         achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
         fma_per_launch = float(n_local) * k_eff * D
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` capture
+        try:
+            for ln in open(os.path.join(ROOT, "profiles", "r01_fused_pass_bench_ncu.csv")):
+                f = ln.strip().split(",")
+                if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+                    traffic = (traffic or 0.0) + float(np.mean([float(v) for v in f[2:]])) * scale
+        except Exception:
+            traffic = None
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": which, "kernel": "fused_pass_kernel", "launch_ms": launch_ms, "launches_timed": pass_cnt,
                     "fp32_fma_per_s": fma_per_launch / (launch_ms * 1e-3), "fp32_fma_peak_measured": 33.4e12,
                     "fp32_frac": fma_per_launch / (launch_ms * 1e-3) / 33.4e12,

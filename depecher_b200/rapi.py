@@ -232,8 +232,30 @@ def _sd(v):
     return float(np.std(v, ddof=1)) if len(v) > 1 else float("nan")
 
 
+def _grid_search_set(eng, X, k, regs, nCores, sampleSize, seed, dist=None):
+    """One set of the search = nCores workers x grid_search(X, k, regs, 1, sampleSize, .) (R/depechePenaltyOpt.R:50-55).
+    Single process: one batched call.  With a torch.distributed group (`dist`) the workers are dealt round-robin over the
+    ranks (each rank holds X), every rank fits its share, and the small per-worker results are all-gathered, so every rank
+    runs the identical state machine afterwards.  No data-path collective: the fits are independent (Clusterer.cpp:349-384)."""
+    if dist is None or dist.get_world_size() == 1:
+        return eng.grid_search_each(X, [k], regs, nCores, sampleSize, seed)
+    from . import shard
+    rank, world = dist.get_rank(), dist.get_world_size()
+    mine = shard.grid_split(nCores, rank, world)
+    part = None
+    if len(mine):
+        part = eng.grid_search_each(X, [k], regs, len(mine), sampleSize, seed * 1000 + rank)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (mine.tolist(), None if part is None else (part["z"], part["m"], part["c"])))
+    z, m, c = [None] * nCores, [None] * nCores, [None] * nCores
+    for workers, payload in gathered:
+        for q, w in enumerate(workers):
+            z[w], m[w], c[w] = payload[0][q], payload[1][q], payload[2][q]
+    return {"d": z, "z": z, "n": m, "m": m, "c": c}
+
+
 def depechePenaltyOpt(inDataFrameUsed, k, maxIter, minARIImprovement, sampleSize, penalties, createOutput=False, disableWarnings=False,
-                      optimARI=0.95, nCores=None, plotDir=".", engine=None, seed=0, verbose=False):
+                      optimARI=0.95, nCores=None, plotDir=".", engine=None, seed=0, verbose=False, dist=None):
     eng = _engine(engine)
     nCores = nCores or default_ncores()
     X = inDataFrameUsed
@@ -247,7 +269,7 @@ def depechePenaltyOpt(inDataFrameUsed, k, maxIter, minARIImprovement, sampleSize
     full = []          # one entry per worker-iteration: {penalty position -> (ARI, nClust, [ret1 centres, ret2 centres])}
     while iterTimesNCores < 20 or (iterTimesNCores < maxIter and stdChange >= minARIImprovement):     # :47-48
         # nCores workers x grid_search(dataMat, k, usedPenalties, 1, sampleSize, i)  (:50-55) as ONE batched call
-        res = eng.grid_search_each(X, [k], realPenalties[usedPos], nCores, sampleSize, seed + 7919 * it)
+        res = _grid_search_set(eng, X, k, realPenalties[usedPos], nCores, sampleSize, seed + 7919 * it, dist)
         for w in range(nCores):
             ari = np.array(res["z"][w]).ravel()
             ncl = np.array(res["m"][w]).ravel()

@@ -77,3 +77,38 @@ def test_shard_ranges_cover_rows():
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _grid_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from depecher_b200 import rapi
+        from oracle_engine import OracleEngine
+        x = rapi.generateBimodalData(observations=200, dataCols=10, rng=np.random.default_rng(6))
+        xs = x["samples"] / np.std(x["samples"], ddof=1)
+        r = rapi.depechePenaltyOpt(xs, k=12, maxIter=20, minARIImprovement=0.01, sampleSize=100, penalties=[0, 4, 16, 64], optimARI=0.95, nCores=4,
+                                   engine=OracleEngine(), seed=2, disableWarnings=True, dist=dist)
+        q.put((rank, r["bestPenalty"], r["meanOptimDf"]["ARI"].tolist(), r["meanOptimDf"]["nClust"].tolist(), len(r["bestClusterCenters"])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grid_split_two_ranks_same_state_machine():
+    """penalty/restart grid split over 2 ranks: every rank ends with the identical search result"""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grid_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1:] == res[1][1:]
+    best, ari, ncl, ncent = res[0][1:]
+    pos = [0, 4, 16, 64].index(best)
+    assert ncl[pos] == 2 and ari[pos] == 1 and ncent >= 2 * 20

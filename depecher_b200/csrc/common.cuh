@@ -37,14 +37,17 @@ constexpr int kSmemBudget = 227 * 1024;
 
 // Resident layout of a cell matrix ("tile-major"): cells are grouped in tiles of kSlotCells = 64 consecutive
 // cells; a tile holds its d marker rows back to back (d * 64 floats, contiguous in HBM, so one bulk-async
-// copy moves a whole slot), and inside marker row j the cell c sits at c ^ (2 * (j & 15)).  The XOR keeps
-// the (2c, 2c+1) pair of a lane adjacent (one LDS.64 per marker in the distance loop, conflict-free) and
-// spreads the marker rows of one cell over 16 banks for the transposed reads of the sum phase.
+// copy moves a whole slot), and inside marker row j the cell c sits at c ^ (2 * ((j >> 2) & 15)).  The XOR keeps
+// the (2c, 2c+1) pair of a lane adjacent (one LDS.64 per marker in the distance loop, conflict-free), changes only
+// every 4th marker (so the unrolled distance loop pays for it once per 4 markers: measured +6 % over a per-marker
+// XOR, profiles/microbench/r01_chunk_bench_b200.log) and still spreads the marker rows of one cell over 8 bank
+// pairs for the transposed reads of the sum phase.
+__host__ __device__ __forceinline__ int x_swizzle(int j) { return ((j >> 2) & 15) << 1; }
 __host__ __device__ __forceinline__ size_t x_index(int64_t cell, int j, int d) {
-    return (size_t)(cell >> 6) * (size_t)(d * kSlotCells) + (size_t)j * kSlotCells + (size_t)((cell & 63) ^ ((j & 15) << 1));
+    return (size_t)(cell >> 6) * (size_t)(d * kSlotCells) + (size_t)j * kSlotCells + (size_t)((cell & 63) ^ x_swizzle(j));
 }
 __host__ __device__ __forceinline__ int x_slot_index(int cell_in_slot, int j) {
-    return j * kSlotCells + (cell_in_slot ^ ((j & 15) << 1));
+    return j * kSlotCells + (cell_in_slot ^ x_swizzle(j));
 }
 
 // Centre table of one problem as the fused pass reads it (global memory, built on device by

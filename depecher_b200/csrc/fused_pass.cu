@@ -57,6 +57,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float r;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -76,33 +79,20 @@ __device__ __forceinline__ void dist_chunk(const float* __restrict__ slot, const
     constexpr int NP = KC / 2;
     constexpr int KCP = (KC + 3) & ~3;
     float2 acc[2][NP];
-    const float2* xs = reinterpret_cast<const float2*>(slot);
-    const float4* cw = reinterpret_cast<const float4*>(tab + KCP);
     {
-        // marker 0 peeled: the accumulators are born as x0 * w0 + ||c||^2 (no register copies of the ||c||^2 row)
         const float2* cc = reinterpret_cast<const float2*>(tab);
-        const float2 xv = xs[lane];
-        const float2 x0 = make_float2(xv.x, xv.x), x1 = make_float2(xv.y, xv.y);
 #pragma unroll
-        for (int q = 0; q < KCP / 4; ++q) {
-            const float4 c = cw[q];
-            const float2 c0 = cc[2 * q];
-            acc[0][2 * q] = __ffma2_rn(x0, make_float2(c.x, c.y), c0);
-            acc[1][2 * q] = __ffma2_rn(x1, make_float2(c.x, c.y), c0);
-            if (2 * q + 1 < NP) {
-                const float2 c1 = cc[2 * q + 1];
-                acc[0][2 * q + 1] = __ffma2_rn(x0, make_float2(c.z, c.w), c1);
-                acc[1][2 * q + 1] = __ffma2_rn(x1, make_float2(c.z, c.w), c1);
-            }
-        }
-        if (FIRST) {
-            xx[0] = xv.x * xv.x;
-            xx[1] = xv.y * xv.y;
+        for (int t = 0; t < NP; ++t) {
+            const float2 c = cc[t];
+            acc[0][t] = c;
+            acc[1][t] = c;
         }
     }
+    const float2* xs = reinterpret_cast<const float2*>(slot);
+    const float4* cw = reinterpret_cast<const float4*>(tab + KCP);
 #pragma unroll 2
-    for (int j = 1; j < d; ++j) {
-        const float2 xv = xs[j * (kRowStride / 2) + (lane ^ (j & 15))];   // cells (2*lane, 2*lane+1) of marker j, swizzled
+    for (int j = 0; j < d; ++j) {
+        const float2 xv = xs[j * (kRowStride / 2) + (lane ^ ((j >> 2) & 15))];   // cells (2*lane, 2*lane+1) of marker j, swizzled
         const float2 x0 = make_float2(xv.x, xv.x), x1 = make_float2(xv.y, xv.y);
 #pragma unroll
         for (int q = 0; q < KCP / 4; ++q) {
@@ -245,7 +235,7 @@ __device__ __forceinline__ void slot_contributions(const float* __restrict__ slo
         const int j = jb + lane;
         const bool on = j < d;
         const float* row = slot + (on ? j : 0) * kRowStride;
-        const int xo = ((on ? j : 0) & 15) << 1;   // swizzle of this lane's marker row
+        const int xo = x_swizzle(on ? j : 0);      // swizzle of this lane's marker row
         for (int Lb = 0; Lb < k; Lb += 32) {
             const int Li = Lb + lane;
             const bool present = (Li < k) && (off[2 * Li + 2] > off[2 * Li]);
@@ -356,6 +346,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
                 mbar_expect_tx(&bars[warp * S + s], slot_bytes_tx);
                 bulk_g2s(smem_u32(slots + (size_t)s * P.slot_floats), pr.x + t_idx * (size_t)(d * kSlotCells), slot_bytes_tx,
                          smem_u32(&bars[warp * S + s]));
+                // the tile this warp will want after that one: pull it into L2 now, so its bulk copy (issued only when the
+                // slot is free again) pays L2 latency instead of HBM latency
+                if (i + 1 < count) bulk_prefetch_l2(pr.x + (t_idx + W) * (size_t)(d * kSlotCells), slot_bytes_tx);
             }
         };
         for (int i = 0; i < min(S, count); ++i) issue(i);

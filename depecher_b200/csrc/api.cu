@@ -81,8 +81,13 @@ static int dataset_alloc(int64_t n, int32_t d, dpr_dataset** out) {
     const size_t bytes = sizeof(float) * (size_t)ds->n_pad * d;
     DPR_CUDA(cudaMalloc(&ds->x, bytes));
     DPR_CUDA(cudaMemsetAsync(ds->x, 0, bytes, ctx().stream));
+    DPR_CUDA(cudaMalloc(&ds->tile_xx, sizeof(float) * (size_t)(ds->n_pad / kSlotCells)));
     *out = ds.release();
     return DPR_OK;
+}
+// after the cells are in place: the per-tile norm bounds the fused pass reads
+static int dataset_finish(dpr_dataset* ds) {
+    return launch_tile_norms(ds->x, ds->n_pad / kSlotCells, ds->d, ds->tile_xx, ctx().stream);
 }
 static int dataset_labels(dpr_dataset* ds) {
     if (!ds->labels) DPR_CUDA(cudaMalloc(&ds->labels, sizeof(int32_t) * (size_t)ds->n_pad));
@@ -144,6 +149,7 @@ static int dataset_upload(dpr_dataset* ds, const T* X) {
         DPR_CUDA(cudaEventRecord(g_stage.done[b], ctx().stream));
         DPR_TRY(launch_f32_to_cols(g_stage.dev[b], e0, cnt, ds->n, ds->d, ds->x, ctx().stream));
     }
+    DPR_TRY(dataset_finish(ds));
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));
     return DPR_OK;
 }
@@ -152,7 +158,7 @@ static int dataset_upload(dpr_dataset* ds, const T* X) {
 static int single_session(dpr_dataset* ds, int k, double reg, int no_zero, bool want_sums, Session& s) {
     DPR_TRY(dataset_labels(ds));
     std::vector<ProblemSpec> specs(1);
-    specs[0] = ProblemSpec{ds->x, ds->n, k, reg, no_zero, ds->labels};
+    specs[0] = ProblemSpec{ds->x, ds->tile_xx, ds->n, k, reg, no_zero, ds->labels};
     return s.init(specs, ds->d, want_sums);
 }
 
@@ -400,6 +406,7 @@ int dpr_dataset_create_synthetic(int64_t n, int32_t d, int32_t groups, double am
     const double used = scale > 0 ? scale : std::sqrt(var);
     if (scale_out) *scale_out = used;
     if (rc == DPR_OK) rc = launch_scale(ds->x, ds->n_pad, d, (float)(1.0 / used), ctx().stream);
+    if (rc == DPR_OK) rc = dataset_finish(ds);
     if (rc == DPR_OK && cudaStreamSynchronize(ctx().stream) != cudaSuccess) rc = fail(DPR_ERR_CUDA, "synthetic generation failed");
     if (rc != DPR_OK) { dpr_dataset_destroy(ds); return rc; }
     *out = ds;
@@ -409,6 +416,7 @@ int dpr_dataset_destroy(dpr_dataset_t ds) {
     if (!ds) return DPR_OK;
     bench_session_forget(ds);
     if (ds->x) cudaFree(ds->x);
+    if (ds->tile_xx) cudaFree(ds->tile_xx);
     if (ds->labels) cudaFree(ds->labels);
     delete ds;
     return DPR_OK;
@@ -439,6 +447,7 @@ int dpr_dataset_gather(dpr_dataset_t ds, const int64_t* rows, int64_t m, dpr_dat
     if (rc == DPR_OK && cudaMemcpyAsync(dr.p, rows, sizeof(int64_t) * m, cudaMemcpyHostToDevice, ctx().stream) != cudaSuccess)
         rc = fail(DPR_ERR_CUDA, "copy of row indices failed");
     if (rc == DPR_OK) rc = launch_gather(ds->x, ds->n, ds->d, dr.as<int64_t>(), 0, 0, m, g->x, 1, 0, ctx().stream);
+    if (rc == DPR_OK) rc = dataset_finish(g);
     if (rc == DPR_OK && cudaStreamSynchronize(ctx().stream) != cudaSuccess) rc = fail(DPR_ERR_CUDA, "gather failed");
     if (rc != DPR_OK) { dpr_dataset_destroy(g); return rc; }
     *out = g;
@@ -619,6 +628,10 @@ static int grid_search_impl(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
     DPR_TRY(xb.alloc(sizeof(float) * (size_t)F * ldb * d, true));
     DPR_TRY(lab_b.alloc(sizeof(int32_t) * (size_t)F * ldb, true));
     DPR_TRY(launch_gather(ds->x, ds->n, d, nullptr, seed, 0, boot_n, xb.as<float>(), F, ldb * d, ctx().stream));
+    DevBuf xb_xx;   // the F bootstrap matrices are back to back and each is a whole number of tiles
+    const int64_t tiles_b = ldb / kSlotCells;
+    DPR_TRY(xb_xx.alloc(sizeof(float) * (size_t)F * tiles_b));
+    DPR_TRY(launch_tile_norms(xb.as<float>(), (int64_t)F * tiles_b, d, xb_xx.as<float>(), ctx().stream));
     // 2. the fits (find_centers with zero-centre removal, :361-362)
     std::vector<ProblemSpec> specs(F);
     auto cell_of = [&](int f, int& it, int& j, int& l) {
@@ -630,7 +643,8 @@ static int grid_search_impl(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
     for (int f = 0; f < F; ++f) {
         int it, j, l;
         cell_of(f, it, j, l);
-        specs[f] = ProblemSpec{xb.as<float>() + (size_t)f * ldb * d, (int64_t)boot_n, k[j], reg[l], 1, lab_b.as<int32_t>() + (size_t)f * ldb};
+        specs[f] = ProblemSpec{xb.as<float>() + (size_t)f * ldb * d, xb_xx.as<float>() + (size_t)f * tiles_b, (int64_t)boot_n, k[j], reg[l], 1,
+                               lab_b.as<int32_t>() + (size_t)f * ldb};
     }
     Session fits;
     DPR_TRY(fits.init(specs, d, true));
@@ -659,7 +673,7 @@ static int grid_search_impl(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
     DPR_TRY(lab_full.alloc(sizeof(int32_t) * (size_t)F * ds->n_pad));
     std::vector<ProblemSpec> sspecs(F);
     for (int f = 0; f < F; ++f)
-        sspecs[f] = ProblemSpec{ds->x, ds->n, specs[f].k, 0.0, 0, lab_full.as<int32_t>() + (size_t)f * ds->n_pad};
+        sspecs[f] = ProblemSpec{ds->x, ds->tile_xx, ds->n, specs[f].k, 0.0, 0, lab_full.as<int32_t>() + (size_t)f * ds->n_pad};
     Session score;
     DPR_TRY(score.init(sspecs, d, false));
     for (int f = 0; f < F; ++f) DPR_TRY(score.set_centres_device(f, fits.h_problems[f].mu));
@@ -738,7 +752,7 @@ int dpr_dataset_allocate_many(dpr_dataset_t ds, const double* mus, int32_t m, in
     DevBuf lab;
     DPR_TRY(lab.alloc(sizeof(int32_t) * (size_t)m * ds->n_pad));
     std::vector<ProblemSpec> specs(m);
-    for (int s = 0; s < m; ++s) specs[s] = ProblemSpec{ds->x, ds->n, k, 0.0, no_zero, lab.as<int32_t>() + (size_t)s * ds->n_pad};
+    for (int s = 0; s < m; ++s) specs[s] = ProblemSpec{ds->x, ds->tile_xx, ds->n, k, 0.0, no_zero, lab.as<int32_t>() + (size_t)s * ds->n_pad};
     Session sess;
     DPR_TRY(sess.init(specs, d, false));
     std::vector<double> rm;

@@ -37,6 +37,32 @@ __global__ void cols_to_f64_kernel(const float* __restrict__ x, int64_t row0, in
 }
 
 // ---------------------------------------------------------------------------------------------------
+// per-tile upper bound of ||x||^2 (one warp per tile).  The fused pass needs ||x||^2 only inside the proven error
+// bound that decides which cells are re-examined in fp64; a bound shared by the 64 cells of a tile is as safe and
+// saves two FMAs per marker and lane in the hot loop.
+// ---------------------------------------------------------------------------------------------------
+__global__ void tile_norms_kernel(const float* __restrict__ x, int64_t n_tiles, int d, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = warp; t < n_tiles; t += nwarps) {
+        const float2* row = reinterpret_cast<const float2*>(x + t * (int64_t)d * kSlotCells);
+        float a = 0.f, b = 0.f;
+        for (int j = 0; j < d; ++j) {
+            const float2 v = row[j * (kSlotCells / 2) + lane];   // any permutation inside a row is fine for a maximum over the tile
+            a = fmaf(v.x, v.x, a);
+            b = fmaf(v.y, v.y, b);
+        }
+        float m = a > b ? a : b;
+        if (a != a || b != b) m = INFINITY;                      // a NaN cell: every cell of the tile is decided exactly
+        for (int o = 16; o > 0; o >>= 1) {
+            const float w = __shfl_xor_sync(0xffffffffu, m, o);
+            m = w > m ? w : m;
+        }
+        if (lane == 0) out[t] = m * 1.00001f;                    // covers the fp32 rounding of the squared norm itself
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // bootstrap_data (src/Clusterer.cpp:308-321): rows drawn with replacement, gathered into a new matrix.
 // rows_explicit == nullptr -> row = Philox(seed, BOOT, fit, i) % n   (include/dpr_philox.h)
 // ---------------------------------------------------------------------------------------------------
@@ -385,6 +411,12 @@ int launch_f32_to_cols(const float* src, int64_t e0, int64_t count, int64_t n, i
 }
 int launch_cols_to_f64(const float* x, int64_t row0, int64_t rows, int d, double* out, cudaStream_t st) {
     cols_to_f64_kernel<<<blocks_for(rows * d), 256, 0, st>>>(x, row0, rows, d, out);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_tile_norms(const float* x, int64_t n_tiles, int d, float* out, cudaStream_t st) {
+    tile_norms_kernel<<<blocks_for(n_tiles * 32), 256, 0, st>>>(x, n_tiles, d, out);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;

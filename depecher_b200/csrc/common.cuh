@@ -71,6 +71,7 @@ struct CentreHeader {
 // One problem = one data matrix + one centre set (+ the state of its Lloyd loop).  Device-resident array.
 struct Problem {
     const float* x;       // resident fp32 cells, tile-major (see x_index)
+    const float* tile_xx; // per tile: an upper bound of ||x||^2 over its cells (enters the near-tie threshold)
     int64_t n;            // cells
     int32_t d;
     int32_t k;
@@ -120,5 +121,6 @@ struct dpr_dataset {
     int32_t d = 0;
     int64_t n_pad = 0;         // n rounded up to whole tiles
     float* x = nullptr;        // device, tile-major (dpr::x_index), n_pad * d floats
+    float* tile_xx = nullptr;  // device, n_pad / 64 floats: max ||x||^2 of each tile (rounded up)
     int32_t* labels = nullptr; // device, n_pad entries (lazily allocated)
 };

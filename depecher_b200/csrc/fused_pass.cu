@@ -73,9 +73,9 @@ __device__ __forceinline__ float pack_idx(float s, int idx) {
     return __uint_as_float((__float_as_uint(s) & 0xFFFFFFE0u) | (unsigned)idx);
 }
 
-template <int KC, bool FIRST>
+template <int KC>
 __device__ __forceinline__ void dist_chunk(const float* __restrict__ slot, const float* __restrict__ tab, int d, int lane,
-                                           float (&xx)[2], float (&best)[2], float (&second)[2]) {
+                                           float (&best)[2], float (&second)[2]) {
     constexpr int NP = KC / 2;
     constexpr int KCP = (KC + 3) & ~3;
     float2 acc[2][NP];
@@ -104,10 +104,6 @@ __device__ __forceinline__ void dist_chunk(const float* __restrict__ slot, const
                 acc[1][2 * q + 1] = __ffma2_rn(x1, make_float2(c.z, c.w), acc[1][2 * q + 1]);
             }
         }
-        if (FIRST) {
-            xx[0] = fmaf(xv.x, xv.x, xx[0]);
-            xx[1] = fmaf(xv.y, xv.y, xx[1]);
-        }
     }
     // two smallest packed scores per cell: merge the sorted pair (lo, hi) of each accumulator pair
 #pragma unroll
@@ -123,13 +119,12 @@ __device__ __forceinline__ void dist_chunk(const float* __restrict__ slot, const
     }
 }
 
-template <bool FIRST>
-__device__ __forceinline__ void dist_chunk_dispatch(int kc, const float* slot, const float* tab, int d, int lane, float (&xx)[2],
-                                                    float (&best)[2], float (&second)[2]) {
+__device__ __forceinline__ void dist_chunk_dispatch(int kc, const float* slot, const float* tab, int d, int lane, float (&best)[2],
+                                                    float (&second)[2]) {
     switch (kc) {
 #define DPR_CASE(KC)                                                \
     case KC:                                                        \
-        dist_chunk<KC, FIRST>(slot, tab, d, lane, xx, best, second); \
+        dist_chunk<KC>(slot, tab, d, lane, best, second);            \
         break;
         DPR_CASE(2) DPR_CASE(4) DPR_CASE(6) DPR_CASE(8) DPR_CASE(10) DPR_CASE(12) DPR_CASE(14) DPR_CASE(16)
         DPR_CASE(18) DPR_CASE(20) DPR_CASE(22) DPR_CASE(24) DPR_CASE(26) DPR_CASE(28) DPR_CASE(30) DPR_CASE(32)
@@ -365,6 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
                 if (full2) oldl = *reinterpret_cast<const int2*>(pr.labels + mycell);
                 else if (mycell < pr.n) oldl.x = pr.labels[mycell];
             }
+            const float xx_tile = pr.tile_xx[first + i * W - pr.first_tile];   // bound of ||x||^2 over this slot's cells
             mbar_wait(&bars[warp * S + s], (phase >> s) & 1u);
             phase ^= (1u << s);
 
@@ -373,20 +369,19 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
                 lab[0] = oldl.x;
                 lab[1] = oldl.y;
             } else if (!trivial) {
-                float xx[2] = {0.f, 0.f};
                 float best[2] = {3.3e38f, 3.3e38f}, second[2] = {3.3e38f, 3.3e38f};
                 int bchunk[2] = {0, 0};
-                dist_chunk_dispatch<true>(chunk0_kc, slot, table + chunk0_off, d, lane, xx, best, second);
+                dist_chunk_dispatch(chunk0_kc, slot, table + chunk0_off, d, lane, best, second);
                 for (int q = 1; q < n_chunks; ++q) {
                     const float prev0 = best[0], prev1 = best[1];
-                    dist_chunk_dispatch<false>(hdr->chunk_kc[q], slot, table + hdr->chunk_off[q], d, lane, xx, best, second);
+                    dist_chunk_dispatch(hdr->chunk_kc[q], slot, table + hdr->chunk_off[q], d, lane, best, second);
                     if (best[0] < prev0) bchunk[0] = q;
                     if (best[1] < prev1) bchunk[1] = q;
                 }
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     const int a = hdr->chunk_base[bchunk[r]] + (int)(__float_as_uint(best[r]) & 31u);
-                    const float tau = tau_c * (xx[r] + cc2);
+                    const float tau = tau_c * (xx_tile + cc2);
                     const bool sure = (second[r] - best[r] > tau) && !force_exact;
                     lab[r] = orig[a < n_slots ? a : 0];
                     unsigned redo = __ballot_sync(0xffffffffu, !sure && (mycell + r < pr.n));

@@ -57,6 +57,7 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
         Problem& pr = h_problems[p];
         const ProblemSpec& s = specs[p];
         pr.x = s.x;
+        pr.tile_xx = s.tile_xx;
         pr.n = s.n;
         pr.d = d;
         pr.k = s.k;

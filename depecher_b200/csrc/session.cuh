@@ -14,7 +14,8 @@
 namespace dpr {
 
 struct ProblemSpec {
-    const float* x;    // tile-major resident cells
+    const float* x;        // tile-major resident cells
+    const float* tile_xx;  // per-tile bound of ||x||^2
     int64_t n;
     int32_t k;
     double reg;

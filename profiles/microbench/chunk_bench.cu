@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(512, 1) k_chunk(float* out, int d, int slots_p
     for (int s = 0; s < slots_per_warp; ++s) {
         float xx[2] = {0.f, 0.f}, best[2] = {3e38f, 3e38f}, second[2] = {3e38f, 3e38f};
         if (FOLD_ONLY) dist_chunk_sp<KC>(slot, table, d, lane, xx, best, second);
-        else dist_chunk<KC, true>(slot, table, d, lane, xx, best, second);
+        else dist_chunk<KC>(slot, table, d, lane, best, second);   // the product's micro-kernel
         acc_out += best[0] + best[1] + second[0] + second[1] + xx[0] + xx[1];
         table[0] = acc_out * 1e-30f;   // keep iterations dependent
     }

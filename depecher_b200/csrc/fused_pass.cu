@@ -334,23 +334,28 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
 
         const int first = tile + warp;
         const int count = first < p_end ? (p_end - first + W - 1) / W : 0;
-        auto issue = [&](int i) {   // ONE bulk-async copy: a tile is contiguous (and already swizzled) in HBM
+        // ONE bulk-async copy per slot: a tile is contiguous (and already swizzled) in HBM.  Tiles of this warp are W apart.
+        const size_t tile_floats = (size_t)d * kSlotCells;
+        const float* next_src = pr.x + (size_t)(first - pr.first_tile) * tile_floats;   // tile the next issue() loads
+        int issued = 0, s_issue = 0;
+        auto issue = [&]() {
             if (lane == 0) {
-                const int s = i % S;
-                const size_t t_idx = (size_t)(first + i * W - pr.first_tile);
-                mbar_expect_tx(&bars[warp * S + s], slot_bytes_tx);
-                bulk_g2s(smem_u32(slots + (size_t)s * P.slot_floats), pr.x + t_idx * (size_t)(d * kSlotCells), slot_bytes_tx,
-                         smem_u32(&bars[warp * S + s]));
+                mbar_expect_tx(&bars[warp * S + s_issue], slot_bytes_tx);
+                bulk_g2s(smem_u32(slots + (size_t)s_issue * P.slot_floats), next_src, slot_bytes_tx, smem_u32(&bars[warp * S + s_issue]));
                 // the tile this warp will want after that one: pull it into L2 now, so its bulk copy (issued only when the
                 // slot is free again) pays L2 latency instead of HBM latency
-                if (i + 1 < count) bulk_prefetch_l2(pr.x + (t_idx + W) * (size_t)(d * kSlotCells), slot_bytes_tx);
+                if (issued + 1 < count) bulk_prefetch_l2(next_src + (size_t)W * tile_floats, slot_bytes_tx);
             }
+            next_src += (size_t)W * tile_floats;
+            ++issued;
+            s_issue = (s_issue + 1 == S) ? 0 : s_issue + 1;
         };
-        for (int i = 0; i < min(S, count); ++i) issue(i);
+        for (int i = 0; i < min(S, count); ++i) issue();
 
-        for (int i = 0; i < count; ++i) {
-            const int s = i % S;
-            const int64_t cell0 = (int64_t)(first + i * W - pr.first_tile) * kSlotCells;
+        int s = 0;   // slot of tile i: advances round-robin like s_issue (no runtime modulo in the loop)
+        int64_t cell0 = (int64_t)(first - pr.first_tile) * kSlotCells;
+        const float* xx_ptr = pr.tile_xx + (first - pr.first_tile);
+        for (int i = 0; i < count; ++i, cell0 += (int64_t)W * kSlotCells, xx_ptr += W) {
             const int64_t mycell = cell0 + 2 * lane;
             const float* slot = slots + (size_t)s * P.slot_floats;
             // previous labels (the reference compares against the previous assignment, Clusterer.cpp:247)
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
                 if (full2) oldl = *reinterpret_cast<const int2*>(pr.labels + mycell);
                 else if (mycell < pr.n) oldl.x = pr.labels[mycell];
             }
-            const float xx_tile = pr.tile_xx[first + i * W - pr.first_tile];   // bound of ||x||^2 over this slot's cells
+            const float xx_tile = *xx_ptr;   // bound of ||x||^2 over this slot's cells
             mbar_wait(&bars[warp * S + s], (phase >> s) & 1u);
             phase ^= (1u << s);
 
@@ -450,7 +455,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
                 }
             }
             __syncwarp();
-            if (i + S < count) issue(i + S);
+            if (issued < count) issue();
+            s = (s + 1 == S) ? 0 : s + 1;
         }
         // ---- combine the warps' tables of this (CTA, problem) in fixed order; reset them for the next range
         if (P.cta_tables) {

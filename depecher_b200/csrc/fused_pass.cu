@@ -433,15 +433,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
                             const int newL = __shfl_sync(0xffffffffu, lab[r], src);
                             const int oldL = __shfl_sync(0xffffffffu, r ? oldl.y : oldl.x, src);
                             const int c = 2 * src + r;
-                            for (int jb = 0; jb < d; jb += 32) {
-                                const int j = jb + lane;
-                                if (j < d) {
-                                    const double v = (double)slot[x_slot_index(c, j)];
-                                    double* pa = my_sums + (size_t)newL * d + j;
-                                    double* pb = my_sums + (size_t)oldL * d + j;
-                                    const double a = __ldcg(pa), b = __ldcg(pb);
-                                    __stcg(pa, a + v);
-                                    __stcg(pb, b - v);
+                            double* ta = my_sums + (size_t)newL * d;
+                            double* tb = my_sums + (size_t)oldL * d;
+                            for (int jb = 0; jb < d; jb += 64) {   // two markers per lane: four table loads in flight at once
+                                const int j0 = jb + lane, j1 = jb + 32 + lane;
+                                const bool on0 = j0 < d, on1 = j1 < d;
+                                const double v0 = on0 ? (double)slot[x_slot_index(c, j0)] : 0.0;
+                                const double v1 = on1 ? (double)slot[x_slot_index(c, j1)] : 0.0;
+                                const double a0 = on0 ? __ldcg(ta + j0) : 0.0, b0 = on0 ? __ldcg(tb + j0) : 0.0;
+                                const double a1 = on1 ? __ldcg(ta + j1) : 0.0, b1 = on1 ? __ldcg(tb + j1) : 0.0;
+                                if (on0) {
+                                    __stcg(ta + j0, a0 + v0);
+                                    __stcg(tb + j0, b0 - v0);
+                                }
+                                if (on1) {
+                                    __stcg(ta + j1, a1 + v1);
+                                    __stcg(tb + j1, b1 - v1);
                                 }
                             }
                             if (lane == 0) {

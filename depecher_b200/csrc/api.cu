@@ -668,25 +668,29 @@ static int grid_search_impl(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
     // distinct labels of each bootstrap fit (n_used_clusters, :379-380) = clusters with a non-zero count
     std::vector<long long> counts((size_t)F * fits.k_max());
     DPR_CUDA(cudaMemcpyAsync(counts.data(), fits.h_problems[0].counts, sizeof(long long) * counts.size(), cudaMemcpyDeviceToHost, ctx().stream));
-    // 3. score on the full data, no_zero = false (:370-371)
-    DevBuf lab_full;
-    DPR_TRY(lab_full.alloc(sizeof(int32_t) * (size_t)F * ds->n_pad));
-    std::vector<ProblemSpec> sspecs(F);
-    for (int f = 0; f < F; ++f)
-        sspecs[f] = ProblemSpec{ds->x, ds->tile_xx, ds->n, specs[f].k, 0.0, 0, lab_full.as<int32_t>() + (size_t)f * ds->n_pad};
-    Session score;
-    DPR_TRY(score.init(sspecs, d, false));
-    for (int f = 0; f < F; ++f) DPR_TRY(score.set_centres_device(f, fits.h_problems[f].mu));
-    DPR_TRY(score.prepare());
-    DPR_TRY(score.pass(kPassAssign, false));
-    // 4. ARI per cell; tables are sized by the largest k
+    // 3. score on the full data, no_zero = false (:370-371), and 4. ARI per cell.  The label arrays of a batch of
+    //    cells are bounded (4 GB), so a 100M-cell matrix is scored a few cells at a time instead of all 2 * cells at once.
     int kmax = 0;
     for (int j = 0; j < nk; ++j) kmax = std::max(kmax, (int)k[j]);
-    std::vector<PairJob> pairs(cells);
-    for (int c = 0; c < cells; ++c)
-        pairs[c] = PairJob{sspecs[2 * c].labels, sspecs[2 * c + 1].labels, ds->n, (uint32_t)c};
     std::vector<double> ari(cells);
-    DPR_TRY(run_ari(pairs, (uint32_t)kmax, seed, ari.data()));
+    const size_t per_cell_bytes = 2 * sizeof(int32_t) * (size_t)ds->n_pad;
+    const int batch_cells = (int)std::max<size_t>(1, std::min<size_t>((size_t)cells, ((size_t)4 << 30) / per_cell_bytes));
+    DevBuf lab_full;
+    DPR_TRY(lab_full.alloc(per_cell_bytes * (size_t)batch_cells));
+    for (int c0 = 0; c0 < cells; c0 += batch_cells) {
+        const int nc = std::min(batch_cells, cells - c0);
+        std::vector<ProblemSpec> sspecs(2 * nc);
+        for (int q = 0; q < 2 * nc; ++q)
+            sspecs[q] = ProblemSpec{ds->x, ds->tile_xx, ds->n, specs[2 * c0 + q].k, 0.0, 0, lab_full.as<int32_t>() + (size_t)q * ds->n_pad};
+        Session score;
+        DPR_TRY(score.init(sspecs, d, false));
+        for (int q = 0; q < 2 * nc; ++q) DPR_TRY(score.set_centres_device(q, fits.h_problems[2 * c0 + q].mu));
+        DPR_TRY(score.prepare());
+        DPR_TRY(score.pass(kPassAssign, false));
+        std::vector<PairJob> pairs(nc);
+        for (int c = 0; c < nc; ++c) pairs[c] = PairJob{sspecs[2 * c].labels, sspecs[2 * c + 1].labels, ds->n, (uint32_t)(c0 + c)};
+        DPR_TRY(run_ari(pairs, (uint32_t)kmax, seed, ari.data() + c0));
+    }
     // 5. per-iteration results: ARI of the cell and the mean number of used clusters of its two fits
     size_t coff = 0;
     for (int c = 0; c < cells; ++c) {

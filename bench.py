@@ -125,7 +125,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -191,11 +191,13 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
 
     # A step = one fused Lloyd iteration of a FRESH fit (iterations 0, 1, 2, ... of find_centers: all labels change in
     # iteration 0, the penalty ramps up over the first 20, dying clusters drop out) - not a converged steady state.
+    sampler = ClockSampler(local_rank)   # samples from the warm-up on, so that a short timed region still has clock readings under load
+    sampler.start()
     eng.lloyd_iterations(ds, mu0, reg, True, -1, max(args.warmup, 3))             # warm-up (>= 3 steps)
+    for _ in range(3):                                                            # keep the GPU busy ~100 ms for the sampler
+        eng.lloyd_iterations(ds, mu0, reg, True, -1, 30)
     eng.pass_timing(True)
     launches0 = eng.kernel_launches(reset=True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

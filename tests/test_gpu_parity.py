@@ -215,3 +215,37 @@ def test_allocate_many_matches_single(engine, oracle):
         for j in range(5):
             assert abs(ari[i, j] - oracle.rand_index_exact(lab[j] + 1, lab[i] + 1, 9)) < 1e-12
     assert np.allclose(np.diag(ari), 1.0)
+
+
+# ---------------------------------------------------------------------------------------------- edges of the supported range
+@pytest.mark.parametrize("n,d,k", [(63, 1, 2), (64, 1, 3), (65, 2, 2), (1000, 3, 240), (4097, 64, 31), (300, 200, 7)])
+def test_edge_shapes(engine, oracle, n, d, k):
+    rng = np.random.default_rng(n + d + k)
+    X = blobs(rng, n, d, 3)
+    mu = blobs(rng, k, d, 3)
+    assert np.array_equal(engine.allocate_points(X, mu, False)["i"], oracle.allocate_points(X, mu, False))
+    idx = rng.integers(0, k, n).astype(np.int32)
+    got, cnt = engine.reevaluate_centers(X, idx, k, 1.5)
+    want, wcnt = oracle.reevaluate_centers(X, idx, k, 1.5)
+    assert np.array_equal(cnt, wcnt)
+    centres_close(got, want)
+
+
+def test_unsupported_shapes_and_bad_arguments_fail_loudly(engine):
+    import depecher_b200 as dp
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(200, 4))
+    with pytest.raises(dp.DepecherError, match="not supported"):
+        engine.allocate_points(X, rng.normal(size=(241, 4)), False)          # more than 240 centres
+    with pytest.raises(dp.DepecherError, match="not supported"):
+        engine.allocate_points(rng.normal(size=(10, 1000)), rng.normal(size=(3, 1000)), False)   # a slot would not fit in shared memory
+    with pytest.raises(dp.DepecherError):
+        engine.sparse_k_means(X, 1, 1.0, True)                               # k >= 2 (Clusterer.cpp:157-162 writes two rows)
+    with pytest.raises(dp.DepecherError):
+        engine.reevaluate_centers(X, np.full(200, 9, np.int32), 5, 0.0)      # label outside [0, k)
+    with pytest.raises(dp.DepecherError):
+        engine.grid_search(X, [1], [1.0], 1, 50)
+    # all-identical cells: every k-means++ weight is zero after the first pick; the reference then picks row 0 again
+    same = np.ones((100, 3))
+    mu, rows = engine.initialize_mu(same, 4, seed=1)
+    assert np.array_equal(mu, np.ones((4, 3))) and (rows[1:] == 0).all()

@@ -278,6 +278,18 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         line["e2e"] = {"value": float(n_local) * K * res["n_iter"] / dt, "unit": UNIT, "h2d_bytes_per_step": int(Xh.nbytes),
                        "d2h_bytes_per_step": int(res["i"].nbytes + res["c"].nbytes), "seconds": dt, "lloyd_iterations": res["n_iter"],
                        "k_active_final": k_e2e, "call": "dpr_sparse_k_means(host double*, ...) - H2D, k-means++ seeding, Lloyd loop, D2H inside"}
+        # the other half of the metric: depeche() itself on the 10M x 40 host matrix - upload, device-side pre-scaling
+        # (kurtosis test, histogram-peak centring, global sd), full default penalty sweep, solution selection, final allocation
+        try:
+            from depecher_b200 import rapi
+            t0 = time.perf_counter()
+            dep = rapi.depeche(Xh, nCores=10, engine=eng, seed=SEED + 1)
+            line["depeche_call_10Mx40"] = {"seconds": time.perf_counter() - t0, "bestPenalty": dep["penaltyOptList"]["bestPenalty"],
+                                           "clusters": int(dep["clusterCenters"].shape[0]),
+                                           "workerIterations": dep["penaltyOptList"]["workerIterations"],
+                                           "call": "depecher_b200.rapi.depeche(host double matrix, nCores=10): everything inside"}
+        except Exception as exc:
+            line["depeche_call_10Mx40"] = {"error": repr(exc)}
         workers = host_workers()
         rows = 60_000
         sample = np.array(Xh[:rows])

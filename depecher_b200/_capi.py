@@ -139,6 +139,33 @@ class Engine:
             self._chk(self.lib.dpr_dataset_create(_ptr(Xf, _dp), C.c_int64(X.shape[0]), C.c_int32(X.shape[1]), C.byref(h)))
         return Dataset(self, h, X.shape[0], X.shape[1])
 
+    def dataset_scaled(self, X, log2Off=False, center="default", scale=True):
+        """depecheLogCenterSd (R/depecheLogCenterSd.R:6-115) on the device -> (resident scaled Dataset, [log2 applied, centres | False, sd])"""
+        Xf = _f64(X)
+        n, d = Xf.shape
+        centres = np.zeros(d, np.float64)
+        if isinstance(center, str):
+            if center not in ("default", "peak", "mean"):
+                raise DepecherError("center must be 'default', 'peak', 'mean', False or a vector")
+            mode = 1 if (center == "peak" or (center == "default" and d <= 100)) else 2
+        elif center is False:
+            mode = 0
+        else:
+            mode = 3
+            centres[:] = np.asarray(center, np.float64)
+        sd = C.c_double(1.0)
+        if scale is True:
+            smode = 1
+        elif scale is False:
+            smode = 0
+        else:
+            smode, sd = 2, C.c_double(float(scale))
+        applied, h = C.c_int32(), C.c_void_p()
+        self._chk(self.lib.dpr_dataset_create_scaled(_ptr(Xf, _dp), C.c_int64(n), C.c_int32(d), C.c_int32(int(bool(log2Off))), C.c_int32(mode),
+                                                     _ptr(centres, _dp), C.c_int32(smode), C.byref(sd), C.byref(applied), C.byref(h)))
+        info = [bool(applied.value), (centres if mode != 0 else False), (sd.value if smode != 0 else 1)]
+        return Dataset(self, h, n, d), info
+
     def synthetic(self, n: int, d: int, groups: int, amplitude: float, seed: int, row0: int = 0, scale: float = 0.0) -> Dataset:
         h = C.c_void_p()
         used = C.c_double()

@@ -10,6 +10,7 @@
 #include "aux_kernels.cuh"
 #include "comm.cuh"
 #include "common.cuh"
+#include "scale.cuh"
 #include "session.cuh"
 #include "../../include/dpr_philox.h"
 
@@ -412,6 +413,219 @@ int dpr_dataset_create_synthetic(int64_t n, int32_t d, int32_t groups, double am
     *out = ds;
     return DPR_OK;
 }
+// ---- depecheLogCenterSd on the device (R/depecheLogCenterSd.R:6-115) ----------------------------------------
+namespace {
+// R's pretty(c(lo, hi), n, min.n = 1) as hist.default calls it (R_pretty in src/appl/pretty.c + seq.int of the bounds)
+std::vector<double> r_pretty_breaks(double lo, double hi, int ndiv) {
+    const double h = 1.5, h5 = 0.5 + 1.5 * h, eps = 1e-10;
+    const int min_n = 1;
+    double dx = hi - lo, cell;
+    bool i_small;
+    if (dx == 0 && hi == 0) {
+        cell = 1;
+        i_small = true;
+    } else {
+        cell = std::max(std::fabs(lo), std::fabs(hi));
+        double U = 1 + ((h5 >= 1.5 * h + .5) ? 1 / (1 + h) : 1.5 / (1 + h5));
+        U *= std::max(1, ndiv) * 2.220446049250313e-16;
+        i_small = dx < cell * U * 3;
+    }
+    if (i_small) {
+        if (cell > 10) cell = 9 + cell / 10;
+        cell *= 0.75;
+    } else {
+        cell = dx;
+        if (ndiv > 1) cell /= ndiv;
+    }
+    cell = std::max(cell, 20 * 2.2250738585072014e-308);
+    const double base = std::pow(10.0, std::floor(std::log10(cell)));
+    double unit = base;
+    if (2 * base - cell < h * (cell - unit)) {
+        unit = 2 * base;
+        if (5 * base - cell < h5 * (cell - unit)) {
+            unit = 5 * base;
+            if (10 * base - cell < h * (cell - unit)) unit = 10 * base;
+        }
+    }
+    double ns = std::floor(lo / unit + eps), nu = std::ceil(hi / unit - eps);
+    while (ns * unit > lo + eps * unit) ns--;
+    while (nu * unit < hi - eps * unit) nu++;
+    int k = (int)(0.5 + nu - ns);
+    if (k < min_n) {
+        k = min_n - k;
+        if (ns >= 0.) { nu += k / 2; ns -= k / 2 + k % 2; }
+        else { ns -= k / 2; nu += k / 2 + k % 2; }
+        k = min_n;
+    }
+    // seq.int(l, u, length.out = k + 1): ends exact, interior l + i * by
+    const double l = ns * unit, u = nu * unit;
+    std::vector<double> b((size_t)k + 1);
+    const double by = k > 0 ? (u - l) / k : 0.0;
+    for (int i = 0; i <= k; ++i) b[i] = l + i * by;
+    b[0] = l;
+    b[k] = u;
+    const double delta = k > 0 ? (u - l) / k : 0.0;
+    for (double& v : b)
+        if (std::fabs(v) < 1e-14 * delta) v = 0.0;
+    return b;
+}
+double median_of(std::vector<double> v) {
+    std::sort(v.begin(), v.end());
+    const size_t m = v.size();
+    return m % 2 ? v[m / 2] : 0.5 * (v[m / 2 - 1] + v[m / 2]);
+}
+}  // namespace
+
+int dpr_dataset_create_scaled(const double* X, int64_t n, int32_t d, int32_t log2_off, int32_t center_mode, double* centers_inout,
+                              int32_t scale_mode, double* scale_inout, int32_t* log2_applied_out, dpr_dataset_t* out) {
+    if (!X || n < 2 || d < 1 || !out) return fail(DPR_ERR_INVALID, "create_scaled: null argument or too few rows");
+    if (center_mode < 0 || center_mode > 3 || scale_mode < 0 || scale_mode > 2) return fail(DPR_ERR_INVALID, "create_scaled: unknown mode");
+    if ((center_mode == 3 && !centers_inout) || (scale_mode == 2 && !scale_inout)) return fail(DPR_ERR_INVALID, "create_scaled: missing values");
+    dpr_dataset* ds = nullptr;
+    DPR_TRY(dataset_alloc(n, d, &ds));
+    std::unique_ptr<dpr_dataset, int (*)(dpr_dataset*)> guard(ds, dpr_dataset_destroy);
+    const int B = stat_blocks();
+    const int64_t total = n * d;
+    DevBuf raw, part, dvec;
+    DPR_TRY(raw.alloc(sizeof(double) * total));
+    DPR_TRY(part.alloc(sizeof(double) * 3 * B * d));
+    DPR_TRY(dvec.alloc(sizeof(double) * 2 * d));
+    // raw doubles to the device through the pinned staging area (as bytes)
+    {
+        const int64_t chunk = std::min<int64_t>(total, (int64_t)16 << 20);
+        DPR_TRY(upload_stage(2 * chunk));
+        const int threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        int b = 0;
+        for (int64_t e0 = 0; e0 < total; e0 += chunk, b ^= 1) {
+            const int64_t cnt = std::min(chunk, total - e0);
+            DPR_CUDA(cudaEventSynchronize(g_stage.done[b]));
+            double* pin = reinterpret_cast<double*>(g_stage.pinned[b]);
+            std::vector<std::thread> pool;
+            for (int t = 0; t < threads; ++t)
+                pool.emplace_back([=] { const int64_t a0 = cnt * t / threads, a1 = cnt * (t + 1) / threads; std::memcpy(pin + a0, X + e0 + a0, sizeof(double) * (a1 - a0)); });
+            for (auto& th : pool) th.join();
+            DPR_CUDA(cudaMemcpyAsync(raw.as<double>() + e0, pin, sizeof(double) * cnt, cudaMemcpyHostToDevice, ctx().stream));
+            DPR_CUDA(cudaEventRecord(g_stage.done[b], ctx().stream));
+        }
+    }
+    std::vector<double> hp((size_t)3 * B * d), colsum(d), colmin(d), colmax(d);
+    auto col_stats = [&]() -> int {
+        double* p = part.as<double>();
+        DPR_TRY(launch_col_sum_minmax(raw.as<double>(), n, d, p, p + (size_t)B * d, p + (size_t)2 * B * d, ctx().stream));
+        DPR_CUDA(cudaMemcpyAsync(hp.data(), p, sizeof(double) * 3 * B * d, cudaMemcpyDeviceToHost, ctx().stream));
+        DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+        for (int j = 0; j < d; ++j) {
+            double s = 0, lo = INFINITY, hi = -INFINITY;
+            for (int q = 0; q < B; ++q) {
+                s += hp[(size_t)j * B + q];
+                lo = std::min(lo, hp[(size_t)B * d + (size_t)j * B + q]);
+                hi = std::max(hi, hp[(size_t)2 * B * d + (size_t)j * B + q]);
+            }
+            colsum[j] = s;
+            colmin[j] = lo;
+            colmax[j] = hi;
+        }
+        return DPR_OK;
+    };
+    auto moments = [&](const std::vector<double>& shift, double* s2, double* s4) -> int {
+        double* p = part.as<double>();
+        DPR_CUDA(cudaMemcpyAsync(dvec.p, shift.data(), sizeof(double) * d, cudaMemcpyHostToDevice, ctx().stream));
+        DPR_TRY(launch_col_moments(raw.as<double>(), n, d, dvec.as<double>(), p, p + (size_t)B * d, ctx().stream));
+        DPR_CUDA(cudaMemcpyAsync(hp.data(), p, sizeof(double) * 2 * B * d, cudaMemcpyDeviceToHost, ctx().stream));
+        DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+        double a = 0, b4 = 0;
+        for (size_t e = 0; e < (size_t)B * d; ++e) {
+            a += hp[e];
+            b4 += hp[(size_t)B * d + e];
+        }
+        *s2 = a;
+        *s4 = b4;
+        return DPR_OK;
+    };
+    DPR_TRY(col_stats());
+    // 1. log2 when the pooled kurtosis exceeds 100 (:11-45)
+    int log2_applied = 0;
+    if (!log2_off) {
+        double tot = 0;
+        for (int j = 0; j < d; ++j) tot += colsum[j];
+        const double mean = tot / (double)total;
+        double s2, s4;
+        DPR_TRY(moments(std::vector<double>(d, mean), &s2, &s4));
+        const double kurt = (double)total * s4 / (s2 * s2);
+        if (kurt > 100) {
+            double gmin = INFINITY;
+            for (int j = 0; j < d; ++j) gmin = std::min(gmin, colmin[j]);
+            DPR_CUDA(cudaMemcpyAsync(dvec.p, colmin.data(), sizeof(double) * d, cudaMemcpyHostToDevice, ctx().stream));
+            DPR_TRY(launch_log2(raw.as<double>(), n, d, dvec.as<double>(), gmin >= 0 ? 0 : 1, ctx().stream));
+            log2_applied = 1;
+            DPR_TRY(col_stats());
+        }
+    }
+    // 2. centres (:49-98)
+    std::vector<double> centre(d, 0.0);
+    if (center_mode == 1) {   // peak of hist(x, breaks = n / 50 | 10)   (dScaleCoFunction.R:74-88)
+        const int n_breaks = n < 500 ? 10 : (int)((double)n / 50.0);
+        DevBuf fb, counts, amax;
+        size_t cap = 0;
+        DPR_TRY(amax.alloc(sizeof(int)));
+        for (int j = 0; j < d; ++j) {
+            std::vector<double> br = r_pretty_breaks(colmin[j], colmax[j], n_breaks);
+            const int nb = (int)br.size() - 1;
+            if (nb < 1) return fail(DPR_ERR_INVALID, "create_scaled: degenerate histogram");
+            std::vector<double> diffs(nb);
+            for (int i = 0; i < nb; ++i) diffs[i] = br[i + 1] - br[i];
+            const double range = colmax[j] - colmin[j];
+            const double diddle = 1e-7 * (nb + 1 > 5 ? median_of(diffs) : (nb + 1 <= 3 ? range : std::max(range, median_of(diffs))));
+            std::vector<double> fz(br);
+            fz[0] -= diddle;
+            for (int i = 1; i <= nb; ++i) fz[i] += diddle;
+            if ((size_t)nb + 1 > cap) {
+                cap = (size_t)nb + 1;
+                if (fb.p) { cudaFree(fb.p); fb.p = nullptr; }
+                if (counts.p) { cudaFree(counts.p); counts.p = nullptr; }
+                DPR_TRY(fb.alloc(sizeof(double) * cap));
+                DPR_TRY(counts.alloc(sizeof(unsigned int) * cap));
+            }
+            DPR_CUDA(cudaMemcpyAsync(fb.p, fz.data(), sizeof(double) * (nb + 1), cudaMemcpyHostToDevice, ctx().stream));
+            DPR_TRY(launch_hist(raw.as<double>() + (int64_t)j * n, n, fb.as<double>(), nb, br[0], 1.0 / diffs[nb / 2], counts.as<unsigned int>(),
+                                amax.as<int>(), ctx().stream));
+            int best = 0;
+            DPR_CUDA(cudaMemcpyAsync(&best, amax.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+            DPR_CUDA(cudaStreamSynchronize(ctx().stream));   // also keeps `fz` alive until the copy is done
+            centre[j] = 0.5 * (br[best] + br[best + 1]);
+        }
+    } else if (center_mode == 2) {
+        for (int j = 0; j < d; ++j) centre[j] = colsum[j] / (double)n;
+    } else if (center_mode == 3) {
+        for (int j = 0; j < d; ++j) centre[j] = centers_inout[j];
+    }
+    // 3. one sd over all centred values (:102-106)
+    double sd = 1.0;
+    if (scale_mode == 1) {
+        double tot = 0;
+        for (int j = 0; j < d; ++j) tot += colsum[j] - (double)n * centre[j];
+        const double vmean = tot / (double)total;
+        std::vector<double> shift(d);
+        for (int j = 0; j < d; ++j) shift[j] = centre[j] + vmean;
+        double s2, s4;
+        DPR_TRY(moments(shift, &s2, &s4));
+        sd = std::sqrt(s2 / (double)(total - 1));
+    } else if (scale_mode == 2) {
+        sd = *scale_inout;
+    }
+    if (!(sd > 0) || !std::isfinite(sd)) return fail(DPR_ERR_INVALID, "create_scaled: the standard deviation is not positive and finite");
+    DPR_CUDA(cudaMemcpyAsync(dvec.p, centre.data(), sizeof(double) * d, cudaMemcpyHostToDevice, ctx().stream));
+    DPR_TRY(launch_scale_to_tiles(raw.as<double>(), n, d, dvec.as<double>(), sd, ds->x, ctx().stream));
+    DPR_TRY(dataset_finish(ds));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (centers_inout && center_mode != 0)
+        for (int j = 0; j < d; ++j) centers_inout[j] = centre[j];
+    if (scale_inout) *scale_inout = sd;
+    if (log2_applied_out) *log2_applied_out = log2_applied;
+    *out = guard.release();
+    return DPR_OK;
+}
+
 int dpr_dataset_destroy(dpr_dataset_t ds) {
     if (!ds) return DPR_OK;
     bench_session_forget(ds);

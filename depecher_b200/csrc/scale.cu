@@ -1,0 +1,178 @@
+// scale.cu — depecheLogCenterSd on the device: the one other O(N*D) step of depeche().
+//
+// Restates /root/reference/R/depecheLogCenterSd.R:6-115 and the "peak" centre of R/dScaleCoFunction.R:74-88:
+//   1. kurtosis of all values (moments::kurtosis = n*sum((x-m)^4)/sum((x-m)^2)^2) > 100 and !log2Off -> log2 transform
+//      (log2(x+1) when min >= 0, else log2(x - colmin + 1));
+//   2. per-column centre: mid of the fullest bin of hist(x, breaks = n/50 (10 below 500 rows)) | column mean | given | none;
+//   3. division by ONE standard deviation taken over all centred values (sd(as.matrix(.)), n-1 denominator);
+// and writes the result as the resident fp32 tile-major dataset.  All statistics are fp64 with fixed-order reductions;
+// (x - c)/sd is evaluated in fp64 and rounded to fp32 once, exactly like R's doubles handed to the fp32 upload.
+// The histogram breakpoints come from the host (R's pretty(), api side) and are searched with the fuzz R applies
+// (hist.default: breaks + 1e-7 * median(diff(breaks)), right-closed bins, lowest value included).
+#include "scale.cuh"
+
+namespace dpr {
+
+constexpr int kStatBlocks = 256;   // partial results per column
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += red[q];
+    __syncthreads();
+    return t;   // valid in thread 0
+}
+
+// per column: sum, min, max (NaN ignored by min/max like R's range() would fail on; depeche's input has no NaN)
+__global__ void col_sum_minmax_kernel(const double* __restrict__ raw, int64_t n, double* psum, double* pmin, double* pmax) {
+    __shared__ double red[32];
+    const int j = blockIdx.y;
+    const double* col = raw + (int64_t)j * n;
+    double s = 0.0, lo = INFINITY, hi = -INFINITY;
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x, i0 = blockIdx.x * per, i1 = min(n, i0 + per);
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const double v = col[i];
+        s += v;
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    __shared__ double rlo[32], rhi[32];
+    if ((threadIdx.x & 31) == 0) {
+        rlo[threadIdx.x >> 5] = lo;
+        rhi[threadIdx.x >> 5] = hi;
+    }
+    const double t = block_sum(s, red);
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) {
+            lo = fmin(lo, rlo[q]);
+            hi = fmax(hi, rhi[q]);
+        }
+        psum[j * gridDim.x + blockIdx.x] = t;
+        pmin[j * gridDim.x + blockIdx.x] = lo;
+        pmax[j * gridDim.x + blockIdx.x] = hi;
+    }
+}
+
+// per column: sum (x - shift_j)^2 and sum (x - shift_j)^4
+__global__ void col_moments_kernel(const double* __restrict__ raw, int64_t n, const double* __restrict__ shift, double* p2, double* p4) {
+    __shared__ double red[32];
+    const int j = blockIdx.y;
+    const double* col = raw + (int64_t)j * n;
+    const double m = shift[j];
+    double s2 = 0.0, s4 = 0.0;
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x, i0 = blockIdx.x * per, i1 = min(n, i0 + per);
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const double v = col[i] - m, q = v * v;
+        s2 += q;
+        s4 += q * q;
+    }
+    const double t2 = block_sum(s2, red);
+    const double t4 = block_sum(s4, red);
+    if (threadIdx.x == 0) {
+        p2[j * gridDim.x + blockIdx.x] = t2;
+        p4[j * gridDim.x + blockIdx.x] = t4;
+    }
+}
+
+// R/depecheLogCenterSd.R:21-41
+__global__ void log2_kernel(double* raw, int64_t n, int d, const double* __restrict__ colmin, int per_column) {
+    const int64_t total = n * d;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t / n);
+        double v = per_column ? log2(raw[t] - colmin[j] + 1.0) : log2(raw[t] + 1.0);
+        if (v != v) v = 0.0;
+        raw[t] = v;
+    }
+}
+
+// hist.default + C_BinCount for one column: fb = fuzzy breaks (nb+1 values), counts[nb]
+__global__ void hist_kernel(const double* __restrict__ col, int64_t n, const double* __restrict__ fb, int nb, double lo, double inv_by,
+                            unsigned int* counts) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = col[i];
+        if (!(fb[0] <= x && x <= fb[nb])) continue;        // outside the (fuzzy) range: not counted, like BinCount
+        int b = (int)((x - lo) * inv_by);
+        b = b < 0 ? 0 : (b > nb - 1 ? nb - 1 : b);
+        while (b < nb - 1 && x > fb[b + 1]) ++b;            // right-closed bins: fb[b] < x <= fb[b+1]
+        while (b > 0 && !(x > fb[b])) --b;
+        atomicAdd(&counts[b], 1u);                          // integer counts: order-independent
+    }
+}
+__global__ void argmax_first_kernel(const unsigned int* __restrict__ counts, int nb, int* out) {
+    __shared__ unsigned int sv[256];
+    __shared__ int si[256];
+    unsigned int bv = 0;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x)
+        if (counts[i] > bv || (counts[i] == bv && i < bi)) {
+            bv = counts[i];
+            bi = i;
+        }
+    sv[threadIdx.x] = bv;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 1; t < (int)blockDim.x; ++t)
+            if (sv[t] > bv || (sv[t] == bv && si[t] < bi)) {
+                bv = sv[t];
+                bi = si[t];
+            }
+        *out = bi;   // match(max(counts), counts): first maximum
+    }
+}
+
+// (x - c_j) / sd in fp64 -> fp32, into the tile-major resident layout
+__global__ void scale_to_tiles_kernel(const double* __restrict__ raw, int64_t n, int d, const double* __restrict__ centre, double sd,
+                                      float* __restrict__ out) {
+    const int64_t total = n * d;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = t / n, i = t - j * n;
+        out[x_index(i, (int)j, d)] = (float)((raw[t] - centre[j]) / sd);
+    }
+}
+
+static inline int grid_for(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(148 * 8, (n + 255) / 256)); }
+
+int launch_col_sum_minmax(const double* raw, int64_t n, int d, double* psum, double* pmin, double* pmax, cudaStream_t st) {
+    col_sum_minmax_kernel<<<dim3(kStatBlocks, d), 256, 0, st>>>(raw, n, psum, pmin, pmax);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_col_moments(const double* raw, int64_t n, int d, const double* shift, double* p2, double* p4, cudaStream_t st) {
+    col_moments_kernel<<<dim3(kStatBlocks, d), 256, 0, st>>>(raw, n, shift, p2, p4);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_log2(double* raw, int64_t n, int d, const double* colmin, int per_column, cudaStream_t st) {
+    log2_kernel<<<grid_for(n * d), 256, 0, st>>>(raw, n, d, colmin, per_column);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_hist(const double* col, int64_t n, const double* fb, int nb, double lo, double inv_by, unsigned int* counts, int* argmax_out,
+                cudaStream_t st) {
+    DPR_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned int) * nb, st));
+    hist_kernel<<<grid_for(n), 256, 0, st>>>(col, n, fb, nb, lo, inv_by, counts);
+    argmax_first_kernel<<<1, 256, 0, st>>>(counts, nb, argmax_out);
+    count_launch(2);
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_scale_to_tiles(const double* raw, int64_t n, int d, const double* centre, double sd, float* out, cudaStream_t st) {
+    scale_to_tiles_kernel<<<grid_for(n * d), 256, 0, st>>>(raw, n, d, centre, sd, out);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int stat_blocks() { return kStatBlocks; }
+
+}  // namespace dpr

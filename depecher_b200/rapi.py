@@ -63,7 +63,8 @@ def generateSparseData(modeN=5, dataCols=100, observations=10000, rng=None):
 # pre-scaling: R/depecheLogCenterSd.R, R/dScaleCoFunction.R:74-99
 # --------------------------------------------------------------------------------------------------------
 def _r_pretty(lo: float, hi: float, n: int, min_n: int = 1):
-    """R's pretty.default(c(lo, hi), n, min.n): 'nice' breakpoints (1, 2, 5 x 10^k) covering [lo, hi]."""
+    """R's pretty.default(c(lo, hi), n, min.n) as hist.default calls it: R_pretty (src/appl/pretty.c) for the 'nice' unit
+    (1, 2, 5 x 10^k) and bounds, then seq.int(l, u, length.out = k + 1) for the breakpoints."""
     h, h5, eps = 1.5, 0.5 + 1.5 * 1.5, 1e-10
     dx = hi - lo
     if dx == 0 and hi == 0:
@@ -76,7 +77,7 @@ def _r_pretty(lo: float, hi: float, n: int, min_n: int = 1):
     if i_small:
         if cell > 10:
             cell = 9 + cell / 10
-        cell *= 1e-7 * 3     # shrink_sml default
+        cell *= 0.75          # shrink.sml
         if min_n > 1:
             cell /= min_n
     else:
@@ -92,7 +93,7 @@ def _r_pretty(lo: float, hi: float, n: int, min_n: int = 1):
             unit = 5 * base
             if 10 * base - cell < h * (cell - unit):
                 unit = 10 * base
-    ns, nu = math.floor(lo / unit + 1e-7), math.ceil(hi / unit - 1e-7)
+    ns, nu = math.floor(lo / unit + eps), math.ceil(hi / unit - eps)
     while ns * unit > lo + eps * unit:
         ns -= 1
     while nu * unit < hi - eps * unit:
@@ -106,17 +107,29 @@ def _r_pretty(lo: float, hi: float, n: int, min_n: int = 1):
         else:
             ns -= k // 2
             nu += k // 2 + k % 2
-    return np.arange(ns, nu + 1) * unit
+        k = min_n
+    l, u = ns * unit, nu * unit
+    by = (u - l) / k if k else 0.0
+    b = l + np.arange(k + 1) * by
+    b[0], b[-1] = l, u
+    b[np.abs(b) < 1e-14 * by] = 0.0
+    return b
 
 
 def _peak_center(x: np.ndarray) -> float:
-    """dScaleCoFunction.R:74-88: mid of the fullest bin of hist(x, breaks = n/50 (10 below 500 rows))."""
-    n_breaks = 10 if len(x) < 500 else len(x) / 50
-    br = _r_pretty(float(x.min()), float(x.max()), int(n_breaks), 1)
-    # hist.default: right-closed bins, lowest value included in the first
-    idx = np.searchsorted(br, x, side="left") - 1
-    idx[idx < 0] = 0
-    counts = np.bincount(idx, minlength=len(br) - 1)[:len(br) - 1]
+    """dScaleCoFunction.R:74-88: mid of the fullest bin of hist(x, breaks = n/50 (10 below 500 rows)); hist.default's
+    right-closed bins with its 1e-7 * median(diff(breaks)) fuzz, lowest value included."""
+    n_breaks = 10 if len(x) < 500 else int(len(x) / 50)
+    br = _r_pretty(float(x.min()), float(x.max()), n_breaks, 1)
+    h = np.diff(br)
+    nB = len(br)
+    diddle = 1e-7 * (np.median(h) if nB > 5 else (np.ptp(x) if nB <= 3 else max(np.ptp(x), np.median(h))))
+    fz = br + diddle
+    fz[0] = br[0] - diddle
+    idx = np.searchsorted(fz, x, side="left") - 1        # fz[b] < x <= fz[b+1]
+    idx[(x >= fz[0]) & (idx < 0)] = 0                     # include.lowest
+    ok = (idx >= 0) & (idx < nB - 1)
+    counts = np.bincount(idx[ok], minlength=nB - 1)
     b = int(np.argmax(counts))          # match(max(counts), counts): first maximum
     return float((br[b] + br[b + 1]) / 2)
 
@@ -372,36 +385,48 @@ def depeche(inDataFrame, samplingSubset=None, penalties=None, sampleSize="defaul
     X = np.asarray(inDataFrame, float)
     if penalties is None:
         penalties = 2.0 ** np.arange(0, 5.5, 0.5)                                              # :128
-    Xs, logCenterSd = depecheLogCenterSd(X, log2Off, center, scale)                             # :141
+    device_scaled = hasattr(eng, "dataset_scaled") and samplingSubset is None
+    if device_scaled:   # the whole pre-scaling on the device; the scaled matrix never exists on the host (SURVEY f-3)
+        ds_scaled, logCenterSd = eng.dataset_scaled(X, log2Off, center, scale)                  # :141
+        Xs = None
+        n_rows = X.shape[0]
+    else:
+        Xs, logCenterSd = depecheLogCenterSd(X, log2Off, center, scale)                         # :141
+        n_rows = len(Xs)
     if samplingSubset is None:
-        samplingSubset = np.arange(len(Xs))
+        samplingSubset = np.arange(n_rows)
     if len(samplingSubset) > 1e6:                                                               # :150-156
         warnings.warn("This dataset is very large; the reference recommends fitting on a sampling subset and allocating the rest with dAllocate")
-    used = Xs[samplingSubset]
+    used = None if device_scaled else Xs[samplingSubset]
+    n_used = n_rows if device_scaled else len(used)
     if sampleSize == "default":
-        sampleSize = len(used) if len(used) <= 10000 else 10000                                 # :161-167
+        sampleSize = n_used if n_used <= 10000 else 10000                                       # :161-167
     if nCores == "default":
         nCores = default_ncores()                                                               # :169-174
     use_ds = hasattr(eng, "dataset")
-    ds_used = eng.dataset(used) if use_ds else used                                             # resident for the whole search (SURVEY f-2)
+    ds_used = ds_scaled if device_scaled else (eng.dataset(used) if use_ds else used)           # resident for the whole search (SURVEY f-2)
     try:
         opt = depechePenaltyOpt(ds_used, k=k, maxIter=maxIter, sampleSize=sampleSize, penalties=penalties, createOutput=createOutput,
                                 minARIImprovement=minARIImprovement, optimARI=optimARI, nCores=nCores, plotDir=plotDir, engine=eng,
                                 seed=seed, verbose=verbose)                                    # :176-184
         if selectionSampleSize == "default":
             selectionSampleSize = sampleSize
-        if len(used) < 10000:                                                                   # :207-215
+        if n_used < 10000:                                                                      # :207-215
             r = depecheAllData(ds_used, penalty=opt["bestPenalty"], k=k, nCores=nCores, engine=eng, seed=seed + 104729)
             clusterVector, reduced, cols = r["clusterVector"], r["clusterCenters"], r["cols"]
         else:
-            if len(used) <= selectionSampleSize:                                                # :191-199
-                sel = used
+            if n_used <= selectionSampleSize:                                                   # :191-199
+                sel = ds_used if device_scaled else used
+            elif device_scaled:
+                sel = eng.gather(ds_used, rng.integers(0, n_used, selectionSampleSize))
             else:
-                sel = used[rng.integers(0, len(used), selectionSampleSize)]
+                sel = used[rng.integers(0, n_used, selectionSampleSize)]
             r = depecheClusterCenterSelection(opt["bestClusterCenters"], sel, k, nCores, engine=eng)   # :222-225
             reduced, cols = r["clusterCenters"], r["cols"]
-            ds_all = ds_used if (use_ds and len(samplingSubset) == len(Xs)) else (eng.dataset(Xs[:, cols]) if use_ds else Xs[:, cols])
-            full_cc = np.zeros((reduced.shape[0], Xs.shape[1]))
+            if device_scaled and sel is not ds_used:
+                sel.close()
+            ds_all = ds_used if (use_ds and len(samplingSubset) == n_rows) else (eng.dataset(Xs[:, cols]) if use_ds else Xs[:, cols])
+            full_cc = np.zeros((reduced.shape[0], X.shape[1]))
             full_cc[:, cols] = reduced
             model_cc = full_cc if ds_all is ds_used else reduced
             clusterVector = dAllocate(ds_all, {"clusterCenters": model_cc, "logCenterSd": False}, engine=eng)   # :228-232

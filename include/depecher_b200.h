@@ -96,6 +96,14 @@ int dpr_dataset_create_f32(const float* X, int64_t n, int32_t d, dpr_dataset_t* 
  * divisor actually used is returned in *scale_out (nullable). */
 int dpr_dataset_create_synthetic(int64_t n, int32_t d, int32_t groups, double amplitude, uint64_t seed,
                                  int64_t row0, double scale, double* scale_out, dpr_dataset_t* out);
+/* depecheLogCenterSd on the device (R/depecheLogCenterSd.R:6-115; "peak" centre: R/dScaleCoFunction.R:74-88): optional log2
+ * transform when the pooled kurtosis exceeds 100, per-column centring, division by one global standard deviation, then the
+ * resident dataset of the scaled cells.  center_mode: 0 none, 1 histogram peak, 2 mean, 3 given in centers_inout.
+ * scale_mode: 0 none, 1 sd of all centred values, 2 given in *scale_inout.  On return centers_inout[d] (nullable for mode 0),
+ * *scale_inout and *log2_applied_out hold what was applied — the logCenterSd record dAllocate needs (R/dAllocate.R:81-90). */
+int dpr_dataset_create_scaled(const double* X, int64_t n, int32_t d, int32_t log2_off, int32_t center_mode,
+                              double* centers_inout, int32_t scale_mode, double* scale_inout, int32_t* log2_applied_out,
+                              dpr_dataset_t* out);
 int dpr_dataset_destroy(dpr_dataset_t ds);
 int dpr_dataset_shape(dpr_dataset_t ds, int64_t* n, int32_t* d);
 /* copy rows [row0, row0+rows) back as column-major doubles (tests / CPU baseline sample) */

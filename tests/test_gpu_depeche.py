@@ -73,3 +73,32 @@ def test_testdata_against_stored_depeche_result(engine, testdata):
     assert np.all(np.diff(sizes) <= 0)                                              # clusters numbered by size (R/depeche.R:236-249)
     stored = np.bincount(testdata["stored_clusterVector"])[1:]
     assert np.all(np.abs(sizes - stored) < 0.05 * 20000)
+
+
+def test_device_prescaling_matches_host(engine, testdata):
+    """depecheLogCenterSd on the device (dpr_dataset_create_scaled) against the numpy restatement: same peak centres,
+    same sd, scaled cells equal up to the last fp32 bit; also the mean / given-centre / log2 paths."""
+    X = testdata["X"]
+    want, winfo = rapi.depecheLogCenterSd(X)
+    ds, info = engine.dataset_scaled(X)
+    got = engine.read(ds, 0, len(X))
+    ds.close()
+    assert info[0] is False and np.allclose(info[1], winfo[1], rtol=0, atol=1e-12)
+    assert abs(info[2] - winfo[2]) <= 1e-12 * winfo[2]
+    w32 = want.astype(np.float32).astype(np.float64)
+    assert np.max(np.abs(got - w32)) <= 2.5e-7 * np.max(np.abs(w32))
+    assert (got == w32).mean() > 0.999
+    for center in ("mean", False, list(np.arange(14.0))):
+        want, winfo = rapi.depecheLogCenterSd(X, True, center, True)
+        ds, info = engine.dataset_scaled(X, True, center, True)
+        got = engine.read(ds, 0, 2000)
+        ds.close()
+        assert abs(info[2] - winfo[2]) <= 1e-12 * winfo[2]
+        assert np.allclose(got, want[:2000], rtol=3e-7, atol=1e-7)
+    heavy = np.abs(np.random.default_rng(0).standard_cauchy(size=(5000, 6))) ** 2      # kurtosis >> 100 -> log2(x + 1)
+    want, winfo = rapi.depecheLogCenterSd(heavy)
+    ds, info = engine.dataset_scaled(heavy)
+    got = engine.read(ds, 0, 5000)
+    ds.close()
+    assert winfo[0] is True and info[0] is True
+    assert np.allclose(info[1], winfo[1], atol=1e-9) and np.allclose(got, want, rtol=3e-6, atol=1e-6)

@@ -196,6 +196,41 @@ __global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_s
     if (threadIdx.x == 0 && n_active_out && !(iter + 1 >= max_iter)) atomicAdd(n_active_out, 1);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// re-partition: contiguous tile ranges per CTA holding equal numbers of tiles of problems that are still running
+// (converged fits keep their place in the tile order but weigh nothing), so late Lloyd iterations of a batch stay balanced.
+// One CTA.  Boundaries only move; the tile numbering, and with it every warp's accumulation order inside a range, is fixed
+// by (range, problem), so results stay reproducible for a given sequence of convergences.
+// ---------------------------------------------------------------------------------------------------
+__global__ void partition_kernel(const Problem* problems, int n_problems, int grid_ctas, int total_tiles, int32_t* cta_tile_start) {
+    extern __shared__ long long s_pref[];   // [n_problems + 1] running count of live tiles
+    if (threadIdx.x == 0) {
+        long long acc = 0;
+        for (int p = 0; p < n_problems; ++p) {
+            s_pref[p] = acc;
+            acc += problems[p].done ? 0 : problems[p].n_tiles;
+        }
+        s_pref[n_problems] = acc;
+    }
+    __syncthreads();
+    const long long live = s_pref[n_problems];
+    for (int c = threadIdx.x; c <= grid_ctas; c += blockDim.x) {
+        int start = total_tiles;
+        if (live > 0 && c < grid_ctas) {
+            const long long target = live * c / grid_ctas;   // first live tile of CTA c
+            int lo = 0, hi = n_problems - 1;                 // last problem whose prefix <= target and that is live
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_pref[mid] <= target) lo = mid; else hi = mid - 1;
+            }
+            while (lo < n_problems - 1 && s_pref[lo + 1] == s_pref[lo]) ++lo;   // skip converged problems
+            start = problems[lo].first_tile + (int)(target - s_pref[lo]);
+        }
+        if (c == 0) start = 0;
+        cta_tile_start[c] = start;
+    }
+}
+
 // one update from given sums/counts (reevaluate_centers for explicit labels): mu only
 __global__ void soft_threshold_kernel(const double* sums, const long long* counts, int k, int d, double reg, double* mu) {
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < k * d; e += gridDim.x * blockDim.x) {
@@ -225,6 +260,13 @@ int launch_reduce_partials(const Problem* d_problems, int n_problems, const int3
 int launch_finalize(Problem* d_problems, int n_problems, const double* seg_in, int n_seg, int k_max, int iter, int max_iter,
                     int table_cap, int allow_delta, int32_t* n_active_out, cudaStream_t st) {
     finalize_kernel<<<n_problems, 256, 0, st>>>(d_problems, seg_in, n_seg, k_max, iter, max_iter, table_cap, allow_delta, n_active_out);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+
+int launch_partition(const Problem* d_problems, int n_problems, int grid_ctas, int total_tiles, int32_t* cta_tile_start, cudaStream_t st) {
+    partition_kernel<<<1, 256, sizeof(long long) * (n_problems + 1), st>>>(d_problems, n_problems, grid_ctas, total_tiles, cta_tile_start);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;

@@ -8,5 +8,6 @@ int launch_reduce_partials(const Problem* d_problems, int n_problems, const int3
                            const double* cta_tables, double* seg_out, int n_seg, cudaStream_t st);
 int launch_finalize(Problem* d_problems, int n_problems, const double* seg_in, int n_seg, int k_max, int iter, int max_iter,
                     int table_cap, int allow_delta, int32_t* n_active_out, cudaStream_t st);
+int launch_partition(const Problem* d_problems, int n_problems, int grid_ctas, int total_tiles, int32_t* cta_tile_start, cudaStream_t st);
 int launch_soft_threshold(const double* sums, const long long* counts, int k, int d, double reg, double* mu, cudaStream_t st);
 }  // namespace dpr

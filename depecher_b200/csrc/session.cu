@@ -151,6 +151,7 @@ int Session::zero_labels() {
 int Session::lloyd(int max_iter) {
     // The convergence rule needs i > 20 (Clusterer.cpp:247): iterations 0..20 run back to back without
     // touching the host; after that the host looks at the active-problem counter once per iteration.
+    int last_active = n_problems();
     for (int i = 0; i < max_iter; ++i) {
         DPR_TRY(pass(kPassLloyd, true));
         DPR_TRY(reduce_and_finalize(i, max_iter));
@@ -158,6 +159,11 @@ int Session::lloyd(int max_iter) {
             DPR_CUDA(cudaMemcpyAsync(h_n_active_, d_n_active_, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx().stream));
             DPR_CUDA(cudaStreamSynchronize(ctx().stream));
             if (*h_n_active_ == 0) break;
+            // some fits of the batch have converged: give their CTAs' time to the ones still running
+            if (n_problems() > 1 && *h_n_active_ < last_active) {
+                DPR_TRY(launch_partition(d_problems, n_problems(), grid, total_tiles_, d_cta_start_, ctx().stream));
+                last_active = *h_n_active_;
+            }
         }
     }
     return DPR_OK;

@@ -15,6 +15,11 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # a fresh checkout has no binaries (they are git-ignored): build the library and the checkers once (nvcc cross-compiles)
+    lib = os.path.join(ROOT, "depecher_b200", "lib", "libdepecher_b200.so")
+    if not os.path.exists(lib) or not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+        import subprocess
+        subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.build()"], cwd=ROOT, check=True)
 
 
 def _has_gpu() -> bool:

@@ -79,6 +79,10 @@ int dpr_comm_init(int32_t rank, int32_t world, const void* id128, const char* nc
     }
     if (!id128) return fail(DPR_ERR_INVALID, "null unique id");
     DPR_TRY(load(nccl_path));
+    if (ctx().nccl_comm) {   // re-initialisation: drop the previous communicator first
+        api.CommDestroy(ctx().nccl_comm);
+        ctx().nccl_comm = nullptr;
+    }
     NcclUniqueId id;
     memcpy(&id, id128, sizeof(id));
     NcclComm comm = nullptr;

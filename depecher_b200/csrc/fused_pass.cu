@@ -260,6 +260,7 @@ __device__ __forceinline__ void slot_contributions(const float* __restrict__ slo
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -328,8 +329,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
         const float cc2 = 2.0f * hdr->cc_max;
         const int chunk0_kc = hdr->chunk_kc[0], chunk0_off = hdr->chunk_off[0];
         const uint32_t slot_bytes_tx = (uint32_t)d * (kSlotCells * 4);
-        const bool delta = P.mode == kPassLloyd && pr.delta;
-        const bool need_old = (P.compare_old || P.mode == kPassSums || delta) && pr.labels;
+        const bool delta = MODE == kPassLloyd && pr.delta;
+        const bool need_old = (P.compare_old || MODE == kPassSums || delta) && pr.labels;
         long long changed = 0;
 
         const int first = tile + warp;
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
             phase ^= (1u << s);
 
             int lab[2] = {0, 0};
-            if (P.mode == kPassSums) {
+            if (MODE == kPassSums) {
                 lab[0] = oldl.x;
                 lab[1] = oldl.y;
             } else if (!trivial) {
@@ -403,11 +404,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
             if (mycell + 1 >= pr.n) lab[1] = -1;
             const bool ch0 = lab[0] >= 0 && lab[0] != oldl.x, ch1 = lab[1] >= 0 && lab[1] != oldl.y;
             if (P.compare_old) changed += (int)ch0 + (int)ch1;
-            if (pr.labels && P.mode != kPassSums) {
+            if (pr.labels && MODE != kPassSums) {
                 if (full2) *reinterpret_cast<int2*>(pr.labels + mycell) = make_int2(lab[0], lab[1]);
                 else if (lab[0] >= 0) pr.labels[mycell] = lab[0];
             }
-            if (P.mode != kPassAssign) {
+            if (MODE != kPassAssign) {
                 int key[4], cell[4];
                 cell[0] = cell[2] = 2 * lane;
                 cell[1] = cell[3] = 2 * lane + 1;
@@ -564,7 +565,9 @@ int launch_fused_pass(const PassPlan& plan, PassParams P, int grid, cudaStream_t
     P.off_slots = plan.off_slots;
     static bool configured = false;
     if (!configured) {
-        DPR_CUDA(cudaFuncSetAttribute(fused_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        DPR_CUDA(cudaFuncSetAttribute(fused_pass_kernel<kPassAssign>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        DPR_CUDA(cudaFuncSetAttribute(fused_pass_kernel<kPassLloyd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        DPR_CUDA(cudaFuncSetAttribute(fused_pass_kernel<kPassSums>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
         configured = true;
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -573,7 +576,10 @@ int launch_fused_pass(const PassPlan& plan, PassParams P, int grid, cudaStream_t
         DPR_CUDA(cudaEventCreate(&e1));
         DPR_CUDA(cudaEventRecord(e0, stream));
     }
-    fused_pass_kernel<<<grid, plan.warps * 32, plan.smem_bytes, stream>>>(P);
+    // one instance per mode: the assignment-only pass carries no sums code (fewer registers spilled, smaller I-cache footprint)
+    if (P.mode == kPassAssign) fused_pass_kernel<kPassAssign><<<grid, plan.warps * 32, plan.smem_bytes, stream>>>(P);
+    else if (P.mode == kPassLloyd) fused_pass_kernel<kPassLloyd><<<grid, plan.warps * 32, plan.smem_bytes, stream>>>(P);
+    else fused_pass_kernel<kPassSums><<<grid, plan.warps * 32, plan.smem_bytes, stream>>>(P);
     count_launch();
     if (e0) {
         DPR_CUDA(cudaEventRecord(e1, stream));

@@ -249,3 +249,32 @@ def test_unsupported_shapes_and_bad_arguments_fail_loudly(engine):
     same = np.ones((100, 3))
     mu, rows = engine.initialize_mu(same, 4, seed=1)
     assert np.array_equal(mu, np.ones((4, 3))) and (rows[1:] == 0).all()
+
+
+def test_random_shapes_fuzz(engine, oracle):
+    """60 random problems: sizes, scales, zero rows, duplicated centres, cells sitting on centres — labels bit-exact, and for a
+    subset the whole Lloyd trajectory (iteration count, labels, zero pattern) equal to the oracle's."""
+    rng = np.random.default_rng(20261020)
+    for trial in range(60):
+        n, d, k = int(rng.integers(1, 3000)), int(rng.integers(1, 70)), int(rng.integers(2, 70))
+        scale = float(10.0 ** rng.uniform(-3, 3))
+        g = int(rng.integers(1, 8))
+        X = (blobs(rng, n, d, g) * scale).astype(np.float32).astype(np.float64)
+        mu = (blobs(rng, k, d, g) * scale).astype(np.float32).astype(np.float64)
+        if k > 3:
+            mu[rng.integers(0, k, 2)] = 0.0
+            mu[int(rng.integers(0, k))] = mu[int(rng.integers(0, k))]
+        if n > 10:
+            X[rng.integers(0, n, 3)] = mu[rng.integers(0, k, 3)]
+        nz = bool(rng.integers(0, 2))
+        got = engine.allocate_points(X, mu, nz)["i"]
+        want = oracle.allocate_points(X, mu, nz)
+        assert np.array_equal(got, want), f"trial {trial}: n={n} d={d} k={k} no_zero={nz}: {(got != want).sum()} labels differ"
+        if trial % 6 == 0 and n >= 2 * k:
+            Xu = X / scale
+            reg = float(rng.choice([0.0, 2.0, 16.0])) * n * np.sqrt(d) / 1450.0
+            mu0 = Xu[rng.choice(n, k, replace=False)]
+            a = engine.find_centers_from(Xu, mu0, reg, True)
+            b = oracle.find_centers_from(Xu, mu0, reg, True)
+            assert a["n_iter"] == b["n_iter"] and np.array_equal(a["i"], b["i"]), f"trial {trial}: trajectories differ"
+            centres_close(a["c"], b["c"])

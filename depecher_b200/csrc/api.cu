@@ -44,8 +44,24 @@ int ensure_ready() {
     c.sms = prop.multiProcessorCount;
     DPR_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
     if (!c.stream) c.stream = c.own_stream;
+    {   // keep freed device memory in the stream-ordered pool: a penalty sweep allocates and frees multi-GB label and
+        // partial-sum buffers per call, and going back to the driver for them costs more than the kernels
+        cudaMemPool_t pool;
+        DPR_CUDA(cudaDeviceGetDefaultMemPool(&pool, c.device));
+        unsigned long long keep = ~0ULL;
+        DPR_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     c.ready = true;
     return DPR_OK;
+}
+
+// stream-ordered device memory (see ensure_ready): allocation and release are ordered on the library's stream
+int dev_alloc(void** p, size_t bytes) {
+    DPR_CUDA(cudaMallocAsync(p, bytes ? bytes : 1, ctx().stream));
+    return DPR_OK;
+}
+void dev_free(void* p) {
+    if (p) cudaFreeAsync(p, ctx().stream);
 }
 
 void bench_session_forget(dpr_dataset* ds);
@@ -53,9 +69,9 @@ void bench_session_forget(dpr_dataset* ds);
 // ---- small RAII helpers for temporaries ----------------------------------------------------------
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { dev_free(p); }
     int alloc(size_t bytes, bool zero = false) {
-        DPR_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+        DPR_TRY(dev_alloc(&p, bytes));
         if (zero) DPR_CUDA(cudaMemsetAsync(p, 0, bytes ? bytes : 1, ctx().stream));
         return DPR_OK;
     }
@@ -80,9 +96,9 @@ static int dataset_alloc(int64_t n, int32_t d, dpr_dataset** out) {
     ds->d = d;
     ds->n_pad = (n + kSlotCells - 1) / kSlotCells * kSlotCells;
     const size_t bytes = sizeof(float) * (size_t)ds->n_pad * d;
-    DPR_CUDA(cudaMalloc(&ds->x, bytes));
+    DPR_TRY(dev_alloc((void**)&ds->x, bytes));
     DPR_CUDA(cudaMemsetAsync(ds->x, 0, bytes, ctx().stream));
-    DPR_CUDA(cudaMalloc(&ds->tile_xx, sizeof(float) * (size_t)(ds->n_pad / kSlotCells)));
+    DPR_TRY(dev_alloc((void**)&ds->tile_xx, sizeof(float) * (size_t)(ds->n_pad / kSlotCells)));
     *out = ds.release();
     return DPR_OK;
 }
@@ -91,7 +107,7 @@ static int dataset_finish(dpr_dataset* ds) {
     return launch_tile_norms(ds->x, ds->n_pad / kSlotCells, ds->d, ds->tile_xx, ctx().stream);
 }
 static int dataset_labels(dpr_dataset* ds) {
-    if (!ds->labels) DPR_CUDA(cudaMalloc(&ds->labels, sizeof(int32_t) * (size_t)ds->n_pad));
+    if (!ds->labels) DPR_TRY(dev_alloc((void**)&ds->labels, sizeof(int32_t) * (size_t)ds->n_pad));
     return DPR_OK;
 }
 
@@ -321,6 +337,7 @@ int dpr_set_device(int32_t ordinal) {
 }
 int dpr_set_stream(void* s) {
     DPR_TRY(ensure_ready());
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));   // device memory is released in stream order: finish the old stream first
     ctx().stream = s ? (cudaStream_t)s : ctx().own_stream;
     return DPR_OK;
 }
@@ -581,8 +598,8 @@ int dpr_dataset_create_scaled(const double* X, int64_t n, int32_t d, int32_t log
             for (int i = 1; i <= nb; ++i) fz[i] += diddle;
             if ((size_t)nb + 1 > cap) {
                 cap = (size_t)nb + 1;
-                if (fb.p) { cudaFree(fb.p); fb.p = nullptr; }
-                if (counts.p) { cudaFree(counts.p); counts.p = nullptr; }
+                if (fb.p) { dev_free(fb.p); fb.p = nullptr; }
+                if (counts.p) { dev_free(counts.p); counts.p = nullptr; }
                 DPR_TRY(fb.alloc(sizeof(double) * cap));
                 DPR_TRY(counts.alloc(sizeof(unsigned int) * cap));
             }
@@ -629,9 +646,9 @@ int dpr_dataset_create_scaled(const double* X, int64_t n, int32_t d, int32_t log
 int dpr_dataset_destroy(dpr_dataset_t ds) {
     if (!ds) return DPR_OK;
     bench_session_forget(ds);
-    if (ds->x) cudaFree(ds->x);
-    if (ds->tile_xx) cudaFree(ds->tile_xx);
-    if (ds->labels) cudaFree(ds->labels);
+    dev_free(ds->x);
+    dev_free(ds->tile_xx);
+    dev_free(ds->labels);
     delete ds;
     return DPR_OK;
 }

@@ -45,15 +45,18 @@ __global__ void tile_norms_kernel(const float* __restrict__ x, int64_t n_tiles, 
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t t = warp; t < n_tiles; t += nwarps) {
-        const float2* row = reinterpret_cast<const float2*>(x + t * (int64_t)d * kSlotCells);
-        float a = 0.f, b = 0.f;
+        const float4* row = reinterpret_cast<const float4*>(x + t * (int64_t)d * kSlotCells);
+        float a = 0.f, b = 0.f, c = 0.f, e = 0.f;
         for (int j = 0; j < d; ++j) {
-            const float2 v = row[j * (kSlotCells / 2) + lane];   // any permutation inside a row is fine for a maximum over the tile
+            const float4 v = row[j * (kSlotCells / 4) + lane];   // any permutation inside a row is fine for a maximum over the tile
             a = fmaf(v.x, v.x, a);
             b = fmaf(v.y, v.y, b);
+            c = fmaf(v.z, v.z, c);
+            e = fmaf(v.w, v.w, e);
         }
-        float m = a > b ? a : b;
-        if (a != a || b != b) m = INFINITY;                      // a NaN cell: every cell of the tile is decided exactly
+        const bool bad = (a != a) || (b != b) || (c != c) || (e != e);
+        float m = fmaxf(fmaxf(a, b), fmaxf(c, e));
+        if (bad) m = INFINITY;                                   // a NaN cell: every cell of the tile is decided exactly
         for (int o = 16; o > 0; o >>= 1) {
             const float w = __shfl_xor_sync(0xffffffffu, m, o);
             m = w > m ? w : m;

@@ -27,24 +27,23 @@ int fail(int code, const std::string& msg);
     } while (0)
 
 // ---- geometry of the fused pass --------------------------------------------------------------
-constexpr int kSlotCells = 64;    // cells per warp slot (32 lanes x 2 cells, one LDS.64 per marker)
-constexpr int kRowStride = 64;    // floats per marker row of a slot: rows are dense, cells are XOR-swizzled inside a row
-constexpr int kMaxKC = 32;        // centres per register-tile chunk (2 cells x 32 centres = 64 accumulators)
-constexpr int kWarpsPerCta = 16;
+constexpr int kSlotCells = 128;   // cells per warp slot (32 lanes x 4 cells, one LDS.128 per marker)
+constexpr int kRowStride = 128;   // floats per marker row of a slot: rows are dense, 4-cell groups are XOR-swizzled inside a row
+constexpr int kMaxKC = 32;        // centres per register-tile chunk (4 cells x 32 centres = 128 accumulators)
+constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kMaxChunks = 8;     // => fast path handles up to 256 active centres
 constexpr int kSmemBudget = 227 * 1024;
 
-// Resident layout of a cell matrix ("tile-major"): cells are grouped in tiles of kSlotCells = 64 consecutive
-// cells; a tile holds its d marker rows back to back (d * 64 floats, contiguous in HBM, so one bulk-async
-// copy moves a whole slot), and inside marker row j the cell c sits at c ^ (2 * ((j >> 2) & 15)).  The XOR keeps
-// the (2c, 2c+1) pair of a lane adjacent (one LDS.64 per marker in the distance loop, conflict-free), changes only
-// every 4th marker (so the unrolled distance loop pays for it once per 4 markers: measured +6 % over a per-marker
-// XOR, profiles/microbench/r01_chunk_bench_b200.log) and still spreads the marker rows of one cell over 8 bank
-// pairs for the transposed reads of the sum phase.
-__host__ __device__ __forceinline__ int x_swizzle(int j) { return ((j >> 2) & 15) << 1; }
+// Resident layout of a cell matrix ("tile-major"): cells are grouped in tiles of kSlotCells = 128 consecutive
+// cells; a tile holds its d marker rows back to back (d * 128 floats, contiguous in HBM, so one bulk-async
+// copy moves a whole slot), and inside marker row j the 4-cell group g = c / 4 sits at group g ^ ((j >> 2) & 31).
+// The XOR keeps a lane's four cells adjacent (one LDS.128 per marker in the distance loop, conflict-free), changes
+// only every 4th marker (the unrolled distance loop pays for it once per 4 markers) and spreads the marker rows of
+// one cell over 8 bank groups for the transposed reads of the sum phase.
+__host__ __device__ __forceinline__ int x_swizzle(int j) { return ((j >> 2) & 31) << 2; }
 __host__ __device__ __forceinline__ size_t x_index(int64_t cell, int j, int d) {
-    return (size_t)(cell >> 6) * (size_t)(d * kSlotCells) + (size_t)j * kSlotCells + (size_t)((cell & 63) ^ x_swizzle(j));
+    return (size_t)(cell >> 7) * (size_t)(d * kSlotCells) + (size_t)j * kSlotCells + (size_t)((cell & 127) ^ x_swizzle(j));
 }
 __host__ __device__ __forceinline__ int x_slot_index(int cell_in_slot, int j) {
     return j * kSlotCells + (cell_in_slot ^ x_swizzle(j));
@@ -102,6 +101,7 @@ struct Context {
     cudaStream_t own_stream = nullptr;
     int ari_mode = DPR_ARI_EXACT;
     int64_t launches = 0;
+    int32_t* pinned_word = nullptr;      // pinned host word the Lloyd loop polls the active-problem count through
     // optional per-launch timing of the fused pass (dpr_pass_timing)
     bool time_passes = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pass_events;
@@ -110,7 +110,9 @@ struct Context {
     int rank = 0, world = 1;
 };
 Context& ctx();
-int ensure_ready();   // picks the device, checks sm_100, creates the stream
+int ensure_ready();
+int dev_alloc(void** p, size_t bytes);   // stream-ordered, pooled (api.cu)
+void dev_free(void* p);   // picks the device, checks sm_100, creates the stream
 
 inline void count_launch(int n = 1) { ctx().launches += n; }
 

@@ -75,33 +75,33 @@ __device__ __forceinline__ float pack_idx(float s, int idx) {
 
 template <int KC>
 __device__ __forceinline__ void dist_chunk(const float* __restrict__ slot, const float* __restrict__ tab, int d, int lane,
-                                           float (&best)[2], float (&second)[2]) {
+                                           float (&best)[4], float (&second)[4]) {
     constexpr int NP = KC / 2;
     constexpr int KCP = (KC + 3) & ~3;
-    float2 acc[2][NP];
+    float2 acc[4][NP];
     {
         const float2* cc = reinterpret_cast<const float2*>(tab);
 #pragma unroll
         for (int t = 0; t < NP; ++t) {
             const float2 c = cc[t];
-            acc[0][t] = c;
-            acc[1][t] = c;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r][t] = c;
         }
     }
-    const float2* xs = reinterpret_cast<const float2*>(slot);
+    const float4* xs = reinterpret_cast<const float4*>(slot);
     const float4* cw = reinterpret_cast<const float4*>(tab + KCP);
 #pragma unroll 2
     for (int j = 0; j < d; ++j) {
-        const float2 xv = xs[j * (kRowStride / 2) + (lane ^ ((j >> 2) & 15))];   // cells (2*lane, 2*lane+1) of marker j, swizzled
-        const float2 x0 = make_float2(xv.x, xv.x), x1 = make_float2(xv.y, xv.y);
+        const float4 xv = xs[j * (kRowStride / 4) + (lane ^ ((j >> 2) & 31))];   // cells 4*lane .. 4*lane+3 of marker j, swizzled
+        const float x[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
         for (int q = 0; q < KCP / 4; ++q) {
             const float4 c = cw[j * (KCP / 4) + q];
-            acc[0][2 * q] = __ffma2_rn(x0, make_float2(c.x, c.y), acc[0][2 * q]);
-            acc[1][2 * q] = __ffma2_rn(x1, make_float2(c.x, c.y), acc[1][2 * q]);
-            if (2 * q + 1 < NP) {
-                acc[0][2 * q + 1] = __ffma2_rn(x0, make_float2(c.z, c.w), acc[0][2 * q + 1]);
-                acc[1][2 * q + 1] = __ffma2_rn(x1, make_float2(c.z, c.w), acc[1][2 * q + 1]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float2 xr = make_float2(x[r], x[r]);
+                acc[r][2 * q] = __ffma2_rn(xr, make_float2(c.x, c.y), acc[r][2 * q]);
+                if (2 * q + 1 < NP) acc[r][2 * q + 1] = __ffma2_rn(xr, make_float2(c.z, c.w), acc[r][2 * q + 1]);
             }
         }
     }
@@ -109,7 +109,7 @@ __device__ __forceinline__ void dist_chunk(const float* __restrict__ slot, const
 #pragma unroll
     for (int t = 0; t < NP; ++t) {
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < 4; ++r) {
             const float a = pack_idx(acc[r][t].x, 2 * t);
             const float b = pack_idx(acc[r][t].y, 2 * t + 1);
             const float lo = fminf(a, b), hi = fmaxf(a, b);
@@ -119,8 +119,8 @@ __device__ __forceinline__ void dist_chunk(const float* __restrict__ slot, const
     }
 }
 
-__device__ __forceinline__ void dist_chunk_dispatch(int kc, const float* slot, const float* tab, int d, int lane, float (&best)[2],
-                                                    float (&second)[2]) {
+__device__ __forceinline__ void dist_chunk_dispatch(int kc, const float* slot, const float* tab, int d, int lane, float (&best)[4],
+                                                    float (&second)[4]) {
     switch (kc) {
 #define DPR_CASE(KC)                                                \
     case KC:                                                        \
@@ -175,23 +175,28 @@ __device__ __noinline__ int exact_label_warp(const float* __restrict__ slot, int
     return n_slots > 0 ? orig[bi] : 0;
 }
 
+__device__ __forceinline__ void red_add(double* p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void red_add(long long* p, long long v) { atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+
 // ---------------------------------------------------------------------------------------------------
 // Lloyd mode: signed contributions of one slot into the warp's private table.
-// Each lane brings up to 4 entries: (cell, label, sign); key = 2*label + (sign < 0).  off[0..2k] ints and
-// perm[0..127] bytes are the warp's scratch.  No atomics: one leader per key per instruction.
+// Each lane brings up to 8 entries: (cell, label, sign); key = 2*label + (sign < 0).  off[0..2k] ints and
+// perm[0..255] bytes are the warp's scratch.  No atomics: one leader per key per instruction.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void slot_contributions(const float* __restrict__ slot, const int (&key)[4], const int (&cell)[4], int d,
+__device__ __forceinline__ void slot_contributions(const float* __restrict__ slot, const int (&key)[8], const int (&cell)[8], int d,
                                                    int k, int lane, int* off, unsigned char* perm, double* __restrict__ sums,
                                                    long long* __restrict__ counts) {
     const unsigned full = 0xffffffffu;
     const int nk = 2 * k;
-    const bool any = (key[0] >= 0) | (key[1] >= 0) | (key[2] >= 0) | (key[3] >= 0);
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) any |= key[r] >= 0;
     if (!__any_sync(full, any)) return;
     for (int i = lane; i <= nk; i += 32) off[i] = 0;
     __syncwarp();
-    int pos[4];
+    int pos[8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 8; ++r) {
         const int L = key[r];
         const unsigned m = __match_any_sync(full, L);
         const int leader = __ffs(m) - 1;
@@ -219,12 +224,12 @@ __device__ __forceinline__ void slot_contributions(const float* __restrict__ slo
     }
     __syncwarp();
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 8; ++r)
         if (key[r] >= 0) perm[off[key[r]] + pos[r]] = (unsigned char)cell[r];
     __syncwarp();
     for (int L = lane; L < k; L += 32) {
         const int c = (off[2 * L + 1] - off[2 * L]) - (off[2 * L + 2] - off[2 * L + 1]);
-        if (c) __stcg(&counts[L], __ldcg(&counts[L]) + c);
+        if (c) red_add(&counts[L], (long long)c);
     }
     for (int jb = 0; jb < d; jb += 32) {
         const int j = jb + lane;
@@ -240,7 +245,6 @@ __device__ __forceinline__ void slot_contributions(const float* __restrict__ slo
                 pm &= pm - 1;
                 const int s = off[2 * L], mid = off[2 * L + 1], e = off[2 * L + 2];
                 double* tcell = sums + (size_t)L * d + j;
-                const double old = on ? __ldcg(tcell) : 0.0;
                 double a0 = 0.0, a1 = 0.0;
                 int p = s;
                 for (; p + 1 < mid; p += 2) {
@@ -250,11 +254,30 @@ __device__ __forceinline__ void slot_contributions(const float* __restrict__ slo
                 if (p < mid) a0 += (double)row[perm[p] ^ xo];
                 double m0 = 0.0;
                 for (p = mid; p < e; ++p) m0 += (double)row[perm[p] ^ xo];
-                if (on) __stcg(tcell, old + ((a0 + a1) - m0));
+                if (on) red_add(tcell, (a0 + a1) - m0);
             }
         }
     }
     __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Lloyd delta mode, few moved cells: cell c leaves label oldL for newL.  Lane j owns markers j, j+32, ...
+// The additions are reductions without return value (RED.ADD.F64): nothing waits on the L2 round trip.  They stay
+// deterministic because a table belongs to one warp and a given address is only ever touched by one lane of it —
+// operations of one thread on one address take effect in program order — so every table entry sees a fixed
+// sequence of fp64 additions.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void move_one(const float* __restrict__ slot, int d, int lane, double* __restrict__ sums,
+                                         long long* __restrict__ counts, int c, int newL, int oldL) {
+    double* ta = sums + (size_t)newL * d;
+    double* tb = sums + (size_t)oldL * d;
+    for (int j = lane; j < d; j += 32) {
+        const double v = (double)slot[x_slot_index(c, j)];
+        red_add(ta + j, v);
+        red_add(tb + j, -v);
+    }
+    if (lane < 2) red_add(&counts[lane ? oldL : newL], lane ? -1LL : 1LL);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -357,37 +380,48 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
         int64_t cell0 = (int64_t)(first - pr.first_tile) * kSlotCells;
         const float* xx_ptr = pr.tile_xx + (first - pr.first_tile);
         for (int i = 0; i < count; ++i, cell0 += (int64_t)W * kSlotCells, xx_ptr += W) {
-            const int64_t mycell = cell0 + 2 * lane;
+            const int64_t mycell = cell0 + 4 * lane;
             const float* slot = slots + (size_t)s * P.slot_floats;
             // previous labels (the reference compares against the previous assignment, Clusterer.cpp:247)
-            int2 oldl = make_int2(0, 0);
-            const bool full2 = mycell + 1 < pr.n;
+            int oldl[4] = {0, 0, 0, 0};
+            const bool full4 = mycell + 3 < pr.n;
             if (need_old) {
-                if (full2) oldl = *reinterpret_cast<const int2*>(pr.labels + mycell);
-                else if (mycell < pr.n) oldl.x = pr.labels[mycell];
+                if (full4) {
+                    const int4 o = *reinterpret_cast<const int4*>(pr.labels + mycell);
+                    oldl[0] = o.x; oldl[1] = o.y; oldl[2] = o.z; oldl[3] = o.w;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (mycell + r < pr.n) oldl[r] = pr.labels[mycell + r];
+                }
             }
             const float xx_tile = *xx_ptr;   // bound of ||x||^2 over this slot's cells
             mbar_wait(&bars[warp * S + s], (phase >> s) & 1u);
             phase ^= (1u << s);
 
-            int lab[2] = {0, 0};
+            int lab[4] = {0, 0, 0, 0};
             if (MODE == kPassSums) {
-                lab[0] = oldl.x;
-                lab[1] = oldl.y;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) lab[r] = oldl[r];
             } else if (!trivial) {
-                float best[2] = {3.3e38f, 3.3e38f}, second[2] = {3.3e38f, 3.3e38f};
-                int bchunk[2] = {0, 0};
+                float best[4], second[4];
+                int bchunk[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int r = 0; r < 4; ++r) best[r] = second[r] = 3.3e38f;
                 dist_chunk_dispatch(chunk0_kc, slot, table + chunk0_off, d, lane, best, second);
                 for (int q = 1; q < n_chunks; ++q) {
-                    const float prev0 = best[0], prev1 = best[1];
-                    dist_chunk_dispatch(hdr->chunk_kc[q], slot, table + hdr->chunk_off[q], d, lane, best, second);
-                    if (best[0] < prev0) bchunk[0] = q;
-                    if (best[1] < prev1) bchunk[1] = q;
-                }
+                    float prev[4];
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
+                    for (int r = 0; r < 4; ++r) prev[r] = best[r];
+                    dist_chunk_dispatch(hdr->chunk_kc[q], slot, table + hdr->chunk_off[q], d, lane, best, second);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (best[r] < prev[r]) bchunk[r] = q;
+                }
+                const float tau = tau_c * (xx_tile + cc2);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
                     const int a = hdr->chunk_base[bchunk[r]] + (int)(__float_as_uint(best[r]) & 31u);
-                    const float tau = tau_c * (xx_tile + cc2);
                     const bool sure = (second[r] - best[r] > tau) && !force_exact;
                     lab[r] = orig[a < n_slots ? a : 0];
                     unsigned redo = __ballot_sync(0xffffffffu, !sure && (mycell + r < pr.n));
@@ -395,70 +429,62 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
                     while (redo) {   // the whole warp re-decides each doubtful cell in fp64
                         const int src = __ffs(redo) - 1;
                         redo &= redo - 1;
-                        const int v = exact_label_warp(slot, 2 * src + r, d, pr.mu, orig, n_slots, lane);
+                        const int v = exact_label_warp(slot, 4 * src + r, d, pr.mu, orig, n_slots, lane);
                         if (lane == src) lab[r] = v;
                     }
                 }
             }
-            if (mycell >= pr.n) lab[0] = -1;
-            if (mycell + 1 >= pr.n) lab[1] = -1;
-            const bool ch0 = lab[0] >= 0 && lab[0] != oldl.x, ch1 = lab[1] >= 0 && lab[1] != oldl.y;
-            if (P.compare_old) changed += (int)ch0 + (int)ch1;
+            bool ch[4];
+            int nch = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (mycell + r >= pr.n) lab[r] = -1;
+                ch[r] = lab[r] >= 0 && lab[r] != oldl[r];
+                nch += (int)ch[r];
+            }
+            if (P.compare_old) changed += nch;
             if (pr.labels && MODE != kPassSums) {
-                if (full2) *reinterpret_cast<int2*>(pr.labels + mycell) = make_int2(lab[0], lab[1]);
-                else if (lab[0] >= 0) pr.labels[mycell] = lab[0];
+                if (full4) *reinterpret_cast<int4*>(pr.labels + mycell) = make_int4(lab[0], lab[1], lab[2], lab[3]);
+                else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (lab[r] >= 0) pr.labels[mycell + r] = lab[r];
+                }
             }
             if (MODE != kPassAssign) {
-                int key[4], cell[4];
-                cell[0] = cell[2] = 2 * lane;
-                cell[1] = cell[3] = 2 * lane + 1;
-                if (delta) {
-                    key[0] = ch0 ? 2 * lab[0] : -1;
-                    key[1] = ch1 ? 2 * lab[1] : -1;
-                    key[2] = ch0 ? 2 * oldl.x + 1 : -1;
-                    key[3] = ch1 ? 2 * oldl.y + 1 : -1;
-                } else {
-                    key[0] = lab[0] >= 0 ? 2 * lab[0] : -1;
-                    key[1] = lab[1] >= 0 ? 2 * lab[1] : -1;
-                    key[2] = key[3] = -1;
+                unsigned mch[4];
+                int moved = 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    mch[r] = __ballot_sync(0xffffffffu, ch[r]);
+                    moved += __popc(mch[r]);
                 }
-                const unsigned m0 = __ballot_sync(0xffffffffu, ch0), m1 = __ballot_sync(0xffffffffu, ch1);
-                if (delta && __popc(m0) + __popc(m1) <= 16) {
+                if (delta && moved <= 24) {
                     // few cells moved: no sort, each moved cell adds its row to the new label's sums and takes it off the old one's
 #pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        unsigned m = r ? m1 : m0;
+                    for (int r = 0; r < 4; ++r) {
+                        unsigned m = mch[r];
                         while (m) {
                             const int src = __ffs(m) - 1;
                             m &= m - 1;
                             const int newL = __shfl_sync(0xffffffffu, lab[r], src);
-                            const int oldL = __shfl_sync(0xffffffffu, r ? oldl.y : oldl.x, src);
-                            const int c = 2 * src + r;
-                            double* ta = my_sums + (size_t)newL * d;
-                            double* tb = my_sums + (size_t)oldL * d;
-                            for (int jb = 0; jb < d; jb += 64) {   // two markers per lane: four table loads in flight at once
-                                const int j0 = jb + lane, j1 = jb + 32 + lane;
-                                const bool on0 = j0 < d, on1 = j1 < d;
-                                const double v0 = on0 ? (double)slot[x_slot_index(c, j0)] : 0.0;
-                                const double v1 = on1 ? (double)slot[x_slot_index(c, j1)] : 0.0;
-                                const double a0 = on0 ? __ldcg(ta + j0) : 0.0, b0 = on0 ? __ldcg(tb + j0) : 0.0;
-                                const double a1 = on1 ? __ldcg(ta + j1) : 0.0, b1 = on1 ? __ldcg(tb + j1) : 0.0;
-                                if (on0) {
-                                    __stcg(ta + j0, a0 + v0);
-                                    __stcg(tb + j0, b0 - v0);
-                                }
-                                if (on1) {
-                                    __stcg(ta + j1, a1 + v1);
-                                    __stcg(tb + j1, b1 - v1);
-                                }
-                            }
-                            if (lane == 0) {
-                                __stcg(&my_counts[newL], __ldcg(&my_counts[newL]) + 1);
-                                __stcg(&my_counts[oldL], __ldcg(&my_counts[oldL]) - 1);
-                            }
+                            const int oldL = __shfl_sync(0xffffffffu, oldl[r], src);
+                            move_one(slot, d, lane, my_sums, my_counts, 4 * src + r, newL, oldL);
                         }
                     }
                 } else {
+                    int key[8], cell[8];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        cell[r] = cell[r + 4] = 4 * lane + r;
+                        if (delta) {
+                            key[r] = ch[r] ? 2 * lab[r] : -1;
+                            key[r + 4] = ch[r] ? 2 * oldl[r] + 1 : -1;
+                        } else {
+                            key[r] = lab[r] >= 0 ? 2 * lab[r] : -1;
+                            key[r + 4] = -1;
+                        }
+                    }
                     slot_contributions(slot, key, cell, d, pr.k, lane, wscr, perm, my_sums, my_counts);
                 }
             }

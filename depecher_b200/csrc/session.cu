@@ -9,15 +9,14 @@
 namespace dpr {
 
 Session::~Session() {
-    for (void* p : owned_) cudaFree(p);
-    if (h_n_active_) cudaFreeHost(h_n_active_);
+    for (void* p : owned_) dev_free(p);
 }
 
 template <typename T>
 int Session::alloc(T** p, size_t count, bool zero) {
     void* q = nullptr;
     const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-    DPR_CUDA(cudaMalloc(&q, bytes));
+    DPR_TRY(dev_alloc(&q, bytes));
     owned_.push_back(q);
     if (zero) DPR_CUDA(cudaMemsetAsync(q, 0, bytes, ctx().stream));
     *p = reinterpret_cast<T*>(q);
@@ -94,7 +93,8 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
         DPR_TRY(alloc(&cta_tables_, (size_t)(grid + P) * seg_entries, true));
         DPR_TRY(alloc(&seg, (size_t)P * n_seg * seg_entries, true));
         DPR_TRY(alloc(&d_n_active_, (size_t)1, true));
-        DPR_CUDA(cudaMallocHost(&h_n_active_, sizeof(int32_t)));
+        if (!ctx().pinned_word) DPR_CUDA(cudaMallocHost(&ctx().pinned_word, sizeof(int32_t)));   // kept for the life of the process
+        h_n_active_ = ctx().pinned_word;
     }
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));  // `start`/h_problems are stack/heap temporaries of this call
     return DPR_OK;

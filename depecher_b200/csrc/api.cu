@@ -95,7 +95,7 @@ static int dataset_alloc(int64_t n, int32_t d, dpr_dataset** out) {
     ds->n = n;
     ds->d = d;
     ds->n_pad = (n + kSlotCells - 1) / kSlotCells * kSlotCells;
-    const size_t bytes = sizeof(float) * (size_t)ds->n_pad * d;
+    const size_t bytes = sizeof(float) * (size_t)(ds->n_pad / kSlotCells) * tile_floats(d);
     DPR_TRY(dev_alloc((void**)&ds->x, bytes));
     DPR_CUDA(cudaMemsetAsync(ds->x, 0, bytes, ctx().stream));
     DPR_TRY(dev_alloc((void**)&ds->tile_xx, sizeof(float) * (size_t)(ds->n_pad / kSlotCells)));
@@ -856,11 +856,12 @@ static int grid_search_impl(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
     const int64_t ldb = ((int64_t)boot_n + kSlotCells - 1) / kSlotCells * kSlotCells;
     // 1. bootstrap samples (bootstrap_data, :354-355): fit f = 2 * problem + which
     DevBuf xb, lab_b;
-    DPR_TRY(xb.alloc(sizeof(float) * (size_t)F * ldb * d, true));
-    DPR_TRY(lab_b.alloc(sizeof(int32_t) * (size_t)F * ldb, true));
-    DPR_TRY(launch_gather(ds->x, ds->n, d, nullptr, seed, 0, boot_n, xb.as<float>(), F, ldb * d, ctx().stream));
-    DevBuf xb_xx;   // the F bootstrap matrices are back to back and each is a whole number of tiles
     const int64_t tiles_b = ldb / kSlotCells;
+    const int64_t fit_floats = tiles_b * (int64_t)tile_floats(d);   // floats of one bootstrap matrix
+    DPR_TRY(xb.alloc(sizeof(float) * (size_t)F * fit_floats, true));
+    DPR_TRY(lab_b.alloc(sizeof(int32_t) * (size_t)F * ldb, true));
+    DPR_TRY(launch_gather(ds->x, ds->n, d, nullptr, seed, 0, boot_n, xb.as<float>(), F, fit_floats, ctx().stream));
+    DevBuf xb_xx;   // the F bootstrap matrices are back to back and each is a whole number of tiles
     DPR_TRY(xb_xx.alloc(sizeof(float) * (size_t)F * tiles_b));
     DPR_TRY(launch_tile_norms(xb.as<float>(), (int64_t)F * tiles_b, d, xb_xx.as<float>(), ctx().stream));
     // 2. the fits (find_centers with zero-centre removal, :361-362)
@@ -874,7 +875,7 @@ static int grid_search_impl(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
     for (int f = 0; f < F; ++f) {
         int it, j, l;
         cell_of(f, it, j, l);
-        specs[f] = ProblemSpec{xb.as<float>() + (size_t)f * ldb * d, xb_xx.as<float>() + (size_t)f * tiles_b, (int64_t)boot_n, k[j], reg[l], 1,
+        specs[f] = ProblemSpec{xb.as<float>() + (size_t)f * fit_floats, xb_xx.as<float>() + (size_t)f * tiles_b, (int64_t)boot_n, k[j], reg[l], 1,
                                lab_b.as<int32_t>() + (size_t)f * ldb};
     }
     Session fits;

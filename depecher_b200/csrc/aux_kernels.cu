@@ -38,21 +38,23 @@ __global__ void cols_to_f64_kernel(const float* __restrict__ x, int64_t row0, in
 
 // ---------------------------------------------------------------------------------------------------
 // per-tile upper bound of ||x||^2 (one warp per tile).  The fused pass needs ||x||^2 only inside the proven error
-// bound that decides which cells are re-examined in fp64; a bound shared by the 64 cells of a tile is as safe and
+// bound that decides which cells are re-examined in fp64; a bound shared by the 128 cells of a tile is as safe and
 // saves two FMAs per marker and lane in the hot loop.
 // ---------------------------------------------------------------------------------------------------
 __global__ void tile_norms_kernel(const float* __restrict__ x, int64_t n_tiles, int d, float* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int groups = tile_groups(d);
     for (int64_t t = warp; t < n_tiles; t += nwarps) {
-        const float4* row = reinterpret_cast<const float4*>(x + t * (int64_t)d * kSlotCells);
-        float a = 0.f, b = 0.f, c = 0.f, e = 0.f;
-        for (int j = 0; j < d; ++j) {
-            const float4 v = row[j * (kSlotCells / 4) + lane];   // any permutation inside a row is fine for a maximum over the tile
-            a = fmaf(v.x, v.x, a);
-            b = fmaf(v.y, v.y, b);
-            c = fmaf(v.z, v.z, c);
-            e = fmaf(v.w, v.w, e);
+        const float4* tile = reinterpret_cast<const float4*>(x + t * (int64_t)tile_floats(d));
+        float a = 0.f, b = 0.f, c = 0.f, e = 0.f;   // cells lane, lane+32, lane+64, lane+96
+        for (int g = 0; g < groups; ++g) {
+            const float4* grp = tile + g * (kGroupFloats / 4);
+            const float4 v0 = grp[lane], v1 = grp[lane + 32], v2 = grp[lane + 64], v3 = grp[lane + 96];
+            a = fmaf(v0.x, v0.x, fmaf(v0.y, v0.y, fmaf(v0.z, v0.z, fmaf(v0.w, v0.w, a))));
+            b = fmaf(v1.x, v1.x, fmaf(v1.y, v1.y, fmaf(v1.z, v1.z, fmaf(v1.w, v1.w, b))));
+            c = fmaf(v2.x, v2.x, fmaf(v2.y, v2.y, fmaf(v2.z, v2.z, fmaf(v2.w, v2.w, c))));
+            e = fmaf(v3.x, v3.x, fmaf(v3.y, v3.y, fmaf(v3.z, v3.z, fmaf(v3.w, v3.w, e))));
         }
         const bool bad = (a != a) || (b != b) || (c != c) || (e != e);
         float m = fmaxf(fmaxf(a, b), fmaxf(c, e));
@@ -388,7 +390,7 @@ __global__ void synth_kernel(float* x, int64_t n, int d, const float* __restrict
     }
 }
 __global__ void scale_kernel(float* x, int64_t n_pad, int d, float inv_sd) {
-    const int64_t total = n_pad * d;   // padding cells are zero and stay zero
+    const int64_t total = (n_pad / kSlotCells) * (int64_t)tile_floats(d);   // padding cells / markers are zero and stay zero
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) x[t] *= inv_sd;
 }
 
@@ -504,7 +506,7 @@ int launch_synth(float* x, int64_t n, int d, const float* centres, int groups, u
     return DPR_OK;
 }
 int launch_scale(float* x, int64_t n_pad, int d, float inv_sd, cudaStream_t st) {
-    scale_kernel<<<blocks_for(n_pad * d), 256, 0, st>>>(x, n_pad, d, inv_sd);
+    scale_kernel<<<blocks_for((n_pad / kSlotCells) * (int64_t)tile_floats(d)), 256, 0, st>>>(x, n_pad, d, inv_sd);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;

@@ -74,7 +74,7 @@ __device__ void build_centre_table(const Problem& pr, int no_zero, int table_cap
             h->chunk_kc[q] = kc;
             h->chunk_off[q] = off;
             h->chunk_base[q] = base;
-            off += kcp * (d + 1);
+            off += kcp * (4 * tile_groups(d) + 1);   // marker rows padded to whole groups of 4 (zero rows)
             base += kc;
         }
         h->n_slots = base;
@@ -97,9 +97,9 @@ __device__ void build_centre_table(const Problem& pr, int no_zero, int table_cap
             cc[t] = row >= 0 ? (float)s_cc[row] : 3.0e38f;
             if (t < kc) pr.orig[h->chunk_base[q] + t] = row;
         }
-        for (int e = threadIdx.x; e < kcp * d; e += blockDim.x) {
+        for (int e = threadIdx.x; e < kcp * 4 * tile_groups(d); e += blockDim.x) {
             const int j = e / kcp, t = e % kcp;
-            w[e] = t < real ? (float)(-2.0 * pr.mu[(size_t)s_act[real_before + t] * d + j]) : 0.f;
+            w[e] = (t < real && j < d) ? (float)(-2.0 * pr.mu[(size_t)s_act[real_before + t] * d + j]) : 0.f;
         }
         real_before += real;
     }

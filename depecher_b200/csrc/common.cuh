@@ -27,32 +27,32 @@ int fail(int code, const std::string& msg);
     } while (0)
 
 // ---- geometry of the fused pass --------------------------------------------------------------
-constexpr int kSlotCells = 128;   // cells per warp slot (32 lanes x 4 cells, one LDS.128 per marker)
-constexpr int kRowStride = 128;   // floats per marker row of a slot: rows are dense, 4-cell groups are XOR-swizzled inside a row
+constexpr int kSlotCells = 128;   // cells per tile (= one warp slot of the FFMA pass = the M of one tcgen05 product)
+constexpr int kGroupFloats = kSlotCells * 4 + 4;   // one 4-marker group of a tile: 128 cells x 4 markers, + 16 B so that groups shift by 4 banks
 constexpr int kMaxKC = 32;        // centres per register-tile chunk (4 cells x 32 centres = 128 accumulators)
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kMaxChunks = 8;     // => fast path handles up to 256 active centres
 constexpr int kSmemBudget = 227 * 1024;
 
-// Resident layout of a cell matrix ("tile-major"): cells are grouped in tiles of kSlotCells = 128 consecutive
-// cells; a tile holds its d marker rows back to back (d * 128 floats, contiguous in HBM, so one bulk-async
-// copy moves a whole slot), and inside marker row j the 4-cell group g = c / 4 sits at group g ^ ((j >> 2) & 31).
-// The XOR keeps a lane's four cells adjacent (one LDS.128 per marker in the distance loop, conflict-free), changes
-// only every 4th marker (the unrolled distance loop pays for it once per 4 markers) and spreads the marker rows of
-// one cell over 8 bank groups for the transposed reads of the sum phase.
-__host__ __device__ __forceinline__ int x_swizzle(int j) { return ((j >> 2) & 31) << 2; }
+// Resident layout of a cell matrix ("tile-major"): cells are grouped in tiles of 128 consecutive cells, a tile is
+// contiguous in HBM (one bulk-async copy moves it) and holds ceil(d/4) marker groups; inside a group each cell owns
+// 16 consecutive bytes = its 4 markers (markers beyond d are zero).  This is exactly the K-major, no-swizzle
+// canonical operand layout of tcgen05.mma (core matrix = 8 cells x 16 B, 128 B between 8-cell blocks, one group
+// between the two halves of a K=8 step), so the tensor core reads a landed tile as it is; the FFMA pass reads a
+// cell's 4 markers with one LDS.128 (lane l owns cells l, l+32, l+64, l+96: conflict-free), and the transposed
+// reads of the sum phase (lane = marker, fixed cell) hit 32 different banks thanks to the 16 B group padding.
+__host__ __device__ __forceinline__ int tile_groups(int d) { return (d + 3) >> 2; }
+__host__ __device__ __forceinline__ size_t tile_floats(int d) { return (size_t)tile_groups(d) * kGroupFloats; }
+__host__ __device__ __forceinline__ int x_slot_index(int cell_in_slot, int j) { return (j >> 2) * kGroupFloats + cell_in_slot * 4 + (j & 3); }
 __host__ __device__ __forceinline__ size_t x_index(int64_t cell, int j, int d) {
-    return (size_t)(cell >> 7) * (size_t)(d * kSlotCells) + (size_t)j * kSlotCells + (size_t)((cell & 127) ^ x_swizzle(j));
-}
-__host__ __device__ __forceinline__ int x_slot_index(int cell_in_slot, int j) {
-    return j * kSlotCells + (cell_in_slot ^ x_swizzle(j));
+    return (size_t)(cell >> 7) * tile_floats(d) + (size_t)x_slot_index((int)(cell & 127), j);
 }
 
 // Centre table of one problem as the fused pass reads it (global memory, built on device by
 // finalize_kernel / prepare_centres_kernel).  Floats are laid out per chunk:
 //   cc[kcp]            ||c||^2 of each slot (dummy slots: +huge)
-//   w[d][kcp]          -2 * c (marker-major, kcp = kc rounded up to 4)
+//   w[d4][kcp]         -2 * c (marker-major, kcp = kc rounded up to 4, d4 = d rounded up to 4 with zero rows)
 struct CentreHeader {
     int32_t k;            // rows of mu
     int32_t k_act;        // active centres (no_zero: non-zero rows; else all rows, zero rows deduped)
@@ -122,7 +122,7 @@ struct dpr_dataset {
     int64_t n = 0;
     int32_t d = 0;
     int64_t n_pad = 0;         // n rounded up to whole tiles
-    float* x = nullptr;        // device, tile-major (dpr::x_index), n_pad * d floats
+    float* x = nullptr;        // device, tile-major (dpr::x_index), (n_pad / 128) * tile_floats(d) floats
     float* tile_xx = nullptr;  // device, n_pad / 64 floats: max ||x||^2 of each tile (rounded up)
     int32_t* labels = nullptr; // device, n_pad entries (lazily allocated)
 };

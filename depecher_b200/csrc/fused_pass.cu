@@ -74,7 +74,7 @@ __device__ __forceinline__ float pack_idx(float s, int idx) {
 }
 
 template <int KC>
-__device__ __forceinline__ void dist_chunk(const float* __restrict__ slot, const float* __restrict__ tab, int d, int lane,
+__device__ __forceinline__ void dist_chunk(const float* __restrict__ slot, const float* __restrict__ tab, int groups, int lane,
                                            float (&best)[4], float (&second)[4]) {
     constexpr int NP = KC / 2;
     constexpr int KCP = (KC + 3) & ~3;
@@ -88,20 +88,27 @@ __device__ __forceinline__ void dist_chunk(const float* __restrict__ slot, const
             for (int r = 0; r < 4; ++r) acc[r][t] = c;
         }
     }
-    const float4* xs = reinterpret_cast<const float4*>(slot);
+    const float2* xs = reinterpret_cast<const float2*>(slot) + 2 * lane;   // this lane's cells: lane, lane+32, lane+64, lane+96
     const float4* cw = reinterpret_cast<const float4*>(tab + KCP);
-#pragma unroll 2
-    for (int j = 0; j < d; ++j) {
-        const float4 xv = xs[j * (kRowStride / 4) + (lane ^ ((j >> 2) & 31))];   // cells 4*lane .. 4*lane+3 of marker j, swizzled
-        const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+    for (int h = 0; h < 2 * groups; ++h, cw += KCP / 2) {   // half a marker group per step keeps the x registers at 8
+        float x[2][4];   // [marker of the half group][cell]
+        const float2* xg = xs + (h >> 1) * (kGroupFloats / 2) + (h & 1);
 #pragma unroll
-        for (int q = 0; q < KCP / 4; ++q) {
-            const float4 c = cw[j * (KCP / 4) + q];
+        for (int r = 0; r < 4; ++r) {
+            const float2 v = xg[64 * r];
+            x[0][r] = v.x; x[1][r] = v.y;
+        }
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const float2 xr = make_float2(x[r], x[r]);
-                acc[r][2 * q] = __ffma2_rn(xr, make_float2(c.x, c.y), acc[r][2 * q]);
-                if (2 * q + 1 < NP) acc[r][2 * q + 1] = __ffma2_rn(xr, make_float2(c.z, c.w), acc[r][2 * q + 1]);
+        for (int jj = 0; jj < 2; ++jj) {
+#pragma unroll
+            for (int q = 0; q < KCP / 4; ++q) {
+                const float4 c = cw[jj * (KCP / 4) + q];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float2 xr = make_float2(x[jj][r], x[jj][r]);
+                    acc[r][2 * q] = __ffma2_rn(xr, make_float2(c.x, c.y), acc[r][2 * q]);
+                    if (2 * q + 1 < NP) acc[r][2 * q + 1] = __ffma2_rn(xr, make_float2(c.z, c.w), acc[r][2 * q + 1]);
+                }
             }
         }
     }
@@ -119,12 +126,12 @@ __device__ __forceinline__ void dist_chunk(const float* __restrict__ slot, const
     }
 }
 
-__device__ __forceinline__ void dist_chunk_dispatch(int kc, const float* slot, const float* tab, int d, int lane, float (&best)[4],
+__device__ __forceinline__ void dist_chunk_dispatch(int kc, const float* slot, const float* tab, int groups, int lane, float (&best)[4],
                                                     float (&second)[4]) {
     switch (kc) {
 #define DPR_CASE(KC)                                                \
     case KC:                                                        \
-        dist_chunk<KC>(slot, tab, d, lane, best, second);            \
+        dist_chunk<KC>(slot, tab, groups, lane, best, second);       \
         break;
         DPR_CASE(2) DPR_CASE(4) DPR_CASE(6) DPR_CASE(8) DPR_CASE(10) DPR_CASE(12) DPR_CASE(14) DPR_CASE(16)
         DPR_CASE(18) DPR_CASE(20) DPR_CASE(22) DPR_CASE(24) DPR_CASE(26) DPR_CASE(28) DPR_CASE(30) DPR_CASE(32)
@@ -234,8 +241,7 @@ __device__ __forceinline__ void slot_contributions(const float* __restrict__ slo
     for (int jb = 0; jb < d; jb += 32) {
         const int j = jb + lane;
         const bool on = j < d;
-        const float* row = slot + (on ? j : 0) * kRowStride;
-        const int xo = x_swizzle(on ? j : 0);      // swizzle of this lane's marker row
+        const float* row = slot + x_slot_index(0, on ? j : 0);   // this lane's marker: cell c sits 4*c floats further
         for (int Lb = 0; Lb < k; Lb += 32) {
             const int Li = Lb + lane;
             const bool present = (Li < k) && (off[2 * Li + 2] > off[2 * Li]);
@@ -248,12 +254,12 @@ __device__ __forceinline__ void slot_contributions(const float* __restrict__ slo
                 double a0 = 0.0, a1 = 0.0;
                 int p = s;
                 for (; p + 1 < mid; p += 2) {
-                    a0 += (double)row[perm[p] ^ xo];
-                    a1 += (double)row[perm[p + 1] ^ xo];
+                    a0 += (double)row[4 * perm[p]];
+                    a1 += (double)row[4 * perm[p + 1]];
                 }
-                if (p < mid) a0 += (double)row[perm[p] ^ xo];
+                if (p < mid) a0 += (double)row[4 * perm[p]];
                 double m0 = 0.0;
-                for (p = mid; p < e; ++p) m0 += (double)row[perm[p] ^ xo];
+                for (p = mid; p < e; ++p) m0 += (double)row[4 * perm[p]];
                 if (on) red_add(tcell, (a0 + a1) - m0);
             }
         }
@@ -351,7 +357,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
         const float tau_c = (2.5f * (float)(d + 4)) * 5.9604645e-8f + 7.6293945e-6f;  // fp32 dot bound + 5 masked bits (2*2^-18)
         const float cc2 = 2.0f * hdr->cc_max;
         const int chunk0_kc = hdr->chunk_kc[0], chunk0_off = hdr->chunk_off[0];
-        const uint32_t slot_bytes_tx = (uint32_t)d * (kSlotCells * 4);
+        const int groups = tile_groups(d);
+        const uint32_t slot_bytes_tx = (uint32_t)(tile_floats(d) * 4);
         const bool delta = MODE == kPassLloyd && pr.delta;
         const bool need_old = (P.compare_old || MODE == kPassSums || delta) && pr.labels;
         long long changed = 0;
@@ -359,8 +366,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
         const int first = tile + warp;
         const int count = first < p_end ? (p_end - first + W - 1) / W : 0;
         // ONE bulk-async copy per slot: a tile is contiguous (and already swizzled) in HBM.  Tiles of this warp are W apart.
-        const size_t tile_floats = (size_t)d * kSlotCells;
-        const float* next_src = pr.x + (size_t)(first - pr.first_tile) * tile_floats;   // tile the next issue() loads
+        const size_t tile_fl = tile_floats(d);
+        const float* next_src = pr.x + (size_t)(first - pr.first_tile) * tile_fl;   // tile the next issue() loads
         int issued = 0, s_issue = 0;
         auto issue = [&]() {
             if (lane == 0) {
@@ -368,9 +375,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
                 bulk_g2s(smem_u32(slots + (size_t)s_issue * P.slot_floats), next_src, slot_bytes_tx, smem_u32(&bars[warp * S + s_issue]));
                 // the tile this warp will want after that one: pull it into L2 now, so its bulk copy (issued only when the
                 // slot is free again) pays L2 latency instead of HBM latency
-                if (issued + 1 < count) bulk_prefetch_l2(next_src + (size_t)W * tile_floats, slot_bytes_tx);
+                if (issued + 1 < count) bulk_prefetch_l2(next_src + (size_t)W * tile_fl, slot_bytes_tx);
             }
-            next_src += (size_t)W * tile_floats;
+            next_src += (size_t)W * tile_fl;
             ++issued;
             s_issue = (s_issue + 1 == S) ? 0 : s_issue + 1;
         };
@@ -380,20 +387,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
         int64_t cell0 = (int64_t)(first - pr.first_tile) * kSlotCells;
         const float* xx_ptr = pr.tile_xx + (first - pr.first_tile);
         for (int i = 0; i < count; ++i, cell0 += (int64_t)W * kSlotCells, xx_ptr += W) {
-            const int64_t mycell = cell0 + 4 * lane;
+            const int64_t mycell = cell0 + lane;   // this lane's cells: mycell + 32 * r
             const float* slot = slots + (size_t)s * P.slot_floats;
             // previous labels (the reference compares against the previous assignment, Clusterer.cpp:247)
             int oldl[4] = {0, 0, 0, 0};
-            const bool full4 = mycell + 3 < pr.n;
             if (need_old) {
-                if (full4) {
-                    const int4 o = *reinterpret_cast<const int4*>(pr.labels + mycell);
-                    oldl[0] = o.x; oldl[1] = o.y; oldl[2] = o.z; oldl[3] = o.w;
-                } else {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        if (mycell + r < pr.n) oldl[r] = pr.labels[mycell + r];
-                }
+                for (int r = 0; r < 4; ++r)
+                    if (mycell + 32 * r < pr.n) oldl[r] = pr.labels[mycell + 32 * r];
             }
             const float xx_tile = *xx_ptr;   // bound of ||x||^2 over this slot's cells
             mbar_wait(&bars[warp * S + s], (phase >> s) & 1u);
@@ -408,12 +409,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
                 int bchunk[4] = {0, 0, 0, 0};
 #pragma unroll
                 for (int r = 0; r < 4; ++r) best[r] = second[r] = 3.3e38f;
-                dist_chunk_dispatch(chunk0_kc, slot, table + chunk0_off, d, lane, best, second);
+                dist_chunk_dispatch(chunk0_kc, slot, table + chunk0_off, groups, lane, best, second);
                 for (int q = 1; q < n_chunks; ++q) {
                     float prev[4];
 #pragma unroll
                     for (int r = 0; r < 4; ++r) prev[r] = best[r];
-                    dist_chunk_dispatch(hdr->chunk_kc[q], slot, table + hdr->chunk_off[q], d, lane, best, second);
+                    dist_chunk_dispatch(hdr->chunk_kc[q], slot, table + hdr->chunk_off[q], groups, lane, best, second);
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
                         if (best[r] < prev[r]) bchunk[r] = q;
@@ -424,12 +425,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
                     const int a = hdr->chunk_base[bchunk[r]] + (int)(__float_as_uint(best[r]) & 31u);
                     const bool sure = (second[r] - best[r] > tau) && !force_exact;
                     lab[r] = orig[a < n_slots ? a : 0];
-                    unsigned redo = __ballot_sync(0xffffffffu, !sure && (mycell + r < pr.n));
+                    unsigned redo = __ballot_sync(0xffffffffu, !sure && (mycell + 32 * r < pr.n));
                     if (redo && P.recheck_count && lane == 0) atomicAdd(P.recheck_count, (unsigned long long)__popc(redo));
                     while (redo) {   // the whole warp re-decides each doubtful cell in fp64
                         const int src = __ffs(redo) - 1;
                         redo &= redo - 1;
-                        const int v = exact_label_warp(slot, 4 * src + r, d, pr.mu, orig, n_slots, lane);
+                        const int v = exact_label_warp(slot, src + 32 * r, d, pr.mu, orig, n_slots, lane);
                         if (lane == src) lab[r] = v;
                     }
                 }
@@ -438,18 +439,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
             int nch = 0;
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                if (mycell + r >= pr.n) lab[r] = -1;
+                if (mycell + 32 * r >= pr.n) lab[r] = -1;
                 ch[r] = lab[r] >= 0 && lab[r] != oldl[r];
                 nch += (int)ch[r];
             }
             if (P.compare_old) changed += nch;
             if (pr.labels && MODE != kPassSums) {
-                if (full4) *reinterpret_cast<int4*>(pr.labels + mycell) = make_int4(lab[0], lab[1], lab[2], lab[3]);
-                else {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        if (lab[r] >= 0) pr.labels[mycell + r] = lab[r];
-                }
+                for (int r = 0; r < 4; ++r)
+                    if (lab[r] >= 0) pr.labels[mycell + 32 * r] = lab[r];
             }
             if (MODE != kPassAssign) {
                 unsigned mch[4];
@@ -469,14 +467,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
                             m &= m - 1;
                             const int newL = __shfl_sync(0xffffffffu, lab[r], src);
                             const int oldL = __shfl_sync(0xffffffffu, oldl[r], src);
-                            move_one(slot, d, lane, my_sums, my_counts, 4 * src + r, newL, oldL);
+                            move_one(slot, d, lane, my_sums, my_counts, src + 32 * r, newL, oldL);
                         }
                     }
                 } else {
                     int key[8], cell[8];
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        cell[r] = cell[r + 4] = 4 * lane + r;
+                        cell[r] = cell[r + 4] = lane + 32 * r;
                         if (delta) {
                             key[r] = ch[r] ? 2 * lab[r] : -1;
                             key[r + 4] = ch[r] ? 2 * oldl[r] + 1 : -1;
@@ -551,10 +549,10 @@ constexpr size_t kBarBytes = 512;  // kWarpsPerCta * 3 slots * 8 B mbarriers, ro
 
 int plan_pass(int d, int k_max, PassPlan* plan) {
     if (d < 1 || k_max < 1 || k_max > kMaxKC * kMaxChunks - 2 * kMaxChunks) return 0;
-    const int slot_floats = d * kRowStride;
+    const int slot_floats = (int)((tile_floats(d) + 31) & ~(size_t)31);   // slots stay 128 B aligned
     const size_t slot_bytes = (size_t)slot_floats * 4;
     const int n_chunks = (k_max + kMaxKC - 1) / kMaxKC;
-    const size_t table_bytes = ((size_t)(d + 1) * (k_max + 3 * n_chunks) * 4 + 127) & ~(size_t)127;
+    const size_t table_bytes = ((size_t)(4 * tile_groups(d) + 1) * (k_max + 3 * n_chunks) * 4 + 127) & ~(size_t)127;
     const size_t orig_bytes = ((size_t)(k_max + 2 * n_chunks) * 4 + 127) & ~(size_t)127;
     const size_t scratch = (((size_t)(2 * k_max + 2) * 4 + 2 * kSlotCells) + 127) & ~(size_t)127;
     const size_t hdr_bytes = std::max<size_t>((sizeof(CentreHeader) + 127) & ~(size_t)127, 8 * kWarpsPerCta);

@@ -113,6 +113,10 @@ class Engine:
     def synchronize(self) -> None:
         self._chk(self.lib.dpr_synchronize())
 
+    def set_pass_kernel(self, which: int) -> None:
+        """0 = automatic (tensor-core pass when the shape fits), 1 = always the FFMA pass."""
+        self._chk(self.lib.dpr_set_pass_kernel(C.c_int32(which)))
+
     def set_ari_mode(self, mode: int) -> None:
         self._chk(self.lib.dpr_set_ari_mode(C.c_int32(mode)))
 

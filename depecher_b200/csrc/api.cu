@@ -346,6 +346,12 @@ int dpr_synchronize(void) {
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));
     return DPR_OK;
 }
+int dpr_set_pass_kernel(int32_t which) {
+    if (which != DPR_PASS_AUTO && which != DPR_PASS_FFMA) return fail(DPR_ERR_INVALID, "unknown pass kernel");
+    ctx().force_ffma = which == DPR_PASS_FFMA;
+    g_bench_session.reset();   // a cached session keeps the kernel it was planned for
+    return DPR_OK;
+}
 int dpr_set_ari_mode(int32_t mode) {
     if (mode != DPR_ARI_EXACT && mode != DPR_ARI_MONTE_CARLO) return fail(DPR_ERR_INVALID, "unknown ARI mode");
     ctx().ari_mode = mode;

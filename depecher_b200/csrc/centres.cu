@@ -103,6 +103,28 @@ __device__ void build_centre_table(const Problem& pr, int no_zero, int table_cap
         }
         real_before += real;
     }
+    // Tensor-core path (tc_pass.cu): the B operand of D = X * (-2 C)^T in the K-major no-swizzle canonical layout
+    // (element (row, marker) at (marker/4) * 4*npad + 4*row + marker%4), split as -2c = high + low with `high` the
+    // tf32 truncation, so that xh*ch + xh*cl + xl*ch carries fp32-grade accuracy.  Active rows in order, no dummies
+    // inside; padding columns have cc = +huge and a zero operand.
+    if (pr.tc_table) {
+        const int npad = pr.tc_npad, g8 = 2 * ((d + 7) >> 3);
+        float* cc = pr.tc_table;
+        float* bh = cc + npad;
+        float* bl = bh + (size_t)g8 * npad * 4;
+        if (threadIdx.x == 0) h->tc_n = max(16, (n + 15) & ~15);
+        for (int t = threadIdx.x; t < npad; t += blockDim.x) {
+            cc[t] = t < n ? (float)s_cc[s_act[t]] : 3.0e38f;
+            pr.tc_orig[t] = t < n ? s_act[t] : -1;
+        }
+        for (int e = threadIdx.x; e < g8 * npad * 4; e += blockDim.x) {
+            const int g = e / (npad * 4), row = (e % (npad * 4)) >> 2, j = 4 * g + (e & 3);
+            const float v = (row < n && j < d) ? (float)(-2.0 * pr.mu[(size_t)s_act[row] * d + j]) : 0.f;
+            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            bh[e] = hi;
+            bl[e] = v - hi;
+        }
+    }
 }
 
 __global__ void prepare_centres_kernel(Problem* problems, int table_cap) {

@@ -61,6 +61,7 @@ struct CentreHeader {
     int32_t trivial;      // fewer than two active rows: every label 0 (Clusterer.cpp:50-53)
     int32_t force_exact;  // a centre holds NaN/Inf: decide every cell in fp64
     int32_t table_floats; // floats used in the chunk table
+    int32_t tc_n;         // tensor-core path: active centres rounded up to a multiple of 16 (the N of the products)
     float cc_max;         // max ||c||^2 over active centres
     int32_t chunk_kc[kMaxChunks];
     int32_t chunk_off[kMaxChunks];   // float offset of the chunk inside the table
@@ -79,6 +80,9 @@ struct Problem {
     CentreHeader* hdr;
     float* table;         // chunk table (table_cap floats)
     int32_t* orig;        // active slot -> row of mu (n_slots entries, dummies -1)
+    float* tc_table;      // tensor-core path (nullable): cc[tc_npad], then the -2*c operand split in tf32 high / low parts
+    int32_t* tc_orig;     // tensor-core path: column -> row of mu (tc_npad entries, padding -1)
+    int32_t tc_npad;      // columns reserved per problem (k_max rounded up to 32)
     int32_t first_tile;   // index of this problem's first tile in the global tile order
     int32_t n_tiles;
     // Lloyd-loop state (find_centers, Clusterer.cpp:244-252)
@@ -101,6 +105,7 @@ struct Context {
     cudaStream_t own_stream = nullptr;
     int ari_mode = DPR_ARI_EXACT;
     int64_t launches = 0;
+    bool force_ffma = false;             // diagnostics: keep the tensor-core pass off (dpr_set_pass_kernel)
     int32_t* pinned_word = nullptr;      // pinned host word the Lloyd loop polls the active-problem count through
     // optional per-launch timing of the fused pass (dpr_pass_timing)
     bool time_passes = false;

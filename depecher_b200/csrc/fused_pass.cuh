@@ -30,6 +30,20 @@ struct PassPlan {
     size_t smem_bytes;
 };
 
+// tensor-core pass (tc_pass.cu): shared-memory / tensor-memory plan
+struct TcPlan {
+    int32_t d, g8;          // markers; marker groups of 4 rounded up to whole K=8 steps
+    int32_t npad;           // columns reserved per centre set (k_max rounded up to 32)
+    int32_t tmem_cols;      // allocation: 2 x (accumulator npad + xh 4*g8 + xl 4*g8), power of two
+    int32_t stages, stage_floats;
+    int32_t off_hdr, off_cc, off_orig, off_scratch, scratch_bytes, off_b, off_stages;
+    size_t smem_bytes;
+    size_t table_floats;    // floats of Problem::tc_table
+};
+// returns 1 when the shape fits the tensor-core pass (k_max <= 256 columns, 2 x (npad + 2 d8) <= 512 TMEM columns, >= 3 stages)
+int plan_tc_pass(int d, int k_max, TcPlan* plan);
+int launch_tc_pass(const TcPlan& plan, const PassParams& P, int grid, cudaStream_t stream);
+
 // returns 1 and fills the plan when a d-marker slot per warp fits in shared memory, 0 otherwise
 int plan_pass(int d, int k_max, PassPlan* plan);
 int launch_fused_pass(const PassPlan& plan, PassParams P, int grid, cudaStream_t stream);

@@ -36,6 +36,7 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
     if (!plan_pass(d, k_max_, &plan))
         return fail(DPR_ERR_INVALID, "shape not supported by the sm_100a kernels: d = " + std::to_string(d) + ", k = " +
                                          std::to_string(k_max_) + " (one 128-cell slot of d markers plus the centre table must fit in 227 KB)");
+    use_tc = !ctx().force_ffma && plan_tc_pass(d, k_max_, &tc_plan) != 0;
     const int P = (int)specs.size();
     h_problems.assign(P, Problem{});
     // pooled per-problem storage
@@ -51,6 +52,12 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
     DPR_TRY(alloc(&hdr_pool, (size_t)P, true));
     DPR_TRY(alloc(&tab_pool, tab_sz * P, true));
     DPR_TRY(alloc(&orig_pool, orig_sz * P, true));
+    float* tc_tab_pool = nullptr;
+    int32_t* tc_orig_pool = nullptr;
+    if (use_tc) {
+        DPR_TRY(alloc(&tc_tab_pool, tc_plan.table_floats * P, true));
+        DPR_TRY(alloc(&tc_orig_pool, (size_t)tc_plan.npad * P, true));
+    }
     int tile = 0;
     for (int p = 0; p < P; ++p) {
         Problem& pr = h_problems[p];
@@ -65,6 +72,11 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
         pr.hdr = hdr_pool + p;
         pr.table = tab_pool + tab_sz * p;
         pr.orig = orig_pool + orig_sz * p;
+        if (use_tc) {
+            pr.tc_table = tc_tab_pool + tc_plan.table_floats * p;
+            pr.tc_orig = tc_orig_pool + (size_t)tc_plan.npad * p;
+            pr.tc_npad = tc_plan.npad;
+        }
         pr.first_tile = tile;
         pr.n_tiles = (int)((s.n + kSlotCells - 1) / kSlotCells);
         tile += pr.n_tiles;
@@ -77,7 +89,7 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
     DPR_TRY(alloc(&d_problems, (size_t)P, false));
     DPR_CUDA(cudaMemcpyAsync(d_problems, h_problems.data(), sizeof(Problem) * P, cudaMemcpyHostToDevice, ctx().stream));
     // static partition: contiguous, equal tile counts per CTA
-    const int per_cta_min = plan.warps;  // at least one tile per warp before using another CTA
+    const int per_cta_min = use_tc ? 8 : plan.warps;  // a few tiles per CTA before using another one
     grid = std::min(ctx().sms, std::max(1, (total_tiles_ + per_cta_min - 1) / per_cta_min));
     std::vector<int32_t> start(grid + 1);
     for (int c = 0; c <= grid; ++c) start[c] = (int32_t)((int64_t)total_tiles_ * c / grid);
@@ -87,7 +99,7 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
     n_seg = std::min(16, grid);
     seg_entries = (int64_t)k_max_ * d + k_max_ + 1;
     if (want_sums) {
-        const size_t wtabs = (size_t)grid * plan.warps;
+        const size_t wtabs = (size_t)grid * std::max(plan.warps, 8);   // either pass kernel: one private table per (CTA, warp)
         DPR_TRY(alloc(&warp_sums_, wtabs * mu_sz, true));
         DPR_TRY(alloc(&warp_counts_, wtabs * k_max_, true));
         DPR_TRY(alloc(&cta_tables_, (size_t)(grid + P) * seg_entries, true));
@@ -131,6 +143,7 @@ int Session::pass(int mode, bool compare_old) {
     P.warp_counts = warp_counts_;
     P.cta_tables = cta_tables_;
     P.recheck_count = d_recheck;
+    if (use_tc && mode != kPassSums) return launch_tc_pass(tc_plan, P, grid, ctx().stream);
     return launch_fused_pass(plan, P, grid, ctx().stream);
 }
 

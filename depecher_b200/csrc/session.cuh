@@ -51,6 +51,8 @@ public:
     unsigned long long* d_recheck = nullptr;   // cells decided by the fp64 path (diagnostics)
     int grid = 0;
     PassPlan plan{};
+    TcPlan tc_plan{};
+    bool use_tc = false;       // shape fits the tcgen05 pass (tc_pass.cu); otherwise the FFMA pass runs
     bool allow_delta = true;   // let finalize switch a problem to delta accumulation when few labels change
 
     // raw device buffers (exposed for the multi-GPU allreduce between reduce and finalize)

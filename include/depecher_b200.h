@@ -51,6 +51,12 @@ int dpr_set_device(int32_t ordinal);     /* default: device 0 (or LOCAL_RANK via
 int dpr_set_stream(void* cuda_stream);   /* run everything on the caller's cudaStream_t (NULL = library stream) */
 int dpr_synchronize(void);
 int dpr_set_ari_mode(int32_t mode);      /* DPR_ARI_EXACT (default) | DPR_ARI_MONTE_CARLO */
+/* which kernel runs the pass over the cells: DPR_PASS_AUTO (default: the tcgen05 tensor-core pass when the shape fits
+ * tensor memory, else the FFMA pass) | DPR_PASS_FFMA (always the FFMA pass; A/B measurements and tests).  Both give
+ * the same labels. */
+#define DPR_PASS_AUTO 0
+#define DPR_PASS_FFMA 1
+int dpr_set_pass_kernel(int32_t which);
 /* counters for bench/test evidence: kernels launched by this library since the last reset */
 int dpr_kernel_launches(int64_t* out, int32_t reset);
 /* bench evidence: with enable != 0 every launch of the fused pass is bracketed by CUDA events on the

@@ -51,7 +51,7 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_
 __host__ __device__ inline int op_index(int row, int k, int lbo_floats) { return (k >> 2) * lbo_floats + (row >> 3) * 32 + (row & 7) * 4 + (k & 3); }
 
 // mode bit 0: A from shared memory instead of TMEM;  bit 1: feed raw x instead of masked xh
-__global__ void __launch_bounds__(128, 1) probe(const float* __restrict__ x, const float* __restrict__ c, int d, int N, int mode, float* out) {
+__global__ void __launch_bounds__(128, 1) probe(const float* __restrict__ x, const float* __restrict__ c, int d, int N, int mode, float* out, long long* clk) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t bar;
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128, 1) probe(const float* __restrict__ x, con
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1u));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"((mode & 8) ? 2u : 1u));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(128, 1) probe(const float* __restrict__ x, con
     const uint32_t tmem = tmem_base_s;
     const uint32_t acc_col = 0, ah_col = 256, al_col = 384;
 
+    const long long c0 = clock64();
     // this thread's cell row: split and park as the A operand
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
     for (int k0 = 0; k0 < d8; k0 += 8) {
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(128, 1) probe(const float* __restrict__ x, con
                      : "memory");
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    const long long c1 = clock64();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of the smem operands -> tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -116,7 +118,10 @@ __global__ void __launch_bounds__(128, 1) probe(const float* __restrict__ x, con
 
     // instruction descriptor: D fp32, A/B tf32, both K-major, N, M=128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-    if (tid == 0) {
+    const long long c2 = clock64();
+    long long c3 = 0;
+    if (tid == 0 || ((mode & 8) && tid == 32)) {
+        const uint32_t acc_shift = tid == 32 ? 128u : 0u;   // second issuer: its own accumulator
         uint32_t accumulate = 0;
         for (int term = 0; term < 3; ++term) {   // xl*ch, xh*cl, xh*ch
             const float* bsrc = term == 1 ? bl : bh;
@@ -128,19 +133,26 @@ __global__ void __launch_bounds__(128, 1) probe(const float* __restrict__ x, con
                     const uint64_t adesc = make_desc(smem_u32(asrc + 2 * s * a_lbo), a_lbo * 4, 128);
                     mma_ss(tmem + acc_col, adesc, bdesc, idesc, accumulate);
                 } else {
-                    mma_ts(tmem + acc_col, tmem + acol + 8 * s, bdesc, idesc, accumulate);
+                    mma_ts(tmem + acc_col + acc_shift + ((mode & 4) ? (uint32_t)(term * 64 + (s & 1) * 32) : 0u), tmem + acol + 8 * s, bdesc, idesc, (mode & 4) ? (uint32_t)(s > 1) : accumulate);
                 }
                 accumulate = 1;
             }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        c3 = clock64();
     }
     {   // everyone waits for the products
         uint32_t done = 0;
         while (!done)
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
     }
+    const long long c4 = clock64();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+        clk[0] = c1 - c0;   // split + tcgen05.st + wait::st (includes the global loads of x here)
+        clk[1] = c3 - c2;   // issue of all products + commit
+        clk[2] = c4 - c2;   // issue .. products complete (mbarrier observed)
+    }
     for (int n0 = 0; n0 < N; n0 += 8) {
         uint32_t v[8];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -165,6 +177,8 @@ int main() {
         for (auto& v : x) v = (float)((rand() / (double)RAND_MAX - 0.5) * 8.0);
         for (auto& v : c) v = (float)((rand() / (double)RAND_MAX - 0.5) * 6.0);
         float *dx, *dc, *dout;
+        long long* dclk;
+        CK(cudaMalloc(&dclk, 64));
         CK(cudaMalloc(&dx, x.size() * 4));
         CK(cudaMalloc(&dc, c.size() * 4));
         CK(cudaMalloc(&dout, (size_t)M * N * 4));
@@ -172,12 +186,16 @@ int main() {
         CK(cudaMemcpy(dc, c.data(), c.size() * 4, cudaMemcpyHostToDevice));
         const size_t smem = (size_t)(d8 / 4) * ((N / 8) * 32 * 2 + (16 * 32 + 4) * 2) * 4;
         CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        std::vector<float> res[4];
-        for (int mode = 0; mode < 4; ++mode) {
+        std::vector<float> res[5];
+        for (int mode = 0; mode <= (N <= 32 ? 8 : 3); mode = (mode == 4 ? 8 : mode + 1)) {
             CK(cudaMemset(dout, 0xff, (size_t)M * N * 4));
-            probe<<<1, 128, smem>>>(dx, dc, d, N, mode, dout);
+            probe<<<1, 128, smem>>>(dx, dc, d, N, mode, dout, dclk);
             CK(cudaGetLastError());
             CK(cudaDeviceSynchronize());
+            long long hclk[3];
+            CK(cudaMemcpy(hclk, dclk, 24, cudaMemcpyDeviceToHost));
+            printf("   cycles: split+st %lld, issue %lld, issue..done %lld\n", hclk[0], hclk[1], hclk[2]);
+            if (mode >= 4) continue;
             res[mode].resize((size_t)M * N);
             CK(cudaMemcpy(res[mode].data(), dout, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
             double worst = 0, worst32 = 0;

@@ -98,13 +98,14 @@ static int dataset_alloc(int64_t n, int32_t d, dpr_dataset** out) {
     const size_t bytes = sizeof(float) * (size_t)(ds->n_pad / kSlotCells) * tile_floats(d);
     DPR_TRY(dev_alloc((void**)&ds->x, bytes));
     DPR_CUDA(cudaMemsetAsync(ds->x, 0, bytes, ctx().stream));
-    DPR_TRY(dev_alloc((void**)&ds->tile_xx, sizeof(float) * (size_t)(ds->n_pad / kSlotCells)));
+    DPR_TRY(dev_alloc((void**)&ds->tile_xx, sizeof(float) * (size_t)(ds->n_pad / kSlotCells + 1)));
     *out = ds.release();
     return DPR_OK;
 }
 // after the cells are in place: the per-tile norm bounds the fused pass reads
 static int dataset_finish(dpr_dataset* ds) {
-    return launch_tile_norms(ds->x, ds->n_pad / kSlotCells, ds->d, ds->tile_xx, ctx().stream);
+    DPR_TRY(launch_tile_norms(ds->x, ds->n_pad / kSlotCells, ds->d, ds->tile_xx, ctx().stream));
+    return launch_max_finite(ds->tile_xx, ds->n_pad / kSlotCells, ds->tile_xx + ds->n_pad / kSlotCells, ctx().stream);
 }
 static int dataset_labels(dpr_dataset* ds) {
     if (!ds->labels) DPR_TRY(dev_alloc((void**)&ds->labels, sizeof(int32_t) * (size_t)ds->n_pad));
@@ -175,7 +176,7 @@ static int dataset_upload(dpr_dataset* ds, const T* X) {
 static int single_session(dpr_dataset* ds, int k, double reg, int no_zero, bool want_sums, Session& s) {
     DPR_TRY(dataset_labels(ds));
     std::vector<ProblemSpec> specs(1);
-    specs[0] = ProblemSpec{ds->x, ds->tile_xx, ds->n, k, reg, no_zero, ds->labels};
+    specs[0] = ProblemSpec{ds->x, ds->tile_xx, ds->tile_xx + ds->n_pad / kSlotCells, ds->n, k, reg, no_zero, ds->labels};
     return s.init(specs, ds->d, want_sums);
 }
 
@@ -881,7 +882,7 @@ static int grid_search_impl(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
     for (int f = 0; f < F; ++f) {
         int it, j, l;
         cell_of(f, it, j, l);
-        specs[f] = ProblemSpec{xb.as<float>() + (size_t)f * fit_floats, xb_xx.as<float>() + (size_t)f * tiles_b, (int64_t)boot_n, k[j], reg[l], 1,
+        specs[f] = ProblemSpec{xb.as<float>() + (size_t)f * fit_floats, xb_xx.as<float>() + (size_t)f * tiles_b, ds->tile_xx + ds->n_pad / kSlotCells, (int64_t)boot_n, k[j], reg[l], 1,
                                lab_b.as<int32_t>() + (size_t)f * ldb};
     }
     Session fits;
@@ -919,7 +920,7 @@ static int grid_search_impl(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
         const int nc = std::min(batch_cells, cells - c0);
         std::vector<ProblemSpec> sspecs(2 * nc);
         for (int q = 0; q < 2 * nc; ++q)
-            sspecs[q] = ProblemSpec{ds->x, ds->tile_xx, ds->n, specs[2 * c0 + q].k, 0.0, 0, lab_full.as<int32_t>() + (size_t)q * ds->n_pad};
+            sspecs[q] = ProblemSpec{ds->x, ds->tile_xx, ds->tile_xx + ds->n_pad / kSlotCells, ds->n, specs[2 * c0 + q].k, 0.0, 0, lab_full.as<int32_t>() + (size_t)q * ds->n_pad};
         Session score;
         DPR_TRY(score.init(sspecs, d, false));
         for (int q = 0; q < 2 * nc; ++q) DPR_TRY(score.set_centres_device(q, fits.h_problems[2 * c0 + q].mu));
@@ -994,7 +995,7 @@ int dpr_dataset_allocate_many(dpr_dataset_t ds, const double* mus, int32_t m, in
     DevBuf lab;
     DPR_TRY(lab.alloc(sizeof(int32_t) * (size_t)m * ds->n_pad));
     std::vector<ProblemSpec> specs(m);
-    for (int s = 0; s < m; ++s) specs[s] = ProblemSpec{ds->x, ds->tile_xx, ds->n, k, 0.0, no_zero, lab.as<int32_t>() + (size_t)s * ds->n_pad};
+    for (int s = 0; s < m; ++s) specs[s] = ProblemSpec{ds->x, ds->tile_xx, ds->tile_xx + ds->n_pad / kSlotCells, ds->n, k, 0.0, no_zero, lab.as<int32_t>() + (size_t)s * ds->n_pad};
     Session sess;
     DPR_TRY(sess.init(specs, d, false));
     std::vector<double> rm;

@@ -67,6 +67,23 @@ __global__ void tile_norms_kernel(const float* __restrict__ x, int64_t n_tiles, 
     }
 }
 
+// largest finite value of v[0..n) (0 when there is none): the scale the tensor-core pass sizes its fp16 split by
+__global__ void max_finite_kernel(const float* __restrict__ v, int64_t n, float* __restrict__ out) {
+    __shared__ float red[32];
+    float m = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float t = v[i];
+        if (t < INFINITY && t > m) m = t;
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) m = fmaxf(m, red[q]);
+        *out = m;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // bootstrap_data (src/Clusterer.cpp:308-321): rows drawn with replacement, gathered into a new matrix.
 // rows_explicit == nullptr -> row = Philox(seed, BOOT, fit, i) % n   (include/dpr_philox.h)
@@ -416,6 +433,12 @@ int launch_f32_to_cols(const float* src, int64_t e0, int64_t count, int64_t n, i
 }
 int launch_cols_to_f64(const float* x, int64_t row0, int64_t rows, int d, double* out, cudaStream_t st) {
     cols_to_f64_kernel<<<blocks_for(rows * d), 256, 0, st>>>(x, row0, rows, d, out);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_max_finite(const float* v, int64_t n, float* out, cudaStream_t st) {
+    max_finite_kernel<<<1, 1024, 0, st>>>(v, n, out);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;

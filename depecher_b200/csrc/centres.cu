@@ -9,6 +9,8 @@
 //   labels did not change AND i > 20; penalty ramp reg*((float)i/(float)20) capped at reg).
 #include "centres.cuh"
 
+#include <cuda_fp16.h>
+
 namespace dpr {
 
 // Build header / chunk table / slot map of one problem from its fp64 centres.  One CTA; k, d are small.
@@ -103,26 +105,56 @@ __device__ void build_centre_table(const Problem& pr, int no_zero, int table_cap
         }
         real_before += real;
     }
-    // Tensor-core path (tc_pass.cu): the B operand of D = X * (-2 C)^T in the K-major no-swizzle canonical layout
-    // (element (row, marker) at (marker/4) * 4*npad + 4*row + marker%4), split as -2c = high + low with `high` the
-    // tf32 truncation, so that xh*ch + xh*cl + xl*ch carries fp32-grade accuracy.  Active rows in order, no dummies
-    // inside; padding columns have cc = +huge and a zero operand.
+    // Tensor-core path (tc_pass.cu): the B operand of D = X * (-2 C)^T for tcgen05.mma kind::f16, K-major no-swizzle
+    // canonical layout (core matrix = 8 rows x 8 halves).  Cells and centres are first multiplied by powers of two that
+    // bring their largest magnitude to <= 2^13 (exact), then split as v = high + low with both parts fp16, so that
+    // xh*ch + xh*cl + xl*ch carries fp32-grade accuracy (error model in tc_pass.cu).  ONE operand of 2*npad rows: rows
+    // [0, npad) hold the high parts, rows [npad, 2*npad) the low parts, so a single product against xh yields xh*ch and
+    // xh*cl side by side: half (row, marker) at byte (marker/8) * 32*npad + 16*row + 2*(marker%8).  Active rows in
+    // order, no dummies inside; padding rows are zero and their cc is +huge.
     if (pr.tc_table) {
-        const int npad = pr.tc_npad, g8 = 2 * ((d + 7) >> 3);
+        const int npad = pr.tc_npad, g16 = 2 * ((d + 15) >> 4);
         float* cc = pr.tc_table;
-        float* bh = cc + npad;
-        float* bl = bh + (size_t)g8 * npad * 4;
-        if (threadIdx.x == 0) h->tc_n = max(16, (n + 15) & ~15);
+        __half* b = reinterpret_cast<__half*>(cc + npad);
+        __shared__ float s_sc;
+        if (threadIdx.x == 0) {
+            h->tc_n = max(16, (n + 15) & ~15);
+            auto pow2_to_2p13 = [](float vmax) {   // exponent e with vmax * 2^e <= 2^13, clamped
+                if (!(vmax > 0.f) || !(vmax < INFINITY)) return 0;
+                int q;
+                frexpf(vmax, &q);   // vmax = m * 2^q, m in [0.5, 1)
+                return max(-60, min(60, 13 - q));
+            };
+            // no scaling (exponent 0) when the magnitudes already sit in fp16's comfortable range [2^-6, 2^13]
+            auto scale_exp = [&](float vmax) {
+                if (vmax >= 0.015625f && vmax <= 8192.f) return 0;
+                return pow2_to_2p13(vmax);
+            };
+            const int ex = scale_exp(sqrtf(*pr.xx_max) * 1.0001f);
+            const int ec = scale_exp(2.f * sqrtf(h->cc_max) * 1.0001f);
+            h->tc_scale_x = ldexpf(1.f, ex);
+            h->tc_unscale = ldexpf(1.f, -(ex + ec));
+            // |X - xh - xl| <= 2^-22 |X| + 2^-25 (fp16 subnormal spacing), same for the centres: the absolute parts add up to
+            // 2^-25 (2^-ec ||x||_1 + 2^-ex ||2c||_1) per score, ||.||_1 <= sqrt(d) ||.||_2; doubled for a difference of two scores
+            const float k = 2.02f * 2.9802322e-8f * sqrtf((float)d);
+            h->tc_abs1 = k * ldexpf(1.f, -ec);
+            h->tc_abs2 = k * ldexpf(1.f, -ex) * 2.f * sqrtf(h->cc_max);
+            s_sc = ldexpf(1.f, ec);
+        }
+        __syncthreads();
+        const float sc = s_sc;
         for (int t = threadIdx.x; t < npad; t += blockDim.x) {
             cc[t] = t < n ? (float)s_cc[s_act[t]] : 3.0e38f;
             pr.tc_orig[t] = t < n ? s_act[t] : -1;
         }
-        for (int e = threadIdx.x; e < g8 * npad * 4; e += blockDim.x) {
-            const int g = e / (npad * 4), row = (e % (npad * 4)) >> 2, j = 4 * g + (e & 3);
-            const float v = (row < n && j < d) ? (float)(-2.0 * pr.mu[(size_t)s_act[row] * d + j]) : 0.f;
-            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-            bh[e] = hi;
-            bl[e] = v - hi;
+        for (int e = threadIdx.x; e < g16 * npad * 8; e += blockDim.x) {
+            const int g = e / (npad * 8), row = (e % (npad * 8)) >> 3, j = 8 * g + (e & 7);
+            const float v = (row < n && j < d) ? (float)(-2.0 * pr.mu[(size_t)s_act[row] * d + j]) * sc : 0.f;
+            const __half hi = __float2half_rn(v);
+            const __half lo = __float2half_rn(v - __half2float(hi));
+            const size_t at = (size_t)g * (16 * npad) + (size_t)row * 8 + (e & 7);   // in halves
+            b[at] = hi;
+            b[at + (size_t)npad * 8] = lo;
         }
     }
 }

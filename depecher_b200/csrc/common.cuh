@@ -62,6 +62,9 @@ struct CentreHeader {
     int32_t force_exact;  // a centre holds NaN/Inf: decide every cell in fp64
     int32_t table_floats; // floats used in the chunk table
     int32_t tc_n;         // tensor-core path: active centres rounded up to a multiple of 16 (the N of the products)
+    float tc_scale_x;     // power of two the cells are multiplied by before the fp16 split
+    float tc_unscale;     // 1 / (cell scale * centre scale): brings a product back to -2 x.c
+    float tc_abs1, tc_abs2;   // absolute part of the error bound: tau += tc_abs1 * sqrt(xx_tile) + tc_abs2
     float cc_max;         // max ||c||^2 over active centres
     int32_t chunk_kc[kMaxChunks];
     int32_t chunk_off[kMaxChunks];   // float offset of the chunk inside the table
@@ -72,6 +75,7 @@ struct CentreHeader {
 struct Problem {
     const float* x;       // resident fp32 cells, tile-major (see x_index)
     const float* tile_xx; // per tile: an upper bound of ||x||^2 over its cells (enters the near-tie threshold)
+    const float* xx_max;  // one float: the largest finite tile bound of the matrix the cells come from (fp16 scaling of the tensor-core pass)
     int64_t n;            // cells
     int32_t d;
     int32_t k;
@@ -80,7 +84,7 @@ struct Problem {
     CentreHeader* hdr;
     float* table;         // chunk table (table_cap floats)
     int32_t* orig;        // active slot -> row of mu (n_slots entries, dummies -1)
-    float* tc_table;      // tensor-core path (nullable): cc[tc_npad], then the -2*c operand split in tf32 high / low parts
+    float* tc_table;      // tensor-core path (nullable): cc[tc_npad], then the scaled -2*c operand split in fp16 high / low parts
     int32_t* tc_orig;     // tensor-core path: column -> row of mu (tc_npad entries, padding -1)
     int32_t tc_npad;      // columns reserved per problem (k_max rounded up to 32)
     int32_t first_tile;   // index of this problem's first tile in the global tile order
@@ -128,6 +132,6 @@ struct dpr_dataset {
     int32_t d = 0;
     int64_t n_pad = 0;         // n rounded up to whole tiles
     float* x = nullptr;        // device, tile-major (dpr::x_index), (n_pad / 128) * tile_floats(d) floats
-    float* tile_xx = nullptr;  // device, n_pad / 64 floats: max ||x||^2 of each tile (rounded up)
+    float* tile_xx = nullptr;  // device, n_pad / 128 + 1 floats: max ||x||^2 of each tile (rounded up), then the largest finite one
     int32_t* labels = nullptr; // device, n_pad entries (lazily allocated)
 };

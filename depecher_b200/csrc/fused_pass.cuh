@@ -32,15 +32,18 @@ struct PassPlan {
 
 // tensor-core pass (tc_pass.cu): shared-memory / tensor-memory plan
 struct TcPlan {
-    int32_t d, g8;          // markers; marker groups of 4 rounded up to whole K=8 steps
+    int32_t d, g8;          // markers; groups of 8 markers rounded up to whole K=16 steps
+    int32_t wait_hint;      // suspend-time hint (ns) of the mbarrier waits
+    int32_t debug_terms;    // measurement aid (DPR_TC_DEBUG_TERMS=1: only the xh*ch products — wrong labels, timing only)
+    int32_t groups;         // consumer groups per CTA (2..4: as many as tensor memory holds)
     int32_t npad;           // columns reserved per centre set (k_max rounded up to 32)
-    int32_t tmem_cols;      // allocation: 2 x (accumulator npad + xh 4*g8 + xl 4*g8), power of two
+    int32_t tmem_cols;      // allocation: groups x (accumulator 2*npad + xh 4*g8 + xl 4*g8 columns), power of two
     int32_t stages, stage_floats;
     int32_t off_hdr, off_cc, off_orig, off_scratch, scratch_bytes, off_b, off_stages;
     size_t smem_bytes;
     size_t table_floats;    // floats of Problem::tc_table
 };
-// returns 1 when the shape fits the tensor-core pass (k_max <= 256 columns, 2 x (npad + 2 d8) <= 512 TMEM columns, >= 3 stages)
+// returns 1 when the shape fits the tensor-core pass (k_max <= 128, >= 2 consumer groups in the 512 TMEM columns, >= 3 stages)
 int plan_tc_pass(int d, int k_max, TcPlan* plan);
 int launch_tc_pass(const TcPlan& plan, const PassParams& P, int grid, cudaStream_t stream);
 

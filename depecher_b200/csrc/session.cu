@@ -64,6 +64,7 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
         const ProblemSpec& s = specs[p];
         pr.x = s.x;
         pr.tile_xx = s.tile_xx;
+        pr.xx_max = s.xx_max;
         pr.n = s.n;
         pr.d = d;
         pr.k = s.k;
@@ -89,7 +90,7 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
     DPR_TRY(alloc(&d_problems, (size_t)P, false));
     DPR_CUDA(cudaMemcpyAsync(d_problems, h_problems.data(), sizeof(Problem) * P, cudaMemcpyHostToDevice, ctx().stream));
     // static partition: contiguous, equal tile counts per CTA
-    const int per_cta_min = use_tc ? 8 : plan.warps;  // a few tiles per CTA before using another one
+    const int per_cta_min = use_tc ? 4 * tc_plan.groups : plan.warps;  // a few tiles per CTA before using another one
     grid = std::min(ctx().sms, std::max(1, (total_tiles_ + per_cta_min - 1) / per_cta_min));
     std::vector<int32_t> start(grid + 1);
     for (int c = 0; c <= grid; ++c) start[c] = (int32_t)((int64_t)total_tiles_ * c / grid);
@@ -99,7 +100,7 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
     n_seg = std::min(16, grid);
     seg_entries = (int64_t)k_max_ * d + k_max_ + 1;
     if (want_sums) {
-        const size_t wtabs = (size_t)grid * std::max(plan.warps, 8);   // either pass kernel: one private table per (CTA, warp)
+        const size_t wtabs = (size_t)grid * std::max(plan.warps, 16);   // either pass kernel: one private table per (CTA, warp)
         DPR_TRY(alloc(&warp_sums_, wtabs * mu_sz, true));
         DPR_TRY(alloc(&warp_counts_, wtabs * k_max_, true));
         DPR_TRY(alloc(&cta_tables_, (size_t)(grid + P) * seg_entries, true));

@@ -16,6 +16,7 @@ namespace dpr {
 struct ProblemSpec {
     const float* x;        // tile-major resident cells
     const float* tile_xx;  // per-tile bound of ||x||^2
+    const float* xx_max;   // one float: largest finite tile bound of the source matrix
     int64_t n;
     int32_t k;
     double reg;

@@ -22,11 +22,16 @@
 #include "fused_pass.cuh"
 #include "pass_device.cuh"
 
+#include <cuda_fp16.h>
+
+#include <cstdio>
+#include <cstdlib>
+
 namespace dpr {
 
-constexpr int kTcGroups = 2;                      // consumer groups; group g takes the CTA's tiles g, g + G, ...
-constexpr int kTcWarps = 4 * kTcGroups;           // consumer warps: a group = 4 warps x 32 TMEM lanes = the 128 cells of a tile
-constexpr int kTcThreads = (kTcWarps + 2) * 32;   // + the warp that issues the products + the producer warp
+// G consumer groups per CTA; group g takes the CTA's tiles g, g + G, ...  A group = 4 warps x 32 TMEM lanes = the
+// 128 cells of a tile.  Two more warps: the one that issues the products and the producer.
+constexpr int kTcMaxGroups = 4;
 constexpr int kTcMaxStages = 8;
 
 // ---------------------------------------------------------------------------------------------------
@@ -34,7 +39,22 @@ constexpr int kTcMaxStages = 8;
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kTcWarps * 32) : "memory"); }   // all consumer warps
+template <int THREADS>
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }   // all consumer warps
+// wait with a suspend-time hint: the warp sleeps in hardware between polls instead of burning issue slots
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(hint_ns)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -43,20 +63,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((addr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) | ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(d_tmem),
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float4& a, const float4& b) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__float_as_uint(a.x)),
-                 "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b.x)),
-                 "r"(__float_as_uint(b.y)), "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w))
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&w)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                  : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32], int o) {
@@ -77,13 +96,57 @@ __device__ __forceinline__ bool elect_one() {
         : "r"(0xffffffffu));
     return pred != 0;
 }
-__device__ __forceinline__ float tf32_low(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+// v (already scaled) = hi + lo + r with hi, lo fp16 and |r| <= 2^-22 |v| + 2^-25; two values per 32-bit TMEM column
+// (the element with the lower K index in the low half)
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&w)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+// one cell's markers -> fp16 high / low parts in tensor memory; 8 markers (2 marker groups of the tile, 4 TMEM columns
+// per operand) per step.  st4 points at the cell's 16 bytes inside marker group 0.  Columns past the last step belong
+// to the zero padding of the last K=16 step: written once at kernel start, never again.
+template <bool SCALED>
+__device__ __forceinline__ void split_group(const float4* __restrict__ st4, float scale, uint32_t& hi0, uint32_t& hi1, uint32_t& lo0, uint32_t& lo1) {
+    float4 v = *st4;   // 4 markers of the cell
+    if (SCALED) {
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    }
+    split_pair(v.x, v.y, hi0, lo0);
+    split_pair(v.z, v.w, hi1, lo1);
+}
+template <bool SCALED>
+__device__ __forceinline__ void split_tile(const float4* __restrict__ st4, int steps, float scale, uint32_t a_hi, uint32_t a_lo) {
+    constexpr int G4 = kGroupFloats / 4;   // float4 stride between marker groups
+    int g = 0;
+    for (; g + 1 < steps; g += 2, st4 += 4 * G4, a_hi += 8, a_lo += 8) {   // 16 markers -> 8 columns per operand
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) split_group<SCALED>(st4 + q * G4, scale, hi[2 * q], hi[2 * q + 1], lo[2 * q], lo[2 * q + 1]);
+        tmem_st8(a_hi, hi);
+        tmem_st8(a_lo, lo);
+    }
+    if (g < steps) {   // 8 more markers -> 4 columns
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) split_group<SCALED>(st4 + q * G4, scale, hi[2 * q], hi[2 * q + 1], lo[2 * q], lo[2 * q + 1]);
+        tmem_st4(a_hi, hi);
+        tmem_st4(a_lo, lo);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_pass_kernel(const PassParams P, const TcPlan T) {
+template <int MODE, int kTcGroups>
+__global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(const PassParams P, const TcPlan T) {
+    constexpr int kTcWarps = 4 * kTcGroups;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t_begin = P.cta_tile_start[blockIdx.x], t_end = P.cta_tile_start[blockIdx.x + 1];
@@ -93,19 +156,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pass_kernel(const PassParams
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [S] tile landed
     uint64_t* empty = full + kTcMaxStages;                // [S] tile no longer needed (one arrival per warp of the consuming group)
     uint64_t* a_ready = empty + kTcMaxStages;             // [G] the group's A operands are in tensor memory (one arrival per warp)
-    uint64_t* mma_done = a_ready + 4;                     // [G] products into the group's accumulator finished
-    uint64_t* tables_ready = mma_done + 4;                // the problem's centre tables are in shared memory
+    uint64_t* mma_done = a_ready + kTcMaxGroups;                     // [G] products into the group's accumulator finished
+    uint64_t* tables_ready = mma_done + kTcMaxGroups;                // the problem's centre tables are in shared memory
     uint32_t* tmem_word = reinterpret_cast<uint32_t*>(tables_ready + 1);
     CentreHeader* hdr = reinterpret_cast<CentreHeader*>(smem + T.off_hdr);
     float* cc_s = reinterpret_cast<float*>(smem + T.off_cc);
     int32_t* orig = reinterpret_cast<int32_t*>(smem + T.off_orig);
     float* bmat = reinterpret_cast<float*>(smem + T.off_b);
     float* stages = reinterpret_cast<float*>(smem + T.off_stages);
-    const int d = T.d, groups = tile_groups(d), g8 = T.g8;
+    const int d = T.d, groups = tile_groups(d), g16 = T.g8;   // g16: groups of 8 markers, whole K=16 steps
     const size_t tile_fl = tile_floats(d);
     const uint32_t tile_bytes = (uint32_t)(tile_fl * 4);
-    const int npad = T.npad, d8 = 4 * g8;
-    const uint32_t buf_cols = (uint32_t)(npad + 2 * d8);   // per group: accumulator, xh, xl
+    const int npad = T.npad, acols = 4 * g16;              // 32-bit TMEM columns of one fp16 A operand (2 markers each)
+    const uint32_t buf_cols = (uint32_t)(2 * npad + 2 * acols);   // per group: accumulator (high | low centre parts), xh, xl
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -123,9 +186,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pass_kernel(const PassParams
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)), "r"((uint32_t)T.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (g8 > groups)   // d % 8 in 1..4: the second half of the last K=8 step is a marker group no tile brings — zero, once
+    if (groups & 1)   // the split reads marker groups in pairs: the partner of an odd last group is never written by a copy — zero, once
         for (int s = 0; s < S; ++s)
-            for (int i = threadIdx.x; i < kGroupFloats; i += kTcThreads) stages[(size_t)s * T.stage_floats + (size_t)groups * kGroupFloats + i] = 0.f;
+            for (int i = threadIdx.x; i < kGroupFloats; i += blockDim.x) stages[(size_t)s * T.stage_floats + (size_t)groups * kGroupFloats + i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -156,7 +219,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pass_kernel(const PassParams
             const float* src = pr->x + (size_t)(tile - first_tile) * tile_fl;
             for (; tile < p_end; ++tile, src += tile_fl) {
                 if (issued >= S) {
-                    mbar_wait(&empty[s], (phase >> s) & 1u);
+                    mbar_wait_hint(&empty[s], (phase >> s) & 1u, T.wait_hint);
                     phase ^= 1u << s;
                 }
                 if (elect_one()) {
@@ -176,10 +239,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pass_kernel(const PassParams
     if (warp == kTcWarps) {
         int tile = t_begin;
         uint32_t it = 0, n_prob = 0;
-        const uint32_t bh_addr = smem_u32(bmat), bl_addr = bh_addr + (uint32_t)(g8 * npad * 16);
-        const uint32_t lbo = (uint32_t)npad * 16u;
-        const uint64_t desc_h0 = umma_desc(bh_addr, lbo, 128), desc_l0 = umma_desc(bl_addr, lbo, 128);
-        const uint64_t desc_step = (uint64_t)((2u * lbo) >> 4);   // one K=8 step = two marker groups further
+        const uint32_t lbo = (uint32_t)npad * 32u;   // bytes between 8-marker groups of the (2*npad)-row B operand
+        const uint64_t desc_b0 = umma_desc(smem_u32(bmat), lbo, 128);
+        const uint64_t desc_step = (uint64_t)((2u * lbo) >> 4);   // one K=16 step = two marker groups further
         while (tile < t_end) {
             const Problem* pr = P.problems + p;
             const int p_end = min(t_end, pr->first_tile + pr->n_tiles);
@@ -188,21 +250,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pass_kernel(const PassParams
                 ++p;
                 continue;
             }
-            mbar_wait(tables_ready, n_prob & 1u);
+            mbar_wait_hint(tables_ready, n_prob & 1u, T.wait_hint);
             ++n_prob;
             const int N = hdr->tc_n;
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc0 = (1u << 4) | ((uint32_t)(128 >> 4) << 24);           // D fp32, A/B fp16, both K-major, M = 128
+            const uint32_t idesc_hi = idesc0 | ((uint32_t)((npad + N) >> 3) << 17);     // xh * [ch | cl] -> columns [0, npad + N)
+            const uint32_t idesc_lo = idesc0 | ((uint32_t)(N >> 3) << 17);              // xl * ch        -> columns [0, N)
             for (; tile < p_end; ++tile, ++it) {
                 const uint32_t g = it % kTcGroups, k = it / kTcGroups;
-                mbar_wait(&a_ready[g], k & 1u);
+                mbar_wait_hint(&a_ready[g], k & 1u, T.wait_hint);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t acc = tmem + g * buf_cols, ah = acc + (uint32_t)npad, al = ah + (uint32_t)d8;
-                    for (int s = 0; s < g8 / 2; ++s) {   // small terms first
-                        umma_tf32_ts(acc, al + 8 * s, desc_h0 + s * desc_step, idesc, s > 0 ? 1u : 0u);
-                        umma_tf32_ts(acc, ah + 8 * s, desc_l0 + s * desc_step, idesc, 1);
+                    const uint32_t acc = tmem + g * buf_cols, ah = acc + (uint32_t)(2 * npad), al = ah + (uint32_t)acols;
+                    for (int s = 0; s < g16 / 2; ++s) {
+                        umma_f16_ts(acc, ah + 8 * s, desc_b0 + s * desc_step, idesc_hi, s > 0 ? 1u : 0u);
+                        if (T.debug_terms != 1) umma_f16_ts(acc, al + 8 * s, desc_b0 + s * desc_step, idesc_lo, 1);
                     }
-                    for (int s = 0; s < g8 / 2; ++s) umma_tf32_ts(acc, ah + 8 * s, desc_h0 + s * desc_step, idesc, 1);
                     umma_commit(&mma_done[g]);
                 }
                 __syncwarp();
@@ -221,9 +284,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pass_kernel(const PassParams
     long long* my_counts = P.warp_counts ? P.warp_counts + wtab * P.k_max : nullptr;
     const int mycell_in_tile = wq * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)grp * buf_cols;
-    const uint32_t a_hi = lane_base + (uint32_t)npad, a_lo = a_hi + (uint32_t)d8;
+    const uint32_t a_hi = lane_base + (uint32_t)(2 * npad), a_lo = a_hi + (uint32_t)acols;
+    const int steps8 = (d + 7) >> 3;   // 8-marker steps that hold data
+    {   // zero padding of the last K=16 step, in both operands of this group's buffer
+        const uint32_t z[4] = {0u, 0u, 0u, 0u};
+        for (int c = 4 * steps8; c < acols; c += 4) {
+            tmem_st4(a_hi + c, z);
+            tmem_st4(a_lo + c, z);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
 
+#ifdef DPR_TC_PROFILE
+    long long prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_n = 0;
+#define DPR_PROF(i) do { prof_t[i] = clock64(); if (i > 0) prof_acc[i] += prof_t[i] - prof_t[i - 1]; if (i == 7) ++prof_n; } while (0)
+#else
+#define DPR_PROF(i)
+#endif
     uint32_t it = 0;        // tiles this CTA has walked past (all groups)
+    int s_mine = grp % S;   // stage and landing parity of this group's next tile (its ordinal is grp, grp + G, ...)
+    uint32_t par_mine = (uint32_t)(grp / S) & 1u;
     uint32_t k_mine = 0;    // tiles this group has taken
     int tile = t_begin;
     while (tile < t_end) {
@@ -234,29 +315,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pass_kernel(const PassParams
             ++p;
             continue;
         }
-        consumer_barrier();   // nobody still reads the previous problem's tables (every group has seen its last products complete)
+        consumer_barrier<kTcWarps * 32>();   // nobody still reads the previous problem's tables (every group has seen its last products complete)
         {
             const int* src = reinterpret_cast<const int*>(pr.hdr);
             int* dst = reinterpret_cast<int*>(hdr);
             for (int i = threadIdx.x; i < (int)(sizeof(CentreHeader) / 4); i += kTcWarps * 32) dst[i] = src[i];
             const float4* bsrc = reinterpret_cast<const float4*>(pr.tc_table + npad);
             float4* bdst = reinterpret_cast<float4*>(bmat);
-            for (int i = threadIdx.x; i < 2 * g8 * npad; i += kTcWarps * 32) bdst[i] = bsrc[i];
+            for (int i = threadIdx.x; i < 2 * g16 * npad; i += kTcWarps * 32) bdst[i] = bsrc[i];   // g16 groups x 2*npad rows x 16 B
             for (int i = threadIdx.x; i < npad; i += kTcWarps * 32) {
                 cc_s[i] = pr.tc_table[i];
                 orig[i] = pr.tc_orig[i];
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the B operand was written through the generic proxy
-        consumer_barrier();
+        consumer_barrier<kTcWarps * 32>();
         if (threadIdx.x == 0) mbar_arrive(tables_ready);
         const int N = hdr->tc_n, n_act = hdr->k_act;
         const bool trivial = hdr->trivial != 0, force_exact = hdr->force_exact != 0;
-        // error bound of a score: tf32 splits 3 * 2^-20, accumulation 2^-22 per product step, both relative to
-        // sum|x_j c_j| <= (||x||^2 + ||c||^2) / 2 and doubled by the factor -2; cc rounding and the final add 3 * 2^-24;
-        // twice that for a difference of two scores, plus the 5 masked index bits (2 * 2^-18) — see DESIGN.md §3
-        const float eps = 3.f * 9.5367432e-7f + (float)(3 * (d8 / 8)) * 2.3841858e-7f + 3.f * 5.9604645e-8f;
+        // error bound of a score (see the header comment): fp16 splits 3 * 2^-22 and fp32 accumulation 2^-22 per product
+        // step, both relative to sum|x_j c_j| <= (||x||^2 + ||c||^2) / 2 and doubled by the factor -2; the sum of the two
+        // accumulator halves, the unscaling fma and cc 4 * 2^-24; twice that for a difference of two scores, plus the
+        // 5 masked index bits (2 * 2^-18); the absolute part of the split error comes through tc_abs1 / tc_abs2
+        const float eps = 3.f * 2.3841858e-7f + (float)(g16 + 1) * 2.3841858e-7f + 4.f * 5.9604645e-8f;
         const float tau_c = 2.f * eps + 7.6293945e-6f;
+        const float scale_x = hdr->tc_scale_x, unscale = hdr->tc_unscale, abs1 = hdr->tc_abs1, abs2 = hdr->tc_abs2;
         const float cc2 = 2.0f * hdr->cc_max;
         const bool delta = MODE == kPassLloyd && pr.delta;
         const bool need_old = (P.compare_old || delta) && pr.labels;
@@ -265,54 +348,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pass_kernel(const PassParams
 
         // this group's tiles of the range: j with (it + j) % G == grp
         for (int j = (int)((grp + kTcGroups - it % kTcGroups) % kTcGroups); j < count; j += kTcGroups, ++k_mine) {
-            const uint32_t git = it + (uint32_t)j;             // ordinal of the tile in the CTA's walk: stage and phase of its landing
-            const int s = (int)(git % (uint32_t)S);
+            const int s = s_mine;
+            const uint32_t full_par = par_mine;
+            s_mine += kTcGroups;
+            while (s_mine >= S) {
+                s_mine -= S;
+                par_mine ^= 1u;
+            }
             const float* slot = stages + (size_t)s * T.stage_floats;
             const int64_t mycell = (int64_t)(tile + j - pr.first_tile) * kSlotCells + mycell_in_tile;
             const bool live = mycell < pr.n;
             int oldl = 0;
             if (need_old && live) oldl = pr.labels[mycell];
             const float xx_tile = pr.tile_xx[tile + j - pr.first_tile];
-            mbar_wait(&full[s], (git / (uint32_t)S) & 1u);
+            DPR_PROF(0);
+            mbar_wait_hint(&full[s], full_par, T.wait_hint);
+            DPR_PROF(1);
             // ---- split into tf32 high/low parts, parked in tensor memory as the A operands
             {
                 const float4* st4 = reinterpret_cast<const float4*>(slot) + mycell_in_tile;
-                for (int g = 0; g < g8; g += 2) {
-                    const float4 v0 = st4[g * (kGroupFloats / 4)], v1 = st4[(g + 1) * (kGroupFloats / 4)];
-                    tmem_st8(a_hi + 4 * g, v0, v1);
-                    tmem_st8(a_lo + 4 * g, make_float4(tf32_low(v0.x), tf32_low(v0.y), tf32_low(v0.z), tf32_low(v0.w)),
-                             make_float4(tf32_low(v1.x), tf32_low(v1.y), tf32_low(v1.z), tf32_low(v1.w)));
-                }
+                if (scale_x == 1.f) split_tile<false>(st4, steps8, 1.f, a_hi, a_lo);
+                else split_tile<true>(st4, steps8, scale_x, a_hi, a_lo);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_ready[grp]);
             }
+            DPR_PROF(2);
             // ---- scores -> label (+ sums)
-            mbar_wait(&mma_done[grp], k_mine & 1u);
+            mbar_wait_hint(&mma_done[grp], k_mine & 1u, T.wait_hint);
             tc_fence_after();
+            DPR_PROF(3);
             int lab = 0;
             if (!trivial) {
                 float best = 3.3e38f, second = 3.3e38f;
                 int bchunk = 0;
-                for (int n0 = 0; n0 < N; n0 += 32) {
+                for (int n0 = 0; n0 < N; n0 += 16) {   // N is a multiple of 16
                     uint32_t v[32];
-                    tmem_ld16(lane_base + n0, v, 0);
-                    if (n0 + 16 < N) tmem_ld16(lane_base + n0 + 16, v, 16);
-                    else {
-#pragma unroll
-                        for (int t = 16; t < 32; ++t) v[t] = 0u;   // columns beyond N: cc is +huge there
-                    }
+                    tmem_ld16(lane_base + n0, v, 0);                        // x . ch (+ xl . ch)
+                    tmem_ld16(lane_base + (uint32_t)npad + n0, v, 16);     // xh . cl
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    DPR_PROF(4);
                     const float prev = best;
                     const float4* cc4 = reinterpret_cast<const float4*>(cc_s + n0);
+                    const int i0 = n0 & 16;   // index inside the 32-column block
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
+                    for (int q = 0; q < 4; ++q) {
                         const float4 c = cc4[q];
-                        const float s0 = pack_idx(c.x + __uint_as_float(v[4 * q + 0]), 4 * q + 0);
-                        const float s1 = pack_idx(c.y + __uint_as_float(v[4 * q + 1]), 4 * q + 1);
-                        const float s2 = pack_idx(c.z + __uint_as_float(v[4 * q + 2]), 4 * q + 2);
-                        const float s3 = pack_idx(c.w + __uint_as_float(v[4 * q + 3]), 4 * q + 3);
+                        const float s0 = pack_idx(fmaf(unscale, __uint_as_float(v[4 * q + 0]) + __uint_as_float(v[16 + 4 * q + 0]), c.x), i0 + 4 * q + 0);
+                        const float s1 = pack_idx(fmaf(unscale, __uint_as_float(v[4 * q + 1]) + __uint_as_float(v[16 + 4 * q + 1]), c.y), i0 + 4 * q + 1);
+                        const float s2 = pack_idx(fmaf(unscale, __uint_as_float(v[4 * q + 2]) + __uint_as_float(v[16 + 4 * q + 2]), c.z), i0 + 4 * q + 2);
+                        const float s3 = pack_idx(fmaf(unscale, __uint_as_float(v[4 * q + 3]) + __uint_as_float(v[16 + 4 * q + 3]), c.w), i0 + 4 * q + 3);
                         const float lo0 = fminf(s0, s1), hi0 = fmaxf(s0, s1);
                         second = fmin3(fmaxf(best, lo0), second, hi0);
                         best = fminf(best, lo0);
@@ -320,12 +406,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pass_kernel(const PassParams
                         second = fmin3(fmaxf(best, lo1), second, hi1);
                         best = fminf(best, lo1);
                     }
-                    if (best < prev) bchunk = n0;
+                    if (best < prev) bchunk = n0 & ~31;
                 }
-                const float tau = tau_c * (xx_tile + cc2) + 1e-30f;
+                const float tau = tau_c * (xx_tile + cc2) + (abs1 * sqrtf(xx_tile) + abs2) + 1e-30f;
                 const int a = bchunk + (int)(__float_as_uint(best) & 31u);
                 const bool sure = (second - best > tau) && !force_exact;
                 lab = orig[a < n_act ? a : 0];
+                DPR_PROF(5);
                 unsigned redo = __ballot_sync(0xffffffffu, !sure && live);
                 if (redo && P.recheck_count && lane == 0) atomicAdd(P.recheck_count, (unsigned long long)__popc(redo));
                 while (redo) {   // the whole warp re-decides each doubtful cell in fp64
@@ -335,6 +422,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pass_kernel(const PassParams
                     if (lane == src) lab = v;
                 }
             }
+            DPR_PROF(6);
             if (!live) lab = -1;
             const bool ch = lab >= 0 && lab != oldl;
             if (P.compare_old) changed += (int)ch;
@@ -363,6 +451,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pass_kernel(const PassParams
             tc_fence_before();   // this warp's tcgen05.ld of the accumulator are complete before the next products overwrite it
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
+            DPR_PROF(7);
         }
         it += (uint32_t)count;
         // ---- combine the warps' tables of this (CTA, problem) in fixed order; reset them for the next range
@@ -371,9 +460,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pass_kernel(const PassParams
             for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
             long long* s_changed = reinterpret_cast<long long*>(smem + T.off_cc);   // the centre tables are no longer needed ...
             __threadfence();   // the warps' table updates are visible to the whole CTA
-            consumer_barrier();   // ... once every warp is past its last tile
+            consumer_barrier<kTcWarps * 32>();   // ... once every warp is past its last tile
             if (lane == 0) s_changed[warp] = changed;
-            consumer_barrier();
+            consumer_barrier<kTcWarps * 32>();
             const int64_t stride = P.part_stride;
             const int64_t entries = stride + P.k_max + 1;
             double* out = P.cta_tables + (size_t)(blockIdx.x + p) * entries;
@@ -413,8 +502,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pass_kernel(const PassParams
         tile = p_end;
         ++p;
     }
+#ifdef DPR_TC_PROFILE
+    if (blockIdx.x == 3 && lane == 0 && (warp & 3) == 0)
+        printf("warp %d tiles %lld: wait_full %lld split %lld wait_mma %lld tmem_ld %lld argmin %lld recheck %lld store+release %lld\n", warp, prof_n, prof_acc[1] / prof_n, prof_acc[2] / prof_n,
+               prof_acc[3] / prof_n, prof_acc[4] / prof_n, prof_acc[5] / prof_n, prof_acc[6] / prof_n, prof_acc[7] / prof_n);
+#endif
     tc_fence_before();
-    consumer_barrier();
+    consumer_barrier<kTcWarps * 32>();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)T.tmem_cols));
 }
 
@@ -424,23 +518,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pass_kernel(const PassParams
 int plan_tc_pass(int d, int k_max, TcPlan* plan) {
     if (d < 1 || k_max < 1) return 0;
     const int npad = (k_max + 31) & ~31;
-    const int g8 = 2 * ((d + 7) >> 3), d8 = 4 * g8;
-    if (npad > 256) return 0;
-    int cols = kTcGroups * (npad + 2 * d8), tmem_cols = 32;
+    const int g16 = 2 * ((d + 15) >> 4), acols = 4 * g16;
+    if (2 * npad > 256) return 0;   // the widest product has npad + N <= 2 * npad columns
+    int G = kTcMaxGroups;   // as many consumer groups as tensor memory holds (each: accumulator + xh + xl)
+    while (G > 2 && G * (2 * npad + 2 * acols) > 512) --G;
+    if (const char* e = getenv("DPR_TC_GROUPS")) {   // tuning aid
+        const int want = atoi(e);
+        if (want >= 2 && want < G) G = want;
+    }
+    int cols = G * (2 * npad + 2 * acols), tmem_cols = 32;
     while (tmem_cols < cols) tmem_cols <<= 1;
     if (tmem_cols > 512) return 0;
-    const size_t stage_bytes = (((size_t)g8 * kGroupFloats * 4) + 127) & ~(size_t)127;
+    const size_t stage_bytes = (((size_t)(tile_groups(d) + (tile_groups(d) & 1)) * kGroupFloats * 4) + 127) & ~(size_t)127;   // the tile (+ one zero group when its group count is odd)
     const size_t bars = 256;
     const size_t hdr_bytes = (sizeof(CentreHeader) + 127) & ~(size_t)127;
     const size_t cc_bytes = (size_t)npad * 4, orig_bytes = (size_t)npad * 4;
     const size_t scratch = (((size_t)(2 * k_max + 2) * 4 + 64) + 127) & ~(size_t)127;
-    const size_t b_bytes = (size_t)2 * g8 * npad * 16;
-    const size_t fixed = bars + hdr_bytes + cc_bytes + orig_bytes + scratch * kTcWarps + b_bytes;
+    const size_t b_bytes = (size_t)g16 * 2 * npad * 16;
+    const size_t fixed = bars + hdr_bytes + cc_bytes + orig_bytes + scratch * 4 * G + b_bytes;
     if (fixed + 3 * stage_bytes > (size_t)kSmemBudget) return 0;
     int S = (int)(((size_t)kSmemBudget - fixed) / stage_bytes);
     if (S > kTcMaxStages) S = kTcMaxStages;
     plan->d = d;
-    plan->g8 = g8;
+    plan->groups = G;
+    plan->debug_terms = getenv("DPR_TC_DEBUG_TERMS") ? atoi(getenv("DPR_TC_DEBUG_TERMS")) : 0;
+    plan->g8 = g16;
+    plan->wait_hint = getenv("DPR_TC_HINT") ? atoi(getenv("DPR_TC_HINT")) : 2000;
     plan->npad = npad;
     plan->tmem_cols = tmem_cols;
     plan->stages = S;
@@ -450,18 +553,21 @@ int plan_tc_pass(int d, int k_max, TcPlan* plan) {
     plan->off_orig = plan->off_cc + (int)cc_bytes;
     plan->off_scratch = plan->off_orig + (int)orig_bytes;
     plan->scratch_bytes = (int)scratch;
-    plan->off_b = plan->off_scratch + (int)(scratch * kTcWarps);
+    plan->off_b = plan->off_scratch + (int)(scratch * 4 * G);
     plan->off_stages = plan->off_b + (int)b_bytes;
     plan->smem_bytes = (size_t)plan->off_stages + (size_t)S * stage_bytes;
-    plan->table_floats = (size_t)npad + (size_t)2 * g8 * npad * 4;
+    plan->table_floats = (size_t)npad + b_bytes / 4;
     return 1;
 }
 
 int launch_tc_pass(const TcPlan& plan, const PassParams& P, int grid, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        DPR_CUDA(cudaFuncSetAttribute(tc_pass_kernel<kPassAssign>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-        DPR_CUDA(cudaFuncSetAttribute(tc_pass_kernel<kPassLloyd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+#define DPR_TC_ATTR(G)                                                                                                            \
+    DPR_CUDA(cudaFuncSetAttribute(tc_pass_kernel<kPassAssign, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); \
+    DPR_CUDA(cudaFuncSetAttribute(tc_pass_kernel<kPassLloyd, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        DPR_TC_ATTR(2) DPR_TC_ATTR(3) DPR_TC_ATTR(4)
+#undef DPR_TC_ATTR
         configured = true;
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -470,8 +576,14 @@ int launch_tc_pass(const TcPlan& plan, const PassParams& P, int grid, cudaStream
         DPR_CUDA(cudaEventCreate(&e1));
         DPR_CUDA(cudaEventRecord(e0, stream));
     }
-    if (P.mode == kPassAssign) tc_pass_kernel<kPassAssign><<<grid, kTcThreads, plan.smem_bytes, stream>>>(P, plan);
-    else tc_pass_kernel<kPassLloyd><<<grid, kTcThreads, plan.smem_bytes, stream>>>(P, plan);
+    const int threads = (4 * plan.groups + 2) * 32;
+#define DPR_TC_LAUNCH(G)                                                                                                   \
+    if (plan.groups == G) {                                                                                                \
+        if (P.mode == kPassAssign) tc_pass_kernel<kPassAssign, G><<<grid, threads, plan.smem_bytes, stream>>>(P, plan);     \
+        else tc_pass_kernel<kPassLloyd, G><<<grid, threads, plan.smem_bytes, stream>>>(P, plan);                            \
+    }
+    DPR_TC_LAUNCH(2) DPR_TC_LAUNCH(3) DPR_TC_LAUNCH(4)
+#undef DPR_TC_LAUNCH
     count_launch();
     if (e0) {
         DPR_CUDA(cudaEventRecord(e1, stream));

@@ -50,6 +50,17 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_
 // element (row, k) of a K-major no-swizzle operand: 8 rows x 4 elements (16 B) per core matrix
 __host__ __device__ inline int op_index(int row, int k, int lbo_floats) { return (k >> 2) * lbo_floats + (row >> 3) * 32 + (row & 7) * 4 + (k & 3); }
 
+// number of batches committed before `variant` in the throughput section (parity of the mbarrier)
+__device__ __forceinline__ int variant_count_done(int variant, int N) {
+    int c = 0;
+    for (int v = 0; v < variant; ++v) {
+        const int Nv = v < 2 ? N : (v < 4 ? 2 * N : 4 * N);
+        if (Nv > 256) continue;
+        ++c;
+    }
+    return c;
+}
+
 // mode bit 0: A from shared memory instead of TMEM;  bit 1: feed raw x instead of masked xh
 __global__ void __launch_bounds__(128, 1) probe(const float* __restrict__ x, const float* __restrict__ c, int d, int N, int mode, float* out, long long* clk) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -164,6 +175,43 @@ __global__ void __launch_bounds__(128, 1) probe(const float* __restrict__ x, con
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- throughput of back-to-back products issued from uniform registers: variants of (A source, N)
+    if (warp == 0 && mode == 0) {
+        for (int variant = 0; variant < 6; ++variant) {
+            const bool ss = variant & 1;
+            const int Nv = variant < 2 ? N : (variant < 4 ? 2 * N : 4 * N);
+            if (Nv > 256) continue;
+            const uint32_t idv = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nv >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+            const uint64_t bd0 = make_desc(smem_u32(bh), b_lbo * 4, 128), ad0 = make_desc(smem_u32(ah), a_lbo * 4, 128);
+            const long long t0 = clock64();
+            uint32_t pred = 0;
+            asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred) : "r"(0xffffffffu));
+            if (pred) {
+                for (int rep = 0; rep < 8; ++rep)
+                    for (int s = 0; s < d8 / 8; ++s) {
+                        if (ss) mma_ss(tmem + acc_col, ad0 + (uint64_t)s * ((2 * a_lbo * 4) >> 4), bd0, idv, 1);
+                        else mma_ts(tmem + acc_col, tmem + ah_col + 8 * s, bd0, idv, 1);
+                    }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            }
+            __syncwarp();
+            const long long t1 = clock64();
+            {
+                uint32_t done = 0;
+                const uint32_t par = (uint32_t)((variant_count_done(variant, N) + 1) & 1);
+                while (!done)
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)), "r"(par) : "memory");
+            }
+            const long long t2 = clock64();
+            if (tid == 0) {
+                clk[4 + 2 * variant] = t1 - t0;
+                clk[5 + 2 * variant] = t2 - t0;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
 }
 
@@ -178,7 +226,8 @@ int main() {
         for (auto& v : c) v = (float)((rand() / (double)RAND_MAX - 0.5) * 6.0);
         float *dx, *dc, *dout;
         long long* dclk;
-        CK(cudaMalloc(&dclk, 64));
+        CK(cudaMalloc(&dclk, 256));
+        CK(cudaMemset(dclk, 0, 256));
         CK(cudaMalloc(&dx, x.size() * 4));
         CK(cudaMalloc(&dc, c.size() * 4));
         CK(cudaMalloc(&dout, (size_t)M * N * 4));
@@ -195,6 +244,13 @@ int main() {
             long long hclk[3];
             CK(cudaMemcpy(hclk, dclk, 24, cudaMemcpyDeviceToHost));
             printf("   cycles: split+st %lld, issue %lld, issue..done %lld\n", hclk[0], hclk[1], hclk[2]);
+            if (mode == 0) {
+                long long h2[16];
+                CK(cudaMemcpy(h2, dclk, 128, cudaMemcpyDeviceToHost));
+                const char* names[6] = {"TS N", "SS N", "TS 2N", "SS 2N", "TS 4N", "SS 4N"};
+                for (int v = 0; v < 6; ++v)
+                    if (h2[5 + 2 * v]) printf("   %d products %s: issue %lld cycles, done %lld cycles (%.1f per product)\n", 8 * (d8 / 8), names[v], h2[4 + 2 * v], h2[5 + 2 * v], (double)h2[5 + 2 * v] / (8 * (d8 / 8)));
+            }
             if (mode >= 4) continue;
             res[mode].resize((size_t)M * N);
             CK(cudaMemcpy(res[mode].data(), dout, (size_t)M * N * 4, cudaMemcpyDeviceToHost));

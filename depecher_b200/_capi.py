@@ -113,6 +113,12 @@ class Engine:
     def synchronize(self) -> None:
         self._chk(self.lib.dpr_synchronize())
 
+    def recheck_count(self, reset: bool = True) -> int:
+        """Cells decided by the exact fp64 path since the last reset (diagnostics)."""
+        out = C.c_int64(0)
+        self._chk(self.lib.dpr_recheck_count(C.byref(out), C.c_int32(1 if reset else 0)))
+        return out.value
+
     def set_pass_kernel(self, which: int) -> None:
         """0 = automatic (tensor-core pass when the shape fits), 1 = always the FFMA pass."""
         self._chk(self.lib.dpr_set_pass_kernel(C.c_int32(which)))

@@ -347,6 +347,18 @@ int dpr_synchronize(void) {
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));
     return DPR_OK;
 }
+int dpr_recheck_count(int64_t* out, int32_t reset) {
+    DPR_TRY(ensure_ready());
+    if (!out) return fail(DPR_ERR_INVALID, "recheck_count: null output");
+    unsigned long long v = 0;
+    if (ctx().d_recheck) {
+        DPR_CUDA(cudaMemcpyAsync(&v, ctx().d_recheck, sizeof(v), cudaMemcpyDeviceToHost, ctx().stream));
+        if (reset) DPR_CUDA(cudaMemsetAsync(ctx().d_recheck, 0, sizeof(v), ctx().stream));
+        DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
+    *out = (int64_t)v;
+    return DPR_OK;
+}
 int dpr_set_pass_kernel(int32_t which) {
     if (which != DPR_PASS_AUTO && which != DPR_PASS_FFMA) return fail(DPR_ERR_INVALID, "unknown pass kernel");
     ctx().force_ffma = which == DPR_PASS_FFMA;

@@ -109,6 +109,7 @@ struct Context {
     cudaStream_t own_stream = nullptr;
     int ari_mode = DPR_ARI_EXACT;
     int64_t launches = 0;
+    unsigned long long* d_recheck = nullptr;   // cells decided by the exact fp64 path since the last reset (diagnostics)
     bool force_ffma = false;             // diagnostics: keep the tensor-core pass off (dpr_set_pass_kernel)
     int32_t* pinned_word = nullptr;      // pinned host word the Lloyd loop polls the active-problem count through
     // optional per-launch timing of the fused pass (dpr_pass_timing)

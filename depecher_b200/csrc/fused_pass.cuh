@@ -40,6 +40,8 @@ struct TcPlan {
     int32_t tmem_cols;      // allocation: groups x (accumulator 2*npad + xh 4*g8 + xl 4*g8 columns), power of two
     int32_t stages, stage_floats;
     int32_t off_hdr, off_cc, off_orig, off_scratch, scratch_bytes, off_b, off_stages;
+    int32_t mu_in_smem, off_mu;   // fp64 centres in shared memory for the exact re-decisions
+    int32_t gtab, gtab_bytes, glist_bytes, off_gtab, off_glist;   // Lloyd tables of the consumer groups in shared memory (gtab = 0: per-warp tables in global memory)
     size_t smem_bytes;
     size_t table_floats;    // floats of Problem::tc_table
 };

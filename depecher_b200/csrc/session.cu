@@ -96,7 +96,11 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
     for (int c = 0; c <= grid; ++c) start[c] = (int32_t)((int64_t)total_tiles_ * c / grid);
     DPR_TRY(alloc(&d_cta_start_, (size_t)grid + 1, false));
     DPR_CUDA(cudaMemcpyAsync(d_cta_start_, start.data(), sizeof(int32_t) * (grid + 1), cudaMemcpyHostToDevice, ctx().stream));
-    DPR_TRY(alloc(&d_recheck, (size_t)1, true));
+    if (!ctx().d_recheck) {   // one process-wide diagnostics counter (dpr_recheck_count)
+        DPR_CUDA(cudaMalloc(&ctx().d_recheck, sizeof(unsigned long long)));
+        DPR_CUDA(cudaMemsetAsync(ctx().d_recheck, 0, sizeof(unsigned long long), ctx().stream));
+    }
+    d_recheck = ctx().d_recheck;
     n_seg = std::min(16, grid);
     seg_entries = (int64_t)k_max_ * d + k_max_ + 1;
     if (want_sums) {

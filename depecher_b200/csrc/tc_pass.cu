@@ -141,6 +141,40 @@ __device__ __forceinline__ void split_tile(const float4* __restrict__ st4, int s
     }
 }
 
+// Lloyd full mode, one tile: warp w of the group takes the labels w, w + 4, ...; it finds a label's cells by ballot over the
+// labels the four warps published and adds their rows in cell order, lane = marker.  `lb` is double-buffered by the caller
+// (a warp can be one tile ahead of a slow neighbour at most).
+__device__ __noinline__ void full_tile_sums(const float* __restrict__ slot, unsigned char* lb, double* gsum, long long* gcnt, int d, int k,
+                                            int grp, int wq, int lane, int mycell_in_tile, int lab) {
+    lb[mycell_in_tile] = (unsigned char)(lab >= 0 ? lab : 255);
+    asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+    const int l0 = lb[lane], l1 = lb[32 + lane], l2 = lb[64 + lane], l3 = lb[96 + lane];
+    for (int jb = 0; jb < d; jb += 64) {
+        const int j0 = jb + lane, j1 = jb + 32 + lane;
+        const float* r0 = slot + x_slot_index(0, j0 < d ? j0 : 0);
+        const float* r1 = slot + x_slot_index(0, j1 < d ? j1 : 0);
+        for (int L = wq; L < k; L += 4) {
+            unsigned m[4] = {__ballot_sync(0xffffffffu, l0 == L), __ballot_sync(0xffffffffu, l1 == L), __ballot_sync(0xffffffffu, l2 == L),
+                             __ballot_sync(0xffffffffu, l3 == L)};
+            if (!(m[0] | m[1] | m[2] | m[3])) continue;
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                unsigned mm = m[q];
+                while (mm) {
+                    const int c = 32 * q + __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    a0 += (double)r0[4 * c];
+                    a1 += (double)r1[4 * c];
+                }
+            }
+            if (j0 < d) gsum[L * d + j0] += a0;
+            if (j1 < d) gsum[L * d + j1] += a1;
+            if (jb == 0 && lane == 0) gcnt[L] += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
@@ -164,6 +198,12 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
     int32_t* orig = reinterpret_cast<int32_t*>(smem + T.off_orig);
     float* bmat = reinterpret_cast<float*>(smem + T.off_b);
     float* stages = reinterpret_cast<float*>(smem + T.off_stages);
+    double* mu_s = reinterpret_cast<double*>(smem + T.off_mu);   // the problem's exact centres, for the fp64 re-decisions (when they fit)
+    // Lloyd tables of a consumer group (when they fit): sums[k_max * d] doubles, counts[k_max], and the per-tile hand-over area
+    const int gwarp = (threadIdx.x >> 5) >> 2;   // group of this warp (consumer warps only)
+    double* gsum = reinterpret_cast<double*>(smem + T.off_gtab + (size_t)gwarp * T.gtab_bytes);
+    long long* gcnt = reinterpret_cast<long long*>(gsum + P.part_stride);
+    unsigned char* glab = smem + T.off_glist + (size_t)gwarp * T.glist_bytes;   // [2][128] labels of a whole tile (full mode hand-over)
     const int d = T.d, groups = tile_groups(d), g16 = T.g8;   // g16: groups of 8 markers, whole K=16 steps
     const size_t tile_fl = tile_floats(d);
     const uint32_t tile_bytes = (uint32_t)(tile_fl * 4);
@@ -186,6 +226,8 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)), "r"((uint32_t)T.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    if (T.gtab)
+        for (int i = threadIdx.x; i < (int)(T.gtab_bytes / 8) * kTcGroups; i += blockDim.x) reinterpret_cast<double*>(smem + T.off_gtab)[i] = 0.0;
     if (groups & 1)   // the split reads marker groups in pairs: the partner of an odd last group is never written by a copy — zero, once
         for (int s = 0; s < S; ++s)
             for (int i = threadIdx.x; i < kGroupFloats; i += blockDim.x) stages[(size_t)s * T.stage_floats + (size_t)groups * kGroupFloats + i] = 0.f;
@@ -296,9 +338,9 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
     }
 
 #ifdef DPR_TC_PROFILE
-    long long prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, prof_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long prof_n = 0;
-#define DPR_PROF(i) do { prof_t[i] = clock64(); if (i > 0) prof_acc[i] += prof_t[i] - prof_t[i - 1]; if (i == 7) ++prof_n; } while (0)
+#define DPR_PROF(i) do { prof_t[i] = clock64(); if (i > 0) prof_acc[i] += prof_t[i] - prof_t[i - 1]; if (i == 8) ++prof_n; } while (0)
 #else
 #define DPR_PROF(i)
 #endif
@@ -327,11 +369,14 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                 cc_s[i] = pr.tc_table[i];
                 orig[i] = pr.tc_orig[i];
             }
+            if (T.mu_in_smem)
+                for (int i = threadIdx.x; i < pr.k * d; i += kTcWarps * 32) mu_s[i] = pr.mu[i];
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the B operand was written through the generic proxy
         consumer_barrier<kTcWarps * 32>();
         if (threadIdx.x == 0) mbar_arrive(tables_ready);
         const int N = hdr->tc_n, n_act = hdr->k_act;
+        const double* mu_exact = T.mu_in_smem ? mu_s : pr.mu;
         const bool trivial = hdr->trivial != 0, force_exact = hdr->force_exact != 0;
         // error bound of a score (see the header comment): fp16 splits 3 * 2^-22 and fp32 accumulation 2^-22 per product
         // step, both relative to sum|x_j c_j| <= (||x||^2 + ||c||^2) / 2 and doubled by the factor -2; the sum of the two
@@ -418,7 +463,7 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                 while (redo) {   // the whole warp re-decides each doubtful cell in fp64
                     const int src = __ffs(redo) - 1;
                     redo &= redo - 1;
-                    const int v = exact_label_warp(slot, wq * 32 + src, d, pr.mu, orig, n_act, lane);
+                    const int v = exact_label_warp(slot, wq * 32 + src, d, mu_exact, orig, n_act, lane);
                     if (lane == src) lab = v;
                 }
             }
@@ -427,7 +472,12 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
             const bool ch = lab >= 0 && lab != oldl;
             if (P.compare_old) changed += (int)ch;
             if (pr.labels && live) pr.labels[mycell] = lab;
-            if (MODE == kPassLloyd) {
+            DPR_PROF(7);
+            if (MODE == kPassLloyd && T.gtab && !delta) {
+                // every cell contributes: the four warps of the group publish their labels, meet at the group's barrier, and update
+                // the group's table in shared memory with plain read-modify-writes in a fixed order (no atomics, reproducible)
+                full_tile_sums(slot, glab + (k_mine & 1u) * 128, gsum, gcnt, d, pr.k, grp, wq, lane, mycell_in_tile, lab);
+            } else if (MODE == kPassLloyd) {
                 const unsigned mch = __ballot_sync(0xffffffffu, ch);
                 if (delta && __popc(mch) <= 8) {
                     unsigned m = mch;
@@ -451,7 +501,7 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
             tc_fence_before();   // this warp's tcgen05.ld of the accumulator are complete before the next products overwrite it
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
-            DPR_PROF(7);
+            DPR_PROF(8);
         }
         it += (uint32_t)count;
         // ---- combine the warps' tables of this (CTA, problem) in fixed order; reset them for the next range
@@ -480,17 +530,29 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                             if (v[w] != 0.0) __stcg(P.warp_sums + (wbase + w) * stride + e, 0.0);
                         }
                     }
+                    if (T.gtab)
+                        for (int g = 0; g < kTcGroups; ++g) {
+                            double* t = reinterpret_cast<double*>(smem + T.off_gtab + (size_t)g * T.gtab_bytes) + e;
+                            acc += *t;
+                            *t = 0.0;
+                        }
                 } else if (e < stride + P.k_max) {
+                    long long t = 0;
                     if (P.warp_counts) {
-                        long long t = 0;
 #pragma unroll
                         for (int w = 0; w < kTcWarps; ++w) {
                             const long long v = __ldcg(P.warp_counts + (wbase + w) * P.k_max + (e - stride));
                             t += v;
                             if (v != 0) __stcg(P.warp_counts + (wbase + w) * P.k_max + (e - stride), 0LL);
                         }
-                        acc = (double)t;
                     }
+                    if (T.gtab)
+                        for (int g = 0; g < kTcGroups; ++g) {
+                            long long* c = reinterpret_cast<long long*>(reinterpret_cast<double*>(smem + T.off_gtab + (size_t)g * T.gtab_bytes) + stride) + (e - stride);
+                            t += *c;
+                            *c = 0;
+                        }
+                    acc = (double)t;
                 } else {
                     long long t = 0;
                     for (int w = 0; w < kTcWarps; ++w) t += s_changed[w];
@@ -504,8 +566,8 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
     }
 #ifdef DPR_TC_PROFILE
     if (blockIdx.x == 3 && lane == 0 && (warp & 3) == 0)
-        printf("warp %d tiles %lld: wait_full %lld split %lld wait_mma %lld tmem_ld %lld argmin %lld recheck %lld store+release %lld\n", warp, prof_n, prof_acc[1] / prof_n, prof_acc[2] / prof_n,
-               prof_acc[3] / prof_n, prof_acc[4] / prof_n, prof_acc[5] / prof_n, prof_acc[6] / prof_n, prof_acc[7] / prof_n);
+        printf("warp %d tiles %lld: wait_full %lld split %lld wait_mma %lld tmem_ld %lld argmin %lld recheck %lld store %lld sums+release %lld\n", warp, prof_n, prof_acc[1] / prof_n, prof_acc[2] / prof_n,
+               prof_acc[3] / prof_n, prof_acc[4] / prof_n, prof_acc[5] / prof_n, prof_acc[6] / prof_n, prof_acc[7] / prof_n, prof_acc[8] / prof_n);
 #endif
     tc_fence_before();
     consumer_barrier<kTcWarps * 32>();
@@ -535,8 +597,19 @@ int plan_tc_pass(int d, int k_max, TcPlan* plan) {
     const size_t cc_bytes = (size_t)npad * 4, orig_bytes = (size_t)npad * 4;
     const size_t scratch = (((size_t)(2 * k_max + 2) * 4 + 64) + 127) & ~(size_t)127;
     const size_t b_bytes = (size_t)g16 * 2 * npad * 16;
-    const size_t fixed = bars + hdr_bytes + cc_bytes + orig_bytes + scratch * 4 * G + b_bytes;
+    size_t fixed = bars + hdr_bytes + cc_bytes + orig_bytes + scratch * 4 * G + b_bytes;
     if (fixed + 3 * stage_bytes > (size_t)kSmemBudget) return 0;
+    // the exact centres next to the tables when they are small
+    const size_t mu_bytes = (((size_t)k_max * d * 8) + 127) & ~(size_t)127;
+    const bool mu_in_smem = mu_bytes <= 32 * 1024 && fixed + mu_bytes + 4 * stage_bytes <= (size_t)kSmemBudget;
+    const size_t off_mu = fixed;
+    if (mu_in_smem) fixed += mu_bytes;
+    // Lloyd tables of the consumer groups in shared memory, when at least 4 stages remain
+    const size_t gtab_bytes = (((size_t)k_max * d + k_max) * 8 + 127) & ~(size_t)127;
+    const size_t glist_bytes = 256;   // [2][128] labels
+    const bool gtab = k_max <= 255 && fixed + (gtab_bytes + glist_bytes) * G + 4 * stage_bytes <= (size_t)kSmemBudget && !getenv("DPR_TC_NO_GTAB");
+    const size_t off_gtab = fixed;
+    if (gtab) fixed += (gtab_bytes + glist_bytes) * G;
     int S = (int)(((size_t)kSmemBudget - fixed) / stage_bytes);
     if (S > kTcMaxStages) S = kTcMaxStages;
     plan->d = d;
@@ -554,7 +627,14 @@ int plan_tc_pass(int d, int k_max, TcPlan* plan) {
     plan->off_scratch = plan->off_orig + (int)orig_bytes;
     plan->scratch_bytes = (int)scratch;
     plan->off_b = plan->off_scratch + (int)(scratch * 4 * G);
-    plan->off_stages = plan->off_b + (int)b_bytes;
+    plan->mu_in_smem = mu_in_smem ? 1 : 0;
+    plan->off_mu = (int)off_mu;
+    plan->gtab = gtab ? 1 : 0;
+    plan->gtab_bytes = (int)gtab_bytes;
+    plan->glist_bytes = (int)glist_bytes;
+    plan->off_gtab = (int)off_gtab;
+    plan->off_glist = (int)(off_gtab + gtab_bytes * G);
+    plan->off_stages = (int)fixed;
     plan->smem_bytes = (size_t)plan->off_stages + (size_t)S * stage_bytes;
     plan->table_floats = (size_t)npad + b_bytes / 4;
     return 1;

@@ -54,6 +54,9 @@ int dpr_set_ari_mode(int32_t mode);      /* DPR_ARI_EXACT (default) | DPR_ARI_MO
 /* which kernel runs the pass over the cells: DPR_PASS_AUTO (default: the tcgen05 tensor-core pass when the shape fits
  * tensor memory, else the FFMA pass) | DPR_PASS_FFMA (always the FFMA pass; A/B measurements and tests).  Both give
  * the same labels. */
+/* diagnostics: cells whose label was decided by the exact fp64 path (two best fp32 scores closer than the error bound)
+ * since the last reset */
+int dpr_recheck_count(int64_t* out, int32_t reset);
 #define DPR_PASS_AUTO 0
 #define DPR_PASS_FFMA 1
 int dpr_set_pass_kernel(int32_t which);

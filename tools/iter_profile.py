@@ -16,7 +16,9 @@ eng.lloyd_iterations(ds, mu0, reg, True, -1, 3)
 prev = 0.0
 for it in range(1, 26):
     eng.pass_timing(True)
+    eng.recheck_count(True)
     mu, ch = eng.lloyd_iterations(ds, mu0, reg, True, -1, it)
     ms, cnt = eng.pass_timing(False)
-    print(f"iterations 0..{it-1}: pass total {ms:7.3f} ms  -> iteration {it-1}: {ms - prev:6.3f} ms   changed {ch:9d} ({100.0*ch/n:5.2f} %)  alive {int((np.abs(mu).sum(1)>0).sum())}", flush=True)
+    rc = eng.recheck_count(True)
+    print(f"iterations 0..{it-1}: pass total {ms:7.3f} ms  -> iteration {it-1}: {ms - prev:6.3f} ms   changed {ch:9d} ({100.0*ch/n:5.2f} %)  alive {int((np.abs(mu).sum(1)>0).sum())}  exact rechecks (all {it} iterations) {rc}", flush=True)
     prev = ms

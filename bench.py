@@ -12,8 +12,8 @@ soft-threshold centre update (allocate_clusters + reevaluate_centers, /root/refe
   e2e       the same metric through the drop-in C-ABI call dpr_sparse_k_means() with HOST double buffers:
             H2D of the R-layout matrix, k-means++ seeding, the whole Lloyd loop and the D2H of the labels
             are inside the timed region
-  roofline  fused_pass_kernel: algorithmic bytes (4*D + 8 per cell: the fp32 row, the previous label read
-            and the new label written) / mean launch duration, against the measured HBM copy bandwidth
+  roofline  tc_pass_kernel (the tcgen05 pass over the cells): algorithmic bytes (4*D + 8 per cell: the fp32 row, the
+            previous label read and the new label written) / mean launch duration, against the measured HBM copy bandwidth
   cpu_baseline  the reference's own Clusterer.cpp (oracle/_ref; the oracle port when absent) timed on a
             bounded sample on the host cores, one single-threaded engine per worker like the reference's
             SOCK workers (R/depeche.R:169-174)
@@ -243,7 +243,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         fma_per_launch = float(n_local) * k_eff * D
         traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` capture
         try:
-            for ln in open(os.path.join(ROOT, "profiles", "r01_fused_pass_bench_ncu.csv")):
+            for ln in open(os.path.join(ROOT, "profiles", "r01_tc_pass_bench_ncu.csv")):
                 f = ln.strip().split(",")
                 if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[1]]
@@ -251,10 +251,10 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         except Exception:
             traffic = None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "peak_source": which, "kernel": "fused_pass_kernel", "launch_ms": launch_ms, "launches_timed": pass_cnt,
-                    "fp32_fma_per_s": fma_per_launch / (launch_ms * 1e-3), "fp32_fma_peak_measured": 33.4e12,
-                    "fp32_frac": fma_per_launch / (launch_ms * 1e-3) / 33.4e12,
-                    "note": "K=30, D=40 needs 7.5 flop/B: the FP32 pipe (33.4 TFMA/s measured, profiles/microbench) bounds this shape before HBM does"}
+                    "peak_source": which, "kernel": "tc_pass_kernel", "launch_ms": launch_ms, "launches_timed": pass_cnt,
+                    "fma_per_s": fma_per_launch / (launch_ms * 1e-3),
+                    "note": "distance products on tcgen05 (fp16-split operands, fp32 accumulate, exact fp64 re-decision of near ties); the launches timed "
+                            "include the full-sums first iteration and the iterations in which 1-6 % of the cells change cluster"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -17,7 +17,7 @@ namespace dpr {
 // Active rows: no_zero -> rows with any non-zero coefficient (isZero(0), Clusterer.cpp:41-45; NaN counts as
 // non-zero); otherwise every row, except that all-zero rows after the first are dropped: they are identical,
 // and the reference's first-minimum rule (minCoeff, :64) can only ever pick the first of them.
-__device__ void build_centre_table(const Problem& pr, int no_zero, int table_cap) {
+__device__ void build_centre_table(const Problem& pr, const double* __restrict__ mu, int no_zero, int table_cap) {   // mu: pr.mu or a shared-memory copy of it
     constexpr int kMaxRows = kMaxKC * kMaxChunks;
     __shared__ int s_act[kMaxRows];
     __shared__ double s_cc[kMaxRows];
@@ -32,7 +32,7 @@ __device__ void build_centre_table(const Problem& pr, int no_zero, int table_cap
         bool zero = true, bad = false;
         double s = 0.0;
         for (int t = 0; t < d; ++t) {
-            const double v = pr.mu[(size_t)c * d + t];
+            const double v = mu[(size_t)c * d + t];
             if (!(fabs(v) <= 0.0)) zero = false;
             if (!isfinite(v)) bad = true;
             s += v * v;
@@ -101,7 +101,7 @@ __device__ void build_centre_table(const Problem& pr, int no_zero, int table_cap
         }
         for (int e = threadIdx.x; e < kcp * 4 * tile_groups(d); e += blockDim.x) {
             const int j = e / kcp, t = e % kcp;
-            w[e] = (t < real && j < d) ? (float)(-2.0 * pr.mu[(size_t)s_act[real_before + t] * d + j]) : 0.f;
+            w[e] = (t < real && j < d) ? (float)(-2.0 * mu[(size_t)s_act[real_before + t] * d + j]) : 0.f;
         }
         real_before += real;
     }
@@ -149,7 +149,7 @@ __device__ void build_centre_table(const Problem& pr, int no_zero, int table_cap
         }
         for (int e = threadIdx.x; e < g16 * npad * 8; e += blockDim.x) {
             const int g = e / (npad * 8), row = (e % (npad * 8)) >> 3, j = 8 * g + (e & 7);
-            const float v = (row < n && j < d) ? (float)(-2.0 * pr.mu[(size_t)s_act[row] * d + j]) * sc : 0.f;
+            const float v = (row < n && j < d) ? (float)(-2.0 * mu[(size_t)s_act[row] * d + j]) * sc : 0.f;
             const __half hi = __float2half_rn(v);
             const __half lo = __float2half_rn(v - __half2float(hi));
             const size_t at = (size_t)g * (16 * npad) + (size_t)row * 8 + (e & 7);   // in halves
@@ -161,7 +161,7 @@ __device__ void build_centre_table(const Problem& pr, int no_zero, int table_cap
 
 __global__ void prepare_centres_kernel(Problem* problems, int table_cap) {
     const Problem pr = problems[blockIdx.x];
-    build_centre_table(pr, pr.no_zero, table_cap);
+    build_centre_table(pr, pr.mu, pr.no_zero, table_cap);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -170,8 +170,9 @@ __global__ void prepare_centres_kernel(Problem* problems, int table_cap) {
 // entry layout: [k_max*d sums][k_max counts][1 changed]
 // ---------------------------------------------------------------------------------------------------
 __global__ void reduce_partials_kernel(const Problem* problems, const int32_t* cta_tile_start, int grid_ctas, int k_max, int d,
-                                       const double* cta_tables, double* seg_out, int n_seg) {
+                                       const double* cta_tables, double* seg_out, int n_seg, int32_t* n_active_out) {
     const int p = blockIdx.x, seg = blockIdx.y;
+    if (n_active_out && p == 0 && seg == 0 && threadIdx.x == 0) *n_active_out = 0;   // finalize counts the problems still running
     const Problem pr = problems[p];
     const int64_t entries = (int64_t)k_max * d + k_max + 1;
     double* out = seg_out + ((int64_t)p * n_seg + seg) * entries;
@@ -193,7 +194,7 @@ __global__ void reduce_partials_kernel(const Problem* problems, const int32_t* c
 // finalize: one CTA per problem.  iter = index i of the assignment that just ran.
 // ---------------------------------------------------------------------------------------------------
 __global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_seg, int k_max, int iter, int max_iter, int table_cap,
-                                int allow_delta, int32_t* n_active_out) {
+                                int allow_delta, int32_t* n_active_out, int mu_in_smem) {
     const int p = blockIdx.x;
     Problem pr = problems[p];
     if (pr.done) return;
@@ -202,6 +203,7 @@ __global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_s
     const int64_t entries = stride + k_max + 1;
     const double* in = seg_in + (int64_t)p * n_seg * entries;
     __shared__ long long s_changed;
+    extern __shared__ double s_mu[];   // the new centres, when they fit (mu_in_smem): later phases read them here instead of through L2
     // totals in fixed segment order
     for (int64_t e = threadIdx.x; e < entries; e += blockDim.x) {
         double acc = 0.0;
@@ -242,11 +244,13 @@ __global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_s
         const double lo = (S - reg_i / 2) / nn;
         const double hi = (S + reg_i / 2) / nn;
         const double m0 = lo > 0.0 ? lo : 0.0;  // _mm_max_pd(lo, 0): second operand when lo is NaN
-        pr.mu[e] = hi < m0 ? hi : m0;           // _mm_min_pd(hi, m0)
+        const double m = hi < m0 ? hi : m0;     // _mm_min_pd(hi, m0)
+        pr.mu[e] = m;
+        if (mu_in_smem) s_mu[e] = m;
     }
     __threadfence_block();
     __syncthreads();
-    build_centre_table(pr, pr.no_zero, table_cap);
+    build_centre_table(pr, mu_in_smem ? s_mu : pr.mu, pr.no_zero, table_cap);
     if (threadIdx.x == 0 && n_active_out && !(iter + 1 >= max_iter)) atomicAdd(n_active_out, 1);
 }
 
@@ -303,17 +307,25 @@ int launch_prepare_centres(Problem* d_problems, int n_problems, int table_cap, c
 }
 
 int launch_reduce_partials(const Problem* d_problems, int n_problems, const int32_t* cta_tile_start, int grid_ctas, int k_max, int d,
-                           const double* cta_tables, double* seg_out, int n_seg, cudaStream_t st) {
+                           const double* cta_tables, double* seg_out, int n_seg, int32_t* n_active_out, cudaStream_t st) {
     dim3 g(n_problems, n_seg);
-    reduce_partials_kernel<<<g, 256, 0, st>>>(d_problems, cta_tile_start, grid_ctas, k_max, d, cta_tables, seg_out, n_seg);
+    reduce_partials_kernel<<<g, 256, 0, st>>>(d_problems, cta_tile_start, grid_ctas, k_max, d, cta_tables, seg_out, n_seg, n_active_out);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
 }
 
-int launch_finalize(Problem* d_problems, int n_problems, const double* seg_in, int n_seg, int k_max, int iter, int max_iter,
+int launch_finalize(Problem* d_problems, int n_problems, const double* seg_in, int n_seg, int k_max, int d, int iter, int max_iter,
                     int table_cap, int allow_delta, int32_t* n_active_out, cudaStream_t st) {
-    finalize_kernel<<<n_problems, 256, 0, st>>>(d_problems, seg_in, n_seg, k_max, iter, max_iter, table_cap, allow_delta, n_active_out);
+    const size_t mu_bytes = (size_t)k_max * d * sizeof(double);
+    const int mu_in_smem = mu_bytes <= 64 * 1024;
+    static bool configured = false;
+    if (!configured) {
+        DPR_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        configured = true;
+    }
+    finalize_kernel<<<n_problems, 512, mu_in_smem ? mu_bytes : 0, st>>>(d_problems, seg_in, n_seg, k_max, iter, max_iter, table_cap, allow_delta, n_active_out,
+                                                                        mu_in_smem);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;

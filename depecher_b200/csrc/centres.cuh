@@ -5,8 +5,8 @@
 namespace dpr {
 int launch_prepare_centres(Problem* d_problems, int n_problems, int table_cap, cudaStream_t st);
 int launch_reduce_partials(const Problem* d_problems, int n_problems, const int32_t* cta_tile_start, int grid_ctas, int k_max, int d,
-                           const double* cta_tables, double* seg_out, int n_seg, cudaStream_t st);
-int launch_finalize(Problem* d_problems, int n_problems, const double* seg_in, int n_seg, int k_max, int iter, int max_iter,
+                           const double* cta_tables, double* seg_out, int n_seg, int32_t* n_active_out, cudaStream_t st);
+int launch_finalize(Problem* d_problems, int n_problems, const double* seg_in, int n_seg, int k_max, int d, int iter, int max_iter,
                     int table_cap, int allow_delta, int32_t* n_active_out, cudaStream_t st);
 int launch_partition(const Problem* d_problems, int n_problems, int grid_ctas, int total_tiles, int32_t* cta_tile_start, cudaStream_t st);
 int launch_soft_threshold(const double* sums, const long long* counts, int k, int d, double reg, double* mu, cudaStream_t st);

@@ -153,10 +153,9 @@ int Session::pass(int mode, bool compare_old) {
 }
 
 int Session::reduce_and_finalize(int iter, int max_iter) {
-    DPR_TRY(launch_reduce_partials(d_problems, n_problems(), d_cta_start_, grid, k_max_, d_, cta_tables_, seg, n_seg, ctx().stream));
+    DPR_TRY(launch_reduce_partials(d_problems, n_problems(), d_cta_start_, grid, k_max_, d_, cta_tables_, seg, n_seg, d_n_active_, ctx().stream));
     if (ctx().world > 1) DPR_TRY(comm_allreduce_sum_f64(seg, (size_t)n_problems() * n_seg * seg_entries));
-    DPR_CUDA(cudaMemsetAsync(d_n_active_, 0, sizeof(int32_t), ctx().stream));
-    return launch_finalize(d_problems, n_problems(), seg, n_seg, k_max_, iter, max_iter, plan.table_floats_cap, allow_delta ? 1 : 0, d_n_active_,
+    return launch_finalize(d_problems, n_problems(), seg, n_seg, k_max_, d_, iter, max_iter, plan.table_floats_cap, allow_delta ? 1 : 0, d_n_active_,
                            ctx().stream);
 }
 

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_pass_kernel(const PassParam
                     while (redo) {   // the whole warp re-decides each doubtful cell in fp64
                         const int src = __ffs(redo) - 1;
                         redo &= redo - 1;
-                        const int v = exact_label_warp(slot, src + 32 * r, d, pr.mu, orig, n_slots, lane);
+                        const int v = exact_label_warp(slot, src + 32 * r, d, pr.mu, d, orig, n_slots, lane);
                         if (lane == src) lab[r] = v;
                     }
                 }

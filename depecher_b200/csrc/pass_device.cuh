@@ -57,15 +57,15 @@ __device__ __forceinline__ float pack_idx(float s, int idx) {
 // takes active slots a, a+32, ...; the (distance, slot) pairs are then reduced lexicographically, which is
 // the sequential first-minimum scan (a NaN distance is never chosen unless it is the first one, like there).
 // ---------------------------------------------------------------------------------------------------
-static __device__ __noinline__ int exact_label_warp(const float* __restrict__ slot, int cell, int d, const double* __restrict__ mu,
-                                             const int32_t* __restrict__ orig, int n_slots, int lane) {
+static __device__ __noinline__ int exact_label_warp(const float* __restrict__ slot, int cell, int d, const double* __restrict__ mu, int ld,
+                                                    const int32_t* __restrict__ orig, int n_slots, int lane) {   // ld: doubles between rows of mu
     double bv = INFINITY;
     int bi = 0x7fffffff;
     bool first_nan = false;
     for (int a = lane; a < n_slots; a += 32) {
         const int row = orig[a];
         if (row < 0) continue;
-        const double* m = mu + (size_t)row * d;
+        const double* m = mu + (size_t)row * ld;
         double s = 0.0;
         for (int t = 0; t < d; ++t) {
             const double diff = __dadd_rn(-(double)slot[x_slot_index(cell, t)], m[t]);

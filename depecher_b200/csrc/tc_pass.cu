@@ -106,6 +106,8 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uin
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// index of a column inside its 16-column block, in the 4 low mantissa bits of the score
+__device__ __forceinline__ float pack_idx4(float s, int idx) { return __uint_as_float((__float_as_uint(s) & 0xFFFFFFF0u) | (unsigned)idx); }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&w)[4]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
 }
@@ -370,20 +372,21 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                 orig[i] = pr.tc_orig[i];
             }
             if (T.mu_in_smem)
-                for (int i = threadIdx.x; i < pr.k * d; i += kTcWarps * 32) mu_s[i] = pr.mu[i];
+                for (int i = threadIdx.x; i < pr.k * d; i += kTcWarps * 32) mu_s[(i / d) * (d | 1) + i % d] = pr.mu[i];   // odd row stride: lanes = rows hit different banks
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the B operand was written through the generic proxy
         consumer_barrier<kTcWarps * 32>();
         if (threadIdx.x == 0) mbar_arrive(tables_ready);
         const int N = hdr->tc_n, n_act = hdr->k_act;
         const double* mu_exact = T.mu_in_smem ? mu_s : pr.mu;
+        const int mu_ld = T.mu_in_smem ? (d | 1) : d;
         const bool trivial = hdr->trivial != 0, force_exact = hdr->force_exact != 0;
         // error bound of a score (see the header comment): fp16 splits 3 * 2^-22 and fp32 accumulation 2^-22 per product
         // step, both relative to sum|x_j c_j| <= (||x||^2 + ||c||^2) / 2 and doubled by the factor -2; the sum of the two
         // accumulator halves, the unscaling fma and cc 4 * 2^-24; twice that for a difference of two scores, plus the
-        // 5 masked index bits (2 * 2^-18); the absolute part of the split error comes through tc_abs1 / tc_abs2
+        // 4 masked index bits (2 * 2^-19); the absolute part of the split error comes through tc_abs1 / tc_abs2
         const float eps = 3.f * 2.3841858e-7f + (float)(g16 + 1) * 2.3841858e-7f + 4.f * 5.9604645e-8f;
-        const float tau_c = 2.f * eps + 7.6293945e-6f;
+        const float tau_c = 2.f * eps + 3.8146973e-6f;
         const float scale_x = hdr->tc_scale_x, unscale = hdr->tc_unscale, abs1 = hdr->tc_abs1, abs2 = hdr->tc_abs2;
         const float cc2 = 2.0f * hdr->cc_max;
         const bool delta = MODE == kPassLloyd && pr.delta;
@@ -436,14 +439,13 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                     DPR_PROF(4);
                     const float prev = best;
                     const float4* cc4 = reinterpret_cast<const float4*>(cc_s + n0);
-                    const int i0 = n0 & 16;   // index inside the 32-column block
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float4 c = cc4[q];
-                        const float s0 = pack_idx(fmaf(unscale, __uint_as_float(v[4 * q + 0]) + __uint_as_float(v[16 + 4 * q + 0]), c.x), i0 + 4 * q + 0);
-                        const float s1 = pack_idx(fmaf(unscale, __uint_as_float(v[4 * q + 1]) + __uint_as_float(v[16 + 4 * q + 1]), c.y), i0 + 4 * q + 1);
-                        const float s2 = pack_idx(fmaf(unscale, __uint_as_float(v[4 * q + 2]) + __uint_as_float(v[16 + 4 * q + 2]), c.z), i0 + 4 * q + 2);
-                        const float s3 = pack_idx(fmaf(unscale, __uint_as_float(v[4 * q + 3]) + __uint_as_float(v[16 + 4 * q + 3]), c.w), i0 + 4 * q + 3);
+                        const float s0 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * q + 0]) + __uint_as_float(v[16 + 4 * q + 0]), c.x), 4 * q + 0);
+                        const float s1 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * q + 1]) + __uint_as_float(v[16 + 4 * q + 1]), c.y), 4 * q + 1);
+                        const float s2 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * q + 2]) + __uint_as_float(v[16 + 4 * q + 2]), c.z), 4 * q + 2);
+                        const float s3 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * q + 3]) + __uint_as_float(v[16 + 4 * q + 3]), c.w), 4 * q + 3);
                         const float lo0 = fminf(s0, s1), hi0 = fmaxf(s0, s1);
                         second = fmin3(fmaxf(best, lo0), second, hi0);
                         best = fminf(best, lo0);
@@ -451,10 +453,10 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                         second = fmin3(fmaxf(best, lo1), second, hi1);
                         best = fminf(best, lo1);
                     }
-                    if (best < prev) bchunk = n0 & ~31;
+                    if (best < prev) bchunk = n0;
                 }
                 const float tau = tau_c * (xx_tile + cc2) + (abs1 * sqrtf(xx_tile) + abs2) + 1e-30f;
-                const int a = bchunk + (int)(__float_as_uint(best) & 31u);
+                const int a = bchunk + (int)(__float_as_uint(best) & 15u);
                 const bool sure = (second - best > tau) && !force_exact;
                 lab = orig[a < n_act ? a : 0];
                 DPR_PROF(5);
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                 while (redo) {   // the whole warp re-decides each doubtful cell in fp64
                     const int src = __ffs(redo) - 1;
                     redo &= redo - 1;
-                    const int v = exact_label_warp(slot, wq * 32 + src, d, mu_exact, orig, n_act, lane);
+                    const int v = exact_label_warp(slot, wq * 32 + src, d, mu_exact, mu_ld, orig, n_act, lane);
                     if (lane == src) lab = v;
                 }
             }
@@ -600,7 +602,7 @@ int plan_tc_pass(int d, int k_max, TcPlan* plan) {
     size_t fixed = bars + hdr_bytes + cc_bytes + orig_bytes + scratch * 4 * G + b_bytes;
     if (fixed + 3 * stage_bytes > (size_t)kSmemBudget) return 0;
     // the exact centres next to the tables when they are small
-    const size_t mu_bytes = (((size_t)k_max * d * 8) + 127) & ~(size_t)127;
+    const size_t mu_bytes = (((size_t)k_max * (d | 1) * 8) + 127) & ~(size_t)127;
     const bool mu_in_smem = mu_bytes <= 32 * 1024 && fixed + mu_bytes + 4 * stage_bytes <= (size_t)kSmemBudget;
     const size_t off_mu = fixed;
     if (mu_in_smem) fixed += mu_bytes;

@@ -278,3 +278,59 @@ def test_random_shapes_fuzz(engine, oracle):
             b = oracle.find_centers_from(Xu, mu0, reg, True)
             assert a["n_iter"] == b["n_iter"] and np.array_equal(a["i"], b["i"]), f"trial {trial}: trajectories differ"
             centres_close(a["c"], b["c"])
+
+
+# ---------------------------------------------------------------------------------------------- the two pass kernels
+@pytest.mark.parametrize("n,d,k", [(5000, 40, 30), (3001, 15, 20), (2500, 50, 31), (4000, 8, 100), (1000, 3, 2), (6000, 64, 16)])
+def test_tensor_core_pass_and_ffma_pass_agree(engine, oracle, n, d, k):
+    """the tcgen05 pass (default where the shape fits tensor memory) and the FP32-pipe pass give the oracle's labels, the same
+    Lloyd trajectory and centres equal to ~1e-12 (both accumulate in fp64, in different but fixed orders)"""
+    rng = np.random.default_rng(n + 13 * d + k)
+    X = blobs(rng, n, d, 6, amp=2.5)
+    mu = X[rng.choice(n, k, replace=False)].copy()
+    reg = 4.0 * n * np.sqrt(d) / 1450.0
+    want = oracle.allocate_points(X, mu, True)
+    out = {}
+    try:
+        for which in (0, 1):   # DPR_PASS_AUTO, DPR_PASS_FFMA
+            engine.set_pass_kernel(which)
+            assert np.array_equal(engine.allocate_points(X, mu, True)["i"], want)
+            out[which] = engine.find_centers_from(X, mu, reg, True)
+    finally:
+        engine.set_pass_kernel(0)
+    assert out[0]["n_iter"] == out[1]["n_iter"]
+    assert np.array_equal(out[0]["i"], out[1]["i"])
+    np.testing.assert_allclose(out[0]["c"], out[1]["c"], rtol=1e-10, atol=1e-12)
+    b = oracle.find_centers_from(X, mu, reg, True)
+    assert out[0]["n_iter"] == b["n_iter"] and np.array_equal(out[0]["i"], b["i"])
+    centres_close(out[0]["c"], b["c"])
+
+
+@pytest.mark.parametrize("scale", [2.0 ** -40, 2.0 ** -12, 3.0e-3, 1.0, 777.0, 2.0 ** 15, 2.0 ** 40])
+def test_tensor_core_pass_scales(engine, oracle, scale):
+    """cells and centres far outside fp16's range: the power-of-two scaling in front of the fp16 split keeps labels bit-exact;
+    a few cells far from the bulk (tiles whose norm bound is tiny next to the matrix maximum) exercise the absolute error term"""
+    rng = np.random.default_rng(int(np.log2(scale) * 7) + 1000)
+    n, d, k = 4000, 24, 12
+    X = blobs(rng, n, d, 5)
+    X[:130] *= 1e-3          # a whole tile of tiny cells
+    X[rng.integers(0, n, 4)] *= 60.0
+    X = (X * scale).astype(np.float32).astype(np.float64)
+    mu = X[rng.choice(n, k, replace=False)].copy()
+    mu[0] = 0.0
+    for nz in (False, True):
+        got = engine.allocate_points(X, mu, nz)["i"]
+        want = oracle.allocate_points(X, mu, nz)
+        assert np.array_equal(got, want), f"scale {scale}: {(got != want).sum()} labels differ"
+
+
+def test_recheck_counter(engine):
+    rng = np.random.default_rng(5)
+    X = blobs(rng, 3000, 10, 4)
+    mu = X[:6].copy()
+    mu[3] = mu[2]            # duplicate centre: every cell nearest to it is an exact tie -> decided by the fp64 path
+    engine.recheck_count(True)
+    engine.allocate_points(X, mu, False)
+    first = engine.recheck_count(True)
+    assert first > 0
+    assert engine.recheck_count(True) == 0

@@ -1,28 +1,26 @@
-// fused_pass.cu — the hot kernel: nearest-centre assignment fused with the per-cluster sums/counts.
+// fused_pass.cu — the pass over the cells on the FP32 pipe: nearest-centre assignment fused with the per-cluster
+// sums/counts.  The tensor-core pass (tc_pass.cu) takes the shapes that fit tensor memory; this kernel serves the
+// others (more than 128 active centres, very wide tiles), the sums of given labels (kPassSums), and A/B measurements.
 //
 // Replaces Clusterer::allocate_clusters (/root/reference/src/Clusterer.cpp:34-87) and the scatter-add
 // half of Clusterer::reevaluate_centers (:99-102) with ONE pass over the cells.
 //
-// Shape of the work:
-//   * X lives in HBM as fp32 in tile-major order (common.cuh: x_index): the d marker rows of 64 consecutive
-//     cells are contiguous and pre-swizzled, so a warp fills its "slot" (64 cells x d markers of shared
-//     memory) with ONE bulk-async copy (TMA, cp.async.bulk + mbarrier complete_tx) of d * 256 bytes;
-//     16 warps per SM keep 16 slots (up to 3 per warp when d is small) in flight or in use.
-//   * Distance micro-kernel: each lane holds 2 cells x up to 32 centres = 64 fp32 accumulators as
-//     packed pairs and issues FFMA2 (fma.rn.f32x2): s_k = ||c_k||^2 - 2 x.c_k.  One LDS.64 brings the
-//     lane's 2 cells of a marker, one broadcast LDS.128 brings 4 centres.  (Measured on B200: packed
-//     FFMA2 with >= 32-wide centre tiles reaches 88-98 % of the FP32 pipe, scalar FFMA or narrower tiles
-//     lose 10-30 %: profiles/microbench/r01_pipes_b200.log.)
+//   * X lives in HBM as fp32 tiles of 128 cells (common.cuh: x_index): a warp fills its "slot" (one tile in shared
+//     memory) with ONE bulk-async copy (TMA, cp.async.bulk + mbarrier complete_tx); 8 warps per SM.
+//   * Distance micro-kernel: each lane holds 4 cells (lane, lane+32, lane+64, lane+96) x up to 32 centres = 128
+//     fp32 accumulators as packed pairs and issues FFMA2 (fma.rn.f32x2): s_k = ||c_k||^2 - 2 x.c_k.  One LDS.64
+//     brings two markers of a cell, one broadcast LDS.128 brings 4 centres.  (Measured on B200: packed FFMA2 with
+//     >= 32-wide centre tiles reaches 88-98 % of the FP32 pipe, scalar FFMA or narrower tiles lose 10-30 %:
+//     profiles/microbench/r01_pipes_b200.log.)
 //   * Argmin in registers with the centre index packed into the 5 low mantissa bits (FMNMX/FMNMX3);
 //     cells whose two best fp32 scores are closer than a proven error bound are re-decided in fp64 exactly
 //     as the reference does (sqrt of the left-to-right sum, strict <), so labels are bit-exact for
 //     fp32-representable data.
-//   * Lloyd mode: the warp counting-sorts its contributions by label (match.any, no atomics), then lanes
-//     switch to marker ownership and add each label's run in fp64 registers before one read-modify-write
-//     of the warp's PRIVATE table.  Full mode contributes every cell (+x to its label); delta mode only
-//     the cells whose label changed (+x to the new, -x to the old label), which after the first few
-//     iterations is a fraction of a percent of the cells.  Fixed tile->warp map + private tables + fixed
-//     combine order => bit-reproducible sums.
+//   * Lloyd mode: the warp counting-sorts its contributions by label (match.any), then lanes switch to marker
+//     ownership, add each label's run in fp64 registers and issue one fp64 reduction per (label, marker) into the
+//     warp's PRIVATE table.  Full mode contributes every cell (+x to its label); delta mode only the cells whose
+//     label changed (+x to the new, -x to the old label).  Fixed tile->warp map + private tables (one lane per
+//     address, program order) + fixed combine order => bit-reproducible sums.
 #include "common.cuh"
 #include "fused_pass.cuh"
 #include "pass_device.cuh"

@@ -5,19 +5,25 @@
 // and the scatter-add half of Clusterer::reevaluate_centers, :99-102) for the shapes that fit tensor memory; the
 // distance step  s_k = ||c_k||^2 - 2 x.c_k  becomes D[128 cells x N centres] = X * (-2 C)^T on tcgen05.mma.
 //
-//   * A tile of 128 cells lands in shared memory with ONE bulk-async copy (TMA) — the resident layout in HBM is
-//     already the K-major canonical operand layout (common.cuh).  A producer warp keeps a ring of tiles in flight.
-//   * fp32 accuracy from tf32 products: x = xh + xl, -2c = ch + cl with the high parts the tf32 truncations
-//     (kind::tf32 ignores the low 13 mantissa bits, so the raw fp32 word serves as xh).  Each of the four consumer
-//     warps owns 32 cells = 32 TMEM lanes: a thread reads its cell's markers (LDS.128), computes xl, and parks xh and
-//     xl in tensor memory (tcgen05.st) as the A operands.  One thread then issues xl*ch + xh*cl + xh*ch
-//     (3 * ceil(d/8) tcgen05.mma, A from TMEM, B from shared memory) into a double-buffered TMEM accumulator.
-//     Measured (profiles/microbench/tc_probe.cu): |error| <= 1e-6 * sum|x_j c_j|, the same order as an fp32 FMA chain.
-//   * While the tensor core works on tile i, the consumer warps run the epilogue of tile i-1: tcgen05.ld brings a
-//     thread its cell's N scores, the two smallest are kept with the centre index packed into the 5 low mantissa
-//     bits, and a cell whose two best scores are closer than the error bound is re-decided in fp64 exactly as the
-//     reference does — labels stay bit-exact.  Lloyd mode then adds the cell to the warp's private fp64 tables
-//     (pass_device.cuh), exactly like the FFMA kernel.
+//   * A tile of 128 cells lands in shared memory with ONE bulk-async copy (TMA): the resident layout in HBM is the
+//     K-major canonical operand layout (common.cuh).  A producer warp keeps a ring of tiles in flight.
+//   * fp32 accuracy from fp16 products: cells and centres are scaled by powers of two into fp16's range, then split
+//     v = hi + lo with both parts fp16 (|v - hi - lo| <= 2^-22 |v| + 2^-25).  A consumer thread owns one cell = one
+//     TMEM lane: it reads the cell's markers (LDS.128), splits them and parks xh, xl in tensor memory (tcgen05.st)
+//     as A operands.  The centre table (centres.cu) stacks the high parts on top of the low parts in ONE B operand,
+//     so the issuer warp needs two products per K=16 step: xh*[ch|cl] and xl*ch, accumulated in fp32 in TMEM.
+//     Measured (profiles/microbench/tc_probe.cu): |error| <= 1e-6 * sum|x_j c_j|, the order of an fp32 FMA chain.
+//   * G = 2..4 consumer groups of four warps (as many as tensor memory holds) take the CTA's tiles round-robin: while
+//     one group waits for its products the others split or reduce.  tcgen05.ld brings a thread its cell's scores;
+//     the two smallest are kept with the centre index packed into the 4 low mantissa bits, and a cell whose two
+//     best scores are closer than the error bound is re-decided in fp64 exactly as the reference does — labels stay
+//     bit-exact.  Lloyd mode then adds the cell to fp64 tables in a fixed order (group tables in shared memory for
+//     the full-sums first iteration, per-warp tables in global memory for the later delta iterations).
+//   * Single-thread instructions (tcgen05.mma, cp.async.bulk) are issued under elect.sync from converged warps so
+//     that their operands stay in uniform registers.
+//
+// Build with -DDPR_TC_PROFILE to print per-phase cycle counts of one CTA (how the numbers in profiles/ were taken);
+// the environment variable DPR_TC_GROUPS (2..4) overrides the number of consumer groups (tuning aid).
 #include "common.cuh"
 #include "fused_pass.cuh"
 #include "pass_device.cuh"
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                     const uint32_t acc = tmem + g * buf_cols, ah = acc + (uint32_t)(2 * npad), al = ah + (uint32_t)acols;
                     for (int s = 0; s < g16 / 2; ++s) {
                         umma_f16_ts(acc, ah + 8 * s, desc_b0 + s * desc_step, idesc_hi, s > 0 ? 1u : 0u);
-                        if (T.debug_terms != 1) umma_f16_ts(acc, al + 8 * s, desc_b0 + s * desc_step, idesc_lo, 1);
+                        umma_f16_ts(acc, al + 8 * s, desc_b0 + s * desc_step, idesc_lo, 1);
                     }
                     umma_commit(&mma_done[g]);
                 }
@@ -609,16 +615,15 @@ int plan_tc_pass(int d, int k_max, TcPlan* plan) {
     // Lloyd tables of the consumer groups in shared memory, when at least 4 stages remain
     const size_t gtab_bytes = (((size_t)k_max * d + k_max) * 8 + 127) & ~(size_t)127;
     const size_t glist_bytes = 256;   // [2][128] labels
-    const bool gtab = k_max <= 255 && fixed + (gtab_bytes + glist_bytes) * G + 4 * stage_bytes <= (size_t)kSmemBudget && !getenv("DPR_TC_NO_GTAB");
+    const bool gtab = k_max <= 255 && fixed + (gtab_bytes + glist_bytes) * G + 4 * stage_bytes <= (size_t)kSmemBudget;
     const size_t off_gtab = fixed;
     if (gtab) fixed += (gtab_bytes + glist_bytes) * G;
     int S = (int)(((size_t)kSmemBudget - fixed) / stage_bytes);
     if (S > kTcMaxStages) S = kTcMaxStages;
     plan->d = d;
     plan->groups = G;
-    plan->debug_terms = getenv("DPR_TC_DEBUG_TERMS") ? atoi(getenv("DPR_TC_DEBUG_TERMS")) : 0;
     plan->g8 = g16;
-    plan->wait_hint = getenv("DPR_TC_HINT") ? atoi(getenv("DPR_TC_HINT")) : 2000;
+    plan->wait_hint = 2000;
     plan->npad = npad;
     plan->tmem_cols = tmem_cols;
     plan->stages = S;

@@ -208,10 +208,6 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
     float* stages = reinterpret_cast<float*>(smem + T.off_stages);
     double* mu_s = reinterpret_cast<double*>(smem + T.off_mu);   // the problem's exact centres, for the fp64 re-decisions (when they fit)
     // Lloyd tables of a consumer group (when they fit): sums[k_max * d] doubles, counts[k_max], and the per-tile hand-over area
-    const int gwarp = (threadIdx.x >> 5) >> 2;   // group of this warp (consumer warps only)
-    double* gsum = reinterpret_cast<double*>(smem + T.off_gtab + (size_t)gwarp * T.gtab_bytes);
-    long long* gcnt = reinterpret_cast<long long*>(gsum + P.part_stride);
-    unsigned char* glab = smem + T.off_glist + (size_t)gwarp * T.glist_bytes;   // [2][128] labels of a whole tile (full mode hand-over)
     const int d = T.d, groups = tile_groups(d), g16 = T.g8;   // g16: groups of 8 markers, whole K=16 steps
     const size_t tile_fl = tile_floats(d);
     const uint32_t tile_bytes = (uint32_t)(tile_fl * 4);
@@ -327,11 +323,6 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
 
     // ================================ consumer warps ================================
     const int grp = warp >> 2, wq = warp & 3;   // group, and the TMEM lane quarter this warp may touch
-    int* wscr = reinterpret_cast<int*>(smem + T.off_scratch + (size_t)warp * T.scratch_bytes);
-    unsigned char* perm = reinterpret_cast<unsigned char*>(wscr + 2 * P.k_max + 2);
-    const size_t wtab = (size_t)blockIdx.x * kTcWarps + warp;
-    double* my_sums = P.warp_sums ? P.warp_sums + wtab * P.part_stride : nullptr;
-    long long* my_counts = P.warp_counts ? P.warp_counts + wtab * P.k_max : nullptr;
     const int mycell_in_tile = wq * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)grp * buf_cols;
     const uint32_t a_hi = lane_base + (uint32_t)(2 * npad), a_lo = a_hi + (uint32_t)acols;
@@ -397,7 +388,7 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
         const float cc2 = 2.0f * hdr->cc_max;
         const bool delta = MODE == kPassLloyd && pr.delta;
         const bool need_old = (P.compare_old || delta) && pr.labels;
-        long long changed = 0;
+        int changed = 0;   // per thread: at most one per tile
         const int count = p_end - tile;
 
         // this group's tiles of the range: j with (it + j) % G == grp
@@ -484,10 +475,20 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
             if (MODE == kPassLloyd && T.gtab && !delta) {
                 // every cell contributes: the four warps of the group publish their labels, meet at the group's barrier, and update
                 // the group's table in shared memory with plain read-modify-writes in a fixed order (no atomics, reproducible)
-                full_tile_sums(slot, glab + (k_mine & 1u) * 128, gsum, gcnt, d, pr.k, grp, wq, lane, mycell_in_tile, lab);
+                double* gsum = reinterpret_cast<double*>(smem + T.off_gtab + (size_t)grp * T.gtab_bytes);   // this group's table
+                unsigned char* glab = smem + T.off_glist + (size_t)grp * T.glist_bytes;                        // [2][128] labels of a whole tile
+                full_tile_sums(slot, glab + (k_mine & 1u) * 128, gsum, reinterpret_cast<long long*>(gsum + P.part_stride), d, pr.k, grp, wq, lane,
+                               mycell_in_tile, lab);
             } else if (MODE == kPassLloyd) {
                 const unsigned mch = __ballot_sync(0xffffffffu, ch);
-                if (delta && __popc(mch) <= 8) {
+                // this warp's private tables (global, L2-resident) and sort scratch: addresses formed only when a cell moved
+                const size_t wtab = (size_t)blockIdx.x * kTcWarps + warp;
+                double* my_sums = P.warp_sums + wtab * P.part_stride;
+                long long* my_counts = P.warp_counts + wtab * P.k_max;
+                int* wscr = reinterpret_cast<int*>(smem + T.off_scratch + (size_t)warp * T.scratch_bytes);
+                unsigned char* perm = reinterpret_cast<unsigned char*>(wscr + 2 * P.k_max + 2);
+                if (!mch && delta) {
+                } else if (delta && __popc(mch) <= 8) {
                     unsigned m = mch;
                     while (m) {
                         const int src = __ffs(m) - 1;
@@ -515,11 +516,11 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
         // ---- combine the warps' tables of this (CTA, problem) in fixed order; reset them for the next range
         if (P.cta_tables) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
+            for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);   // <= 32 * tiles of the range: fits an int
             long long* s_changed = reinterpret_cast<long long*>(smem + T.off_cc);   // the centre tables are no longer needed ...
             __threadfence();   // the warps' table updates are visible to the whole CTA
             consumer_barrier<kTcWarps * 32>();   // ... once every warp is past its last tile
-            if (lane == 0) s_changed[warp] = changed;
+            if (lane == 0) s_changed[warp] = (long long)changed;
             consumer_barrier<kTcWarps * 32>();
             const int64_t stride = P.part_stride;
             const int64_t entries = stride + P.k_max + 1;

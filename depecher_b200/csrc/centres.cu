@@ -178,14 +178,32 @@ __global__ void reduce_partials_kernel(const Problem* problems, const int32_t* c
     double* out = seg_out + ((int64_t)p * n_seg + seg) * entries;
     const int c0 = (int)((int64_t)grid_ctas * seg / n_seg), c1 = (int)((int64_t)grid_ctas * (seg + 1) / n_seg);
     const int t0 = pr.first_tile, t1 = pr.first_tile + pr.n_tiles;
+    // the CTAs of this segment whose tile range touches the problem are consecutive: [ca, cb)
+    int ca = c1, cb = c0;
+    if (!pr.done)
+        for (int c = c0; c < c1; ++c) {
+            const int a = cta_tile_start[c], b = cta_tile_start[c + 1];
+            if (a >= t1 || b <= t0 || a >= b) continue;
+            ca = min(ca, c);
+            cb = max(cb, c + 1);
+        }
     for (int64_t e = threadIdx.x; e < entries; e += blockDim.x) {
         double acc = 0.0;
-        if (!pr.done)
-            for (int c = c0; c < c1; ++c) {
-                const int a = cta_tile_start[c], b = cta_tile_start[c + 1];
-                if (a >= t1 || b <= t0 || a >= b) continue;
-                acc += cta_tables[(size_t)(c + p) * entries + e];
+        for (int c = ca; c < cb; c += 8) {   // 8 loads in flight, then the fixed-order sum
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int cc = c + q;
+                bool use = cc < cb;
+                if (use) {
+                    const int a = cta_tile_start[cc], b = cta_tile_start[cc + 1];
+                    use = !(a >= t1 || b <= t0 || a >= b);
+                }
+                v[q] = use ? cta_tables[(size_t)(cc + p) * entries + e] : 0.0;
             }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc += v[q];
+        }
         out[e] = acc;
     }
 }
@@ -207,7 +225,13 @@ __global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_s
     // totals in fixed segment order
     for (int64_t e = threadIdx.x; e < entries; e += blockDim.x) {
         double acc = 0.0;
-        for (int s = 0; s < n_seg; ++s) acc += in[(int64_t)s * entries + e];
+        for (int s0 = 0; s0 < n_seg; s0 += 16) {   // all loads in flight, then the fixed-order sum
+            double v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = s0 + q < n_seg ? in[(int64_t)(s0 + q) * entries + e] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc += v[q];
+        }
         if (e < stride) {
             const int c = (int)(e / d), j = (int)(e % d);
             if (c < k) pr.sums[(size_t)c * d + j] = (pr.delta ? pr.sums[(size_t)c * d + j] : 0.0) + acc;

@@ -378,11 +378,14 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
         const double* mu_exact = T.mu_in_smem ? mu_s : pr.mu;
         const int mu_ld = T.mu_in_smem ? (d | 1) : d;
         const bool trivial = hdr->trivial != 0, force_exact = hdr->force_exact != 0;
-        // error bound of a score (see the header comment): fp16 splits 3 * 2^-22 and fp32 accumulation 2^-22 per product
-        // step, both relative to sum|x_j c_j| <= (||x||^2 + ||c||^2) / 2 and doubled by the factor -2; the sum of the two
-        // accumulator halves, the unscaling fma and cc 4 * 2^-24; twice that for a difference of two scores, plus the
-        // 4 masked index bits (2 * 2^-19); the absolute part of the split error comes through tc_abs1 / tc_abs2
-        const float eps = 3.f * 2.3841858e-7f + (float)(g16 + 1) * 2.3841858e-7f + 4.f * 5.9604645e-8f;
+        // error bound of a score: the fp16 splits leave at most 3 * 2^-22 (proved: |v - hi - lo| <= 2^-22 |v| for round-to-nearest
+        // parts, three cross terms); the fp32 accumulation inside the tensor core is allowed 2^-21 per product step — measured on
+        // this part at <= 2^-24 per step, also for same-sign terms where a truncating adder's bias would add up
+        // (profiles/microbench/tc_probe_f16.cu: total error <= 8e-7, an fp32 FMA chain gives 5.7e-7).  Both are relative to
+        // sum|x_j c_j| <= (||x||^2 + ||c||^2) / 2 and doubled by the factor -2.  The sum of the two accumulator halves, the
+        // un-scaling fma and cc add 4 * 2^-24; twice all that for a difference of two scores, plus the 4 masked index bits
+        // (2 * 2^-19); the absolute part of the split error (fp16 subnormals) comes through tc_abs1 / tc_abs2.
+        const float eps = 3.f * 2.3841858e-7f + (float)(g16 + 1) * 4.7683716e-7f + 4.f * 5.9604645e-8f;
         const float tau_c = 2.f * eps + 3.8146973e-6f;
         const float scale_x = hdr->tc_scale_x, unscale = hdr->tc_unscale, abs1 = hdr->tc_abs1, abs2 = hdr->tc_abs2;
         const float cc2 = 2.0f * hdr->cc_max;

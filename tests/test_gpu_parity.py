@@ -334,3 +334,18 @@ def test_recheck_counter(engine):
     first = engine.recheck_count(True)
     assert first > 0
     assert engine.recheck_count(True) == 0
+
+
+def test_lloyd_is_bit_reproducible(engine):
+    """the per-cluster sums are accumulated in fixed orders (group tables in shared memory, private per-warp tables updated by
+    reductions of one lane per address, fixed combine order): repeated fits give bitwise identical centres and labels"""
+    rng = np.random.default_rng(77)
+    n, d, k = 300_000, 40, 30
+    X = blobs(rng, n, d, 12, amp=2.0)
+    mu0 = X[rng.choice(n, k, replace=False)].copy()
+    reg = 2.0 * n * np.sqrt(d) / 1450.0
+    runs = [engine.find_centers_from(X, mu0, reg, True) for _ in range(3)]
+    for r in runs[1:]:
+        assert r["n_iter"] == runs[0]["n_iter"]
+        assert np.array_equal(r["i"], runs[0]["i"])
+        assert np.array_equal(r["c"].view(np.uint64), runs[0]["c"].view(np.uint64)), "centres differ bitwise between runs"

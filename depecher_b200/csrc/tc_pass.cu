@@ -149,6 +149,15 @@ __device__ __forceinline__ void split_tile(const float4* __restrict__ st4, int s
     }
 }
 
+// Lloyd full mode when the group tables do not fit in shared memory (large k * d): this warp's 32 cells into its private table in
+// global memory by counting sort (out of line: rare)
+__device__ __noinline__ void full_warp_sums(const float* __restrict__ slot, int d, int k, int lane, int lab, int mycell_in_tile, int* wscr,
+                                            unsigned char* perm, double* my_sums, long long* my_counts) {
+    const int key[1] = {lab >= 0 ? 2 * lab : -1};
+    const int cell[1] = {mycell_in_tile};
+    slot_contributions<1>(slot, key, cell, d, k, lane, wscr, perm, my_sums, my_counts);
+}
+
 // Lloyd full mode, one tile: warp w of the group takes the labels w, w + 4, ...; it finds a label's cells by ballot over the
 // labels the four warps published and adds their rows in cell order, lane = marker.  `lb` is double-buffered by the caller
 // (a warp can be one tile ahead of a slow neighbour at most).
@@ -490,24 +499,17 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                 long long* my_counts = P.warp_counts + wtab * P.k_max;
                 int* wscr = reinterpret_cast<int*>(smem + T.off_scratch + (size_t)warp * T.scratch_bytes);
                 unsigned char* perm = reinterpret_cast<unsigned char*>(wscr + 2 * P.k_max + 2);
-                if (!mch && delta) {
-                } else if (delta && __popc(mch) <= 8) {
+                if (delta) {
                     unsigned m = mch;
-                    while (m) {
+                    while (m) {   // +x to the new label's sums, -x to the old one's (fire-and-forget reductions)
                         const int src = __ffs(m) - 1;
                         m &= m - 1;
                         const int newL = __shfl_sync(0xffffffffu, lab, src);
                         const int oldL = __shfl_sync(0xffffffffu, oldl, src);
                         move_one(slot, d, lane, my_sums, my_counts, wq * 32 + src, newL, oldL);
                     }
-                } else if (delta) {
-                    const int key[2] = {ch ? 2 * lab : -1, ch ? 2 * oldl + 1 : -1};
-                    const int cell[2] = {mycell_in_tile, mycell_in_tile};
-                    slot_contributions<2>(slot, key, cell, d, pr.k, lane, wscr, perm, my_sums, my_counts);
                 } else {
-                    const int key[1] = {lab >= 0 ? 2 * lab : -1};
-                    const int cell[1] = {mycell_in_tile};
-                    slot_contributions<1>(slot, key, cell, d, pr.k, lane, wscr, perm, my_sums, my_counts);
+                    full_warp_sums(slot, d, pr.k, lane, lab, mycell_in_tile, wscr, perm, my_sums, my_counts);
                 }
             }
             tc_fence_before();   // this warp's tcgen05.ld of the accumulator are complete before the next products overwrite it

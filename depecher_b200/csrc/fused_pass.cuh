@@ -20,6 +20,12 @@ struct PassParams {
     long long* warp_counts;         // [grid * warps][k_max]
     double* cta_tables;             // [(grid + n_problems)][k_max*d + k_max + 1]: sums, counts, changed of each (CTA, problem)
     unsigned long long* recheck_count;  // diagnostics: cells decided by the fp64 path (nullable)
+    // tensor-core pass, delta iterations: every consumer warp appends the cells whose label changed to its own list
+    // (cell, new label | old label << 16), in tile order; delta_sums_kernel turns the lists into sum tables
+    uint2* move_lists;              // [grid * warps][move_cap]
+    int32_t* move_counts;           // [(grid + n_problems) * warps]: entries of each (CTA, problem, warp)
+    int64_t move_cap;               // entries per warp
+    int32_t* move_overflow;         // set when a list ran out of room (a sizing bug: the host fails loudly)
     // filled from the plan
     int32_t warps, slots_per_warp, slot_floats, off_hdr, off_table, off_orig, off_scratch, scratch_bytes, off_slots;
 };
@@ -47,6 +53,8 @@ struct TcPlan {
 // returns 1 when the shape fits the tensor-core pass (k_max <= 128, >= 2 consumer groups in the 512 TMEM columns, >= 3 stages)
 int plan_tc_pass(int d, int k_max, TcPlan* plan);
 int launch_tc_pass(const TcPlan& plan, const PassParams& P, int grid, cudaStream_t stream);
+// sums/counts of the moved cells recorded by a tensor-core Lloyd pass in delta mode (tc_pass.cu)
+int launch_delta_sums(const TcPlan& plan, const PassParams& P, int grid, cudaStream_t stream);
 
 // returns 1 and fills the plan when a d-marker slot per warp fits in shared memory, 0 otherwise
 int plan_pass(int d, int k_max, PassPlan* plan);

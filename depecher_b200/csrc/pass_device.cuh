@@ -67,7 +67,22 @@ static __device__ __noinline__ int exact_label_warp(const float* __restrict__ sl
         if (row < 0) continue;
         const double* m = mu + (size_t)row * ld;
         double s = 0.0;
-        for (int t = 0; t < d; ++t) {
+        int t = 0;
+        // four markers = one 16-byte group of the cell: the loads, differences and squares of a group are independent of one
+        // another and of the running sum, only the four additions into s form the (left-to-right) chain
+        const float4* x4 = reinterpret_cast<const float4*>(slot + cell * 4);
+#pragma unroll 2
+        for (; t + 4 <= d; t += 4) {
+            const float4 xv = x4[(t >> 2) * (kGroupFloats / 4)];
+            const double d0 = __dadd_rn(-(double)xv.x, m[t]), d1 = __dadd_rn(-(double)xv.y, m[t + 1]);
+            const double d2 = __dadd_rn(-(double)xv.z, m[t + 2]), d3 = __dadd_rn(-(double)xv.w, m[t + 3]);
+            const double q0 = __dmul_rn(d0, d0), q1 = __dmul_rn(d1, d1), q2 = __dmul_rn(d2, d2), q3 = __dmul_rn(d3, d3);
+            s = __dadd_rn(s, q0);
+            s = __dadd_rn(s, q1);
+            s = __dadd_rn(s, q2);
+            s = __dadd_rn(s, q3);
+        }
+        for (; t < d; ++t) {
             const double diff = __dadd_rn(-(double)slot[x_slot_index(cell, t)], m[t]);
             s = __dadd_rn(s, __dmul_rn(diff, diff));
         }

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 #include "comm.cuh"
 
@@ -110,6 +111,26 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
         DPR_TRY(alloc(&cta_tables_, (size_t)(grid + P) * seg_entries, true));
         DPR_TRY(alloc(&seg, (size_t)P * n_seg * seg_entries, true));
         DPR_TRY(alloc(&d_n_active_, (size_t)1, true));
+        if (use_tc) {
+            // lists of moved cells of the delta iterations: one per consumer warp, sized for "every cell of the warp's tiles moves".
+            // A warp sees at most ceil(tiles of a problem range / groups) tiles per (CTA, problem) range, 32 cells of each.
+            int64_t min_tiles = total_tiles_, max_n = 0;
+            for (const auto& pr : h_problems) {
+                min_tiles = std::min<int64_t>(min_tiles, pr.n_tiles);
+                max_n = std::max<int64_t>(max_n, pr.n);
+            }
+            const int64_t range_tiles = (total_tiles_ + grid - 1) / grid + 1;
+            const int64_t range_problems = std::min<int64_t>(P, range_tiles / std::max<int64_t>(min_tiles, 1) + 2);
+            move_cap_ = (range_tiles / tc_plan.groups + range_problems + 1) * 32;
+            if (max_n < (int64_t)1 << 32 && k_max_ <= 65535) {
+                const size_t lists = (size_t)grid * 4 * tc_plan.groups;
+                DPR_TRY(alloc(&move_lists_, lists * (size_t)move_cap_, false));
+                DPR_TRY(alloc(&move_counts_, (size_t)(grid + P) * 4 * tc_plan.groups, true));
+                DPR_TRY(alloc(&move_overflow_, (size_t)1, true));
+            } else {
+                allow_delta = false;   // cell indices would not fit the 32-bit list entries: every iteration sums all cells
+            }
+        }
         if (!ctx().pinned_word) DPR_CUDA(cudaMallocHost(&ctx().pinned_word, sizeof(int32_t)));   // kept for the life of the process
         h_n_active_ = ctx().pinned_word;
     }
@@ -148,7 +169,16 @@ int Session::pass(int mode, bool compare_old) {
     P.warp_counts = warp_counts_;
     P.cta_tables = cta_tables_;
     P.recheck_count = d_recheck;
-    if (use_tc && mode != kPassSums) return launch_tc_pass(tc_plan, P, grid, ctx().stream);
+    P.move_lists = move_lists_;
+    P.move_counts = move_counts_;
+    P.move_cap = move_cap_;
+    P.move_overflow = move_overflow_;
+    if (use_tc && mode != kPassSums) {
+        DPR_TRY(launch_tc_pass(tc_plan, P, grid, ctx().stream));
+        // delta iterations (every Lloyd pass of a fit but the first, where it finds nothing to do): the pass recorded the moved cells, this sums their rows
+        if (mode == kPassLloyd && move_lists_ && allow_delta) return launch_delta_sums(tc_plan, P, grid, ctx().stream);
+        return DPR_OK;
+    }
     return launch_fused_pass(plan, P, grid, ctx().stream);
 }
 
@@ -183,10 +213,20 @@ int Session::lloyd(int max_iter) {
             }
         }
     }
+    return check_lists();
+}
+
+int Session::check_lists() {
+    if (!move_overflow_) return DPR_OK;
+    int32_t flag = 0;
+    DPR_CUDA(cudaMemcpyAsync(&flag, move_overflow_, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx().stream));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (flag) return fail(DPR_ERR_STATE, "internal error: a moved-cell list of the delta iterations overflowed");
     return DPR_OK;
 }
 
 int Session::fetch_state() {
+    DPR_TRY(check_lists());
     DPR_CUDA(cudaMemcpyAsync(h_problems.data(), d_problems, sizeof(Problem) * h_problems.size(), cudaMemcpyDeviceToHost, ctx().stream));
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));
     return DPR_OK;

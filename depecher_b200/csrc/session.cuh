@@ -42,6 +42,7 @@ public:
     // find_centers loop (Clusterer.cpp:244-252) for all problems; labels must be zeroed by the caller
     int lloyd(int max_iter);
     int fetch_state();                                               // d_problems -> h_problems (synchronises)
+    int check_lists();                                               // fails when a moved-cell list overflowed (synchronises)
     int zero_labels();
 
     int n_problems() const { return (int)h_problems.size(); }
@@ -70,6 +71,10 @@ private:
     long long* warp_counts_ = nullptr;
     double* cta_tables_ = nullptr;
     int32_t* d_n_active_ = nullptr;
+    uint2* move_lists_ = nullptr;      // tensor-core pass, delta iterations: moved cells per consumer warp
+    int32_t* move_counts_ = nullptr;
+    int32_t* move_overflow_ = nullptr;
+    int64_t move_cap_ = 0;
     int32_t* h_n_active_ = nullptr;  // pinned
     template <typename T> int alloc(T** p, size_t count, bool zero);
 };

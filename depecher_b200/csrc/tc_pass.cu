@@ -30,6 +30,7 @@
 
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -353,6 +354,7 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
 #define DPR_PROF(i)
 #endif
     uint32_t it = 0;        // tiles this CTA has walked past (all groups)
+    uint32_t list_cursor = 0;   // entries this warp has appended to its list of moved cells (all problems of the CTA's range)
     int s_mine = grp % S;   // stage and landing parity of this group's next tile (its ordinal is grp, grp + G, ...)
     uint32_t par_mine = (uint32_t)(grp / S) & 1u;
     uint32_t k_mine = 0;    // tiles this group has taken
@@ -398,7 +400,8 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
         const float tau_c = 2.f * eps + 3.8146973e-6f;
         const float scale_x = hdr->tc_scale_x, unscale = hdr->tc_unscale, abs1 = hdr->tc_abs1, abs2 = hdr->tc_abs2;
         const float cc2 = 2.0f * hdr->cc_max;
-        const bool delta = MODE == kPassLloyd && pr.delta;
+        const bool delta = MODE == kPassLloyd && pr.delta;   // (a session that lets finalize set it has allocated the lists)
+        const uint32_t list_begin = list_cursor;
         const bool need_old = (P.compare_old || delta) && pr.labels;
         int changed = 0;   // per thread: at most one per tile
         const int count = p_end - tile;
@@ -491,26 +494,27 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                 unsigned char* glab = smem + T.off_glist + (size_t)grp * T.glist_bytes;                        // [2][128] labels of a whole tile
                 full_tile_sums(slot, glab + (k_mine & 1u) * 128, gsum, reinterpret_cast<long long*>(gsum + P.part_stride), d, pr.k, grp, wq, lane,
                                mycell_in_tile, lab);
-            } else if (MODE == kPassLloyd) {
+            } else if (MODE == kPassLloyd && delta) {
+                // only the cells whose label changed contribute (+x to the new label, -x to the old one): the warp appends them to
+                // its own list, in tile and lane order; delta_sums_kernel gathers their rows afterwards.  Nothing in this kernel
+                // waits on a moved cell.
                 const unsigned mch = __ballot_sync(0xffffffffu, ch);
-                // this warp's private tables (global, L2-resident) and sort scratch: addresses formed only when a cell moved
+                if (mch) {   // (addresses formed only here: nothing about the lists stays live across tiles but the cursor)
+                    const size_t wl = (size_t)blockIdx.x * kTcWarps + warp;
+                    uint2* my_list = P.move_lists + wl * P.move_cap;
+                    const uint32_t at = list_cursor + (uint32_t)__popc(mch & ((1u << lane) - 1u));
+                    if (ch) {
+                        if ((int64_t)at < P.move_cap) my_list[at] = make_uint2((uint32_t)mycell, (uint32_t)lab | ((uint32_t)oldl << 16));
+                        else *P.move_overflow = 1;
+                    }
+                    list_cursor += (uint32_t)__popc(mch);
+                }
+            } else if (MODE == kPassLloyd) {
+                // every cell contributes but the group tables do not fit in shared memory: this warp's private table in global memory
                 const size_t wtab = (size_t)blockIdx.x * kTcWarps + warp;
-                double* my_sums = P.warp_sums + wtab * P.part_stride;
-                long long* my_counts = P.warp_counts + wtab * P.k_max;
                 int* wscr = reinterpret_cast<int*>(smem + T.off_scratch + (size_t)warp * T.scratch_bytes);
                 unsigned char* perm = reinterpret_cast<unsigned char*>(wscr + 2 * P.k_max + 2);
-                if (delta) {
-                    unsigned m = mch;
-                    while (m) {   // +x to the new label's sums, -x to the old one's (fire-and-forget reductions)
-                        const int src = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int newL = __shfl_sync(0xffffffffu, lab, src);
-                        const int oldL = __shfl_sync(0xffffffffu, oldl, src);
-                        move_one(slot, d, lane, my_sums, my_counts, wq * 32 + src, newL, oldL);
-                    }
-                } else {
-                    full_warp_sums(slot, d, pr.k, lane, lab, mycell_in_tile, wscr, perm, my_sums, my_counts);
-                }
+                full_warp_sums(slot, d, pr.k, lane, lab, mycell_in_tile, wscr, perm, P.warp_sums + wtab * P.part_stride, P.warp_counts + wtab * P.k_max);
             }
             tc_fence_before();   // this warp's tcgen05.ld of the accumulator are complete before the next products overwrite it
             __syncwarp();
@@ -530,49 +534,60 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
             const int64_t stride = P.part_stride;
             const int64_t entries = stride + P.k_max + 1;
             double* out = P.cta_tables + (size_t)(blockIdx.x + p) * entries;
-            const size_t wbase = (size_t)blockIdx.x * kTcWarps;
-            for (int64_t e = threadIdx.x; e < entries; e += kTcWarps * 32) {
-                double acc = 0.0;
-                if (e < stride) {
-                    if (P.warp_sums) {
-                        double v[kTcWarps];   // all loads in flight first, then the fixed-order sum
-#pragma unroll
-                        for (int w = 0; w < kTcWarps; ++w) v[w] = __ldcg(P.warp_sums + (wbase + w) * stride + e);
-#pragma unroll
-                        for (int w = 0; w < kTcWarps; ++w) {
-                            acc += v[w];
-                            if (v[w] != 0.0) __stcg(P.warp_sums + (wbase + w) * stride + e, 0.0);
-                        }
-                    }
-                    if (T.gtab)
-                        for (int g = 0; g < kTcGroups; ++g) {
-                            double* t = reinterpret_cast<double*>(smem + T.off_gtab + (size_t)g * T.gtab_bytes) + e;
-                            acc += *t;
-                            *t = 0.0;
-                        }
-                } else if (e < stride + P.k_max) {
-                    long long t = 0;
-                    if (P.warp_counts) {
-#pragma unroll
-                        for (int w = 0; w < kTcWarps; ++w) {
-                            const long long v = __ldcg(P.warp_counts + (wbase + w) * P.k_max + (e - stride));
-                            t += v;
-                            if (v != 0) __stcg(P.warp_counts + (wbase + w) * P.k_max + (e - stride), 0LL);
-                        }
-                    }
-                    if (T.gtab)
-                        for (int g = 0; g < kTcGroups; ++g) {
-                            long long* c = reinterpret_cast<long long*>(reinterpret_cast<double*>(smem + T.off_gtab + (size_t)g * T.gtab_bytes) + stride) + (e - stride);
-                            t += *c;
-                            *c = 0;
-                        }
-                    acc = (double)t;
-                } else {
+            if (delta) {
+                // sums and counts of this (CTA, problem) come from delta_sums_kernel: hand it the list lengths
+                if (lane == 0) P.move_counts[(size_t)(blockIdx.x + p) * kTcWarps + warp] = (int32_t)(list_cursor - list_begin);
+                if (threadIdx.x == 0) {
                     long long t = 0;
                     for (int w = 0; w < kTcWarps; ++w) t += s_changed[w];
-                    acc = (double)t;
+                    out[entries - 1] = (double)t;
                 }
-                out[e] = acc;
+            } else {
+                const size_t wbase = (size_t)blockIdx.x * kTcWarps;
+                const bool wt = !T.gtab && P.warp_sums;   // the per-warp tables in global memory were in use
+                for (int64_t e = threadIdx.x; e < entries; e += kTcWarps * 32) {
+                    double acc = 0.0;
+                    if (e < stride) {
+                        if (wt) {
+                            double v[kTcWarps];   // all loads in flight first, then the fixed-order sum
+#pragma unroll
+                            for (int w = 0; w < kTcWarps; ++w) v[w] = __ldcg(P.warp_sums + (wbase + w) * stride + e);
+#pragma unroll
+                            for (int w = 0; w < kTcWarps; ++w) {
+                                acc += v[w];
+                                if (v[w] != 0.0) __stcg(P.warp_sums + (wbase + w) * stride + e, 0.0);
+                            }
+                        }
+                        if (T.gtab)
+                            for (int g = 0; g < kTcGroups; ++g) {
+                                double* t = reinterpret_cast<double*>(smem + T.off_gtab + (size_t)g * T.gtab_bytes) + e;
+                                acc += *t;
+                                *t = 0.0;
+                            }
+                    } else if (e < stride + P.k_max) {
+                        long long t = 0;
+                        if (wt) {
+#pragma unroll
+                            for (int w = 0; w < kTcWarps; ++w) {
+                                const long long v = __ldcg(P.warp_counts + (wbase + w) * P.k_max + (e - stride));
+                                t += v;
+                                if (v != 0) __stcg(P.warp_counts + (wbase + w) * P.k_max + (e - stride), 0LL);
+                            }
+                        }
+                        if (T.gtab)
+                            for (int g = 0; g < kTcGroups; ++g) {
+                                long long* c = reinterpret_cast<long long*>(reinterpret_cast<double*>(smem + T.off_gtab + (size_t)g * T.gtab_bytes) + stride) + (e - stride);
+                                t += *c;
+                                *c = 0;
+                            }
+                        acc = (double)t;
+                    } else {
+                        long long t = 0;
+                        for (int w = 0; w < kTcWarps; ++w) t += s_changed[w];
+                        acc = (double)t;
+                    }
+                    out[e] = acc;
+                }
             }
         }
         tile = p_end;
@@ -587,6 +602,124 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
     consumer_barrier<kTcWarps * 32>();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)T.tmem_cols));
 }
+
+// ---------------------------------------------------------------------------------------------------
+// delta_sums_kernel: the sums/counts of a delta iteration.  CTA c walks the same (CTA, problem) ranges as CTA c of the pass
+// that just ran; warp a turns the lists a, a + A, ... of that CTA's consumer warps into its private fp64 table in shared
+// memory — for each recorded cell, +row to the new label and -row to the old one, lane = marker, in list order — then the
+// tables are added up in warp order and written where the pass itself writes the tables of a full iteration.  Every step has
+// a fixed order, so the sums are bit-reproducible; the rows are gathered from HBM (ceil(d/4) sectors per moved cell), eight
+// cells in flight per warp.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kDeltaBatch = 16;
+__global__ void __launch_bounds__(512, 1) delta_sums_kernel(const PassParams P, const int d, const int W, const int A, const int table_doubles) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    double* tabs = reinterpret_cast<double*>(dsm);
+    __shared__ uint32_t cursor[4 * kTcMaxGroups];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t_begin = P.cta_tile_start[blockIdx.x], t_end = P.cta_tile_start[blockIdx.x + 1];
+    if (t_begin >= t_end) return;
+    if (threadIdx.x < 4 * kTcMaxGroups) cursor[threadIdx.x] = 0;
+    int p = 0;
+    {
+        int lo = 0, hi = P.n_problems - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (P.problems[mid].first_tile <= t_begin) lo = mid; else hi = mid - 1;
+        }
+        p = lo;
+    }
+    const int64_t stride = P.part_stride;
+    const int64_t entries = stride + P.k_max + 1;
+    const size_t tile_fl = tile_floats(d);
+    int tile = t_begin;
+    while (tile < t_end) {
+        const Problem* pr = P.problems + p;
+        const int p_end = min(t_end, pr->first_tile + pr->n_tiles);
+        if (pr->done || p_end <= tile) {
+            tile = max(tile, p_end);
+            ++p;
+            continue;
+        }
+        if (pr->delta) {   // (uniform over the CTA)
+            for (int i = threadIdx.x; i < A * table_doubles; i += blockDim.x) tabs[i] = 0.0;
+            __syncthreads();
+            if (warp < A) {
+                double* tab = tabs + (size_t)warp * table_doubles;
+                long long* cnt = reinterpret_cast<long long*>(tab + stride);
+                const float* __restrict__ x = pr->x;
+                for (int l = warp; l < W; l += A) {
+                    const int n_e = P.move_counts[(size_t)(blockIdx.x + p) * W + l];
+                    const uint32_t pos_l = cursor[l];   // position of this range's first entry in list l
+                    const uint2* __restrict__ list = P.move_lists + ((size_t)blockIdx.x * W + l) * P.move_cap + pos_l;
+                    uint2 ent_next = make_uint2(0u, 0u);
+                    if (lane < min(kDeltaBatch, n_e)) ent_next = list[lane];
+                    for (int e0 = 0; e0 < n_e; e0 += kDeltaBatch) {
+                        const int m = min(kDeltaBatch, n_e - e0);
+                        const uint2 ent = ent_next;
+                        if (e0 + kDeltaBatch + lane < n_e && lane < kDeltaBatch) ent_next = list[e0 + kDeltaBatch + lane];   // next batch's entries: in flight with the gathers
+                        for (int jb = 0; jb < d; jb += 64) {
+                            const int j0 = jb + lane, j1 = j0 + 32;
+                            const bool on0 = j0 < d, on1 = j1 < d;
+                            const int c0 = on0 ? j0 : 0, c1 = on1 ? j1 : 0;   // clamped: the gathers are unconditional (entries past the batch read cell 0)
+                            const size_t jo0 = (size_t)(c0 >> 2) * kGroupFloats + (c0 & 3), jo1 = (size_t)(c1 >> 2) * kGroupFloats + (c1 & 3);
+                            float v0[kDeltaBatch], v1[kDeltaBatch];
+#pragma unroll
+                            for (int q = 0; q < kDeltaBatch; ++q) {   // all gathers of the batch in flight
+                                const uint32_t cell = __shfl_sync(0xffffffffu, ent.x, q);
+                                const float* row = x + (size_t)(cell >> 7) * tile_fl + (size_t)(cell & 127u) * 4;
+                                v0[q] = __ldg(row + jo0);
+                                v1[q] = __ldg(row + jo1);
+                            }
+#pragma unroll
+                            for (int q = 0; q < kDeltaBatch; ++q) {
+                                const uint32_t lab = __shfl_sync(0xffffffffu, ent.y, q);
+                                if (q < m) {
+                                    // the four read-modify-writes of an entry are independent (new != old label, two different markers)
+                                    double* tn = tab + (size_t)(lab & 0xffffu) * d;
+                                    double* to = tab + (size_t)(lab >> 16) * d;
+                                    const double n0 = on0 ? tn[j0] : 0.0, o0 = on0 ? to[j0] : 0.0;
+                                    const double n1 = on1 ? tn[j1] : 0.0, o1 = on1 ? to[j1] : 0.0;
+                                    if (on0) {
+                                        tn[j0] = n0 + (double)v0[q];
+                                        to[j0] = o0 - (double)v0[q];
+                                    }
+                                    if (on1) {
+                                        tn[j1] = n1 + (double)v1[q];
+                                        to[j1] = o1 - (double)v1[q];
+                                    }
+                                    if (jb == 0 && lane == 0) {
+                                        cnt[lab & 0xffffu] += 1;
+                                        cnt[lab >> 16] -= 1;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) cursor[l] += (uint32_t)n_e;
+                }
+            }
+            __syncthreads();
+            double* out = P.cta_tables + (size_t)(blockIdx.x + p) * entries;
+            for (int64_t e = threadIdx.x; e < stride + P.k_max; e += blockDim.x) {
+                if (e < stride) {
+                    double acc = 0.0;
+                    for (int a = 0; a < A; ++a) acc += tabs[(size_t)a * table_doubles + e];
+                    out[e] = acc;
+                } else {
+                    long long t = 0;
+                    for (int a = 0; a < A; ++a) t += reinterpret_cast<const long long*>(tabs + (size_t)a * table_doubles)[e];
+                    out[e] = (double)t;
+                }
+            }
+            __syncthreads();
+        }
+        tile = p_end;
+        ++p;
+    }
+}
+
 
 // ---------------------------------------------------------------------------------------------------
 // host side
@@ -682,6 +815,23 @@ int launch_tc_pass(const TcPlan& plan, const PassParams& P, int grid, cudaStream
         DPR_CUDA(cudaEventRecord(e1, stream));
         ctx().pass_events.emplace_back(e0, e1);
     }
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+
+int launch_delta_sums(const TcPlan& plan, const PassParams& P, int grid, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        DPR_CUDA(cudaFuncSetAttribute(delta_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget - 1024));
+        configured = true;
+    }
+    const int W = 4 * plan.groups;
+    const size_t table_bytes = ((size_t)P.part_stride + P.k_max) * 8;
+    const size_t budget = (size_t)kSmemBudget - 1024;
+    int A = (int)std::min<size_t>((size_t)W, budget / table_bytes);
+    if (A < 1) return fail(DPR_ERR_INVALID, "delta sums: one k x d table does not fit in shared memory");
+    delta_sums_kernel<<<grid, 512, (size_t)A * table_bytes, stream>>>(P, plan.d, W, A, (int)(table_bytes / 8));
+    count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
 }

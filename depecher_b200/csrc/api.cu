@@ -12,6 +12,9 @@
 #include "common.cuh"
 #include "scale.cuh"
 #include "session.cuh"
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include "../../include/dpr_philox.h"
 
 namespace dpr {
@@ -136,11 +139,59 @@ static int upload_stage(int64_t elems) {
     return DPR_OK;
 }
 
+// double -> float of one contiguous piece.  With AVX: four values per convert and streaming (non-temporal) stores, so the
+// pinned destination is written without first being read into the cache (it is only ever read by the DMA engine).
+#if defined(__x86_64__)
+__attribute__((target("avx"))) static void narrow_piece_avx(const double* src, float* dst, int64_t a, int64_t b) {
+    int64_t i = a;
+    for (; i < b && (reinterpret_cast<uintptr_t>(dst + i) & 31); ++i) dst[i] = (float)src[i];
+    for (; i + 8 <= b; i += 8) {
+        const __m128 lo = _mm256_cvtpd_ps(_mm256_loadu_pd(src + i));
+        const __m128 hi = _mm256_cvtpd_ps(_mm256_loadu_pd(src + i + 4));
+        _mm256_stream_ps(dst + i, _mm256_set_m128(hi, lo));
+    }
+    for (; i < b; ++i) dst[i] = (float)src[i];
+    _mm_sfence();
+}
+#endif
+#if defined(__x86_64__)
+__attribute__((target("avx"))) static void copy_piece_avx(const double* src, double* dst, int64_t count) {
+    int64_t i = 0;
+    for (; i < count && (reinterpret_cast<uintptr_t>(dst + i) & 31); ++i) dst[i] = src[i];
+    for (; i + 8 <= count; i += 8) {
+        _mm256_stream_pd(dst + i, _mm256_loadu_pd(src + i));
+        _mm256_stream_pd(dst + i + 4, _mm256_loadu_pd(src + i + 4));
+    }
+    for (; i < count; ++i) dst[i] = src[i];
+    _mm_sfence();
+}
+#endif
+// pageable -> pinned copy of doubles with streaming stores (the destination is only ever read by the DMA engine)
+static void copy_piece(const double* src, double* dst, int64_t count) {
+#if defined(__x86_64__)
+    static const bool avx = __builtin_cpu_supports("avx");
+    if (avx) return copy_piece_avx(src, dst, count);
+#endif
+    std::memcpy(dst, src, sizeof(double) * (size_t)count);
+}
+template <typename T>
+static void narrow_piece(const T* src, float* dst, int64_t a, int64_t b) {
+    for (int64_t i = a; i < b; ++i) dst[i] = (float)src[i];
+}
+template <>
+void narrow_piece<double>(const double* src, float* dst, int64_t a, int64_t b) {
+#if defined(__x86_64__)
+    static const bool avx = __builtin_cpu_supports("avx");
+    if (avx) return narrow_piece_avx(src, dst, a, b);
+#endif
+    for (int64_t i = a; i < b; ++i) dst[i] = (float)src[i];
+}
+
 template <typename T>
 static void narrow_parallel(const T* src, float* dst, int64_t count, int threads) {
     auto work = [=](int t) {
         const int64_t a = count * t / threads, b = count * (t + 1) / threads;
-        for (int64_t i = a; i < b; ++i) dst[i] = (float)src[i];
+        narrow_piece<T>(src, dst, a, b);
     };
     if (threads <= 1 || count < (1 << 16)) {
         for (int t = 0; t < threads; ++t) work(t);
@@ -182,6 +233,37 @@ static int single_session(dpr_dataset* ds, int k, double reg, int no_zero, bool 
 
 static int copy_labels_out(const int32_t* d_labels, int64_t n, int32_t* host) {
     if (!host) return DPR_OK;
+    if (n >= (1 << 19) && g_stage.cap > 0) {
+        // the caller's vector is pageable: the driver would stage it at a few GB/s.  DMA into the pinned upload buffers instead
+        // and let host threads copy a piece out while the next one arrives.
+        const int64_t piece = std::min<int64_t>(g_stage.cap, (int64_t)4 << 20);
+        const int threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+        int b = 0;
+        int64_t prev0 = -1, prev_cnt = 0;
+        for (int64_t e0 = 0; e0 < n || prev0 >= 0; e0 += piece, b ^= 1) {
+            const int64_t cnt = e0 < n ? std::min(piece, n - e0) : 0;
+            if (cnt > 0) {
+                DPR_CUDA(cudaMemcpyAsync(g_stage.pinned[b], d_labels + e0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ctx().stream));
+                DPR_CUDA(cudaEventRecord(g_stage.done[b], ctx().stream));
+            }
+            if (prev0 >= 0) {   // the previous piece has landed in the other buffer: out to the caller
+                DPR_CUDA(cudaEventSynchronize(g_stage.done[b ^ 1]));
+                const int32_t* src = reinterpret_cast<const int32_t*>(g_stage.pinned[b ^ 1]);
+                std::vector<std::thread> pool;
+                auto work = [=](int t) {
+                    const int64_t a = prev_cnt * t / threads, z = prev_cnt * (t + 1) / threads;
+                    std::memcpy(host + prev0 + a, src + a, sizeof(int32_t) * (size_t)(z - a));
+                };
+                for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+                work(0);
+                for (auto& th : pool) th.join();
+            }
+            prev0 = cnt > 0 ? e0 : -1;
+            prev_cnt = cnt;
+        }
+        return DPR_OK;
+    }
     DPR_CUDA(cudaMemcpyAsync(host, d_labels, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx().stream));
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));
     return DPR_OK;
@@ -538,7 +620,7 @@ int dpr_dataset_create_scaled(const double* X, int64_t n, int32_t d, int32_t log
             double* pin = reinterpret_cast<double*>(g_stage.pinned[b]);
             std::vector<std::thread> pool;
             for (int t = 0; t < threads; ++t)
-                pool.emplace_back([=] { const int64_t a0 = cnt * t / threads, a1 = cnt * (t + 1) / threads; std::memcpy(pin + a0, X + e0 + a0, sizeof(double) * (a1 - a0)); });
+                pool.emplace_back([=] { const int64_t a0 = cnt * t / threads, a1 = cnt * (t + 1) / threads; copy_piece(X + e0 + a0, pin + a0, a1 - a0); });
             for (auto& th : pool) th.join();
             DPR_CUDA(cudaMemcpyAsync(raw.as<double>() + e0, pin, sizeof(double) * cnt, cudaMemcpyHostToDevice, ctx().stream));
             DPR_CUDA(cudaEventRecord(g_stage.done[b], ctx().stream));

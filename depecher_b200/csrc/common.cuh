@@ -89,6 +89,9 @@ struct Problem {
     int32_t tc_npad;      // columns reserved per problem (k_max rounded up to 32)
     int32_t first_tile;   // index of this problem's first tile in the global tile order
     int32_t n_tiles;
+    int32_t bundle;       // assignment-only sessions of the tensor-core pass: this problem and the next bundle - 1 ones score the SAME
+                          //   cells against different centre sets; the leader owns the tiles (members: n_tiles = 0, first_tile = the
+                          //   leader's end), a landed tile is split once and multiplied with every set's centres.  0 / 1: on its own
     // Lloyd-loop state (find_centers, Clusterer.cpp:244-252)
     double reg;           // full penalty
     int32_t no_zero;

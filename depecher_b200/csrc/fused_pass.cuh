@@ -14,6 +14,7 @@ struct PassParams {
     const int32_t* cta_tile_start;  // [grid + 1]: contiguous tile range of each CTA in the global tile order
     int32_t mode;
     int32_t compare_old;            // count labels that differ from the previous ones
+    int32_t bundles;                // some problems share their cells with the next ones (Problem::bundle > 1): the tensor-core pass runs its multi-set instance
     int32_t k_max;                  // rows of the widest centre matrix (table strides)
     int64_t part_stride;            // doubles per sum table (k_max * d)
     double* warp_sums;              // [grid * warps][k_max * d]   private per-warp tables (Lloyd / sums modes)
@@ -46,12 +47,15 @@ struct TcPlan {
     int32_t stages, stage_floats;
     int32_t off_hdr, off_cc, off_orig, off_scratch, scratch_bytes, off_b, off_stages;
     int32_t mu_in_smem, off_mu;   // fp64 centres in shared memory for the exact re-decisions
+    int32_t sets, set_bytes;      // centre sets (problems of a bundle) resident at once; hdr/cc/orig/b/mu of set s sit s * set_bytes further
     int32_t gtab, gtab_bytes, glist_bytes, off_gtab, off_glist;   // Lloyd tables of the consumer groups in shared memory (gtab = 0: per-warp tables in global memory)
     size_t smem_bytes;
     size_t table_floats;    // floats of Problem::tc_table
 };
 // returns 1 when the shape fits the tensor-core pass (k_max <= 128, >= 2 consumer groups in the 512 TMEM columns, >= 3 stages)
-int plan_tc_pass(int d, int k_max, TcPlan* plan);
+// sets_wanted: 1 for Lloyd sessions; assignment-only sessions may hold up to kTcMaxSets centre sets that share the cells
+constexpr int kTcMaxSets = 4;
+int plan_tc_pass(int d, int k_max, int sets_wanted, TcPlan* plan);
 int launch_tc_pass(const TcPlan& plan, const PassParams& P, int grid, cudaStream_t stream);
 // sums/counts of the moved cells recorded by a tensor-core Lloyd pass in delta mode (tc_pass.cu)
 int launch_delta_sums(const TcPlan& plan, const PassParams& P, int grid, cudaStream_t stream);

@@ -37,7 +37,7 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
     if (!plan_pass(d, k_max_, &plan))
         return fail(DPR_ERR_INVALID, "shape not supported by the sm_100a kernels: d = " + std::to_string(d) + ", k = " +
                                          std::to_string(k_max_) + " (one 128-cell slot of d markers plus the centre table must fit in 227 KB)");
-    use_tc = !ctx().force_ffma && plan_tc_pass(d, k_max_, &tc_plan) != 0;
+    use_tc = !ctx().force_ffma && plan_tc_pass(d, k_max_, want_sums ? 1 : kTcMaxSets, &tc_plan) != 0;
     const int P = (int)specs.size();
     h_problems.assign(P, Problem{});
     // pooled per-problem storage
@@ -59,7 +59,7 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
         DPR_TRY(alloc(&tc_tab_pool, tc_plan.table_floats * P, true));
         DPR_TRY(alloc(&tc_orig_pool, (size_t)tc_plan.npad * P, true));
     }
-    int tile = 0;
+    int tile = 0, leader = 0, bundle_left = 0;
     for (int p = 0; p < P; ++p) {
         Problem& pr = h_problems[p];
         const ProblemSpec& s = specs[p];
@@ -79,9 +79,25 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
             pr.tc_orig = tc_orig_pool + (size_t)tc_plan.npad * p;
             pr.tc_npad = tc_plan.npad;
         }
-        pr.first_tile = tile;
-        pr.n_tiles = (int)((s.n + kSlotCells - 1) / kSlotCells);
-        tile += pr.n_tiles;
+        // assignment-only sessions of the tensor-core pass: consecutive problems over the same cells form a bundle — the leader
+        // owns the tiles, the others sit (empty) at its end and ride along in the kernel (Problem::bundle)
+        const bool member = use_tc && !want_sums && p > 0 && bundle_left > 0 && s.x == specs[p - 1].x && s.n == specs[p - 1].n &&
+                            s.tile_xx == specs[p - 1].tile_xx && s.xx_max == specs[p - 1].xx_max;
+        if (member) {
+            pr.first_tile = tile;
+            pr.n_tiles = 0;
+            pr.bundle = 0;
+            ++h_problems[leader].bundle;
+            has_bundles_ = true;
+            --bundle_left;
+        } else {
+            leader = p;
+            bundle_left = use_tc && !want_sums ? tc_plan.sets - 1 : 0;
+            pr.bundle = 1;
+            pr.first_tile = tile;
+            pr.n_tiles = (int)((s.n + kSlotCells - 1) / kSlotCells);
+            tile += pr.n_tiles;
+        }
         pr.reg = s.reg;
         pr.no_zero = s.no_zero;
         pr.sums = sums_pool + mu_sz * p;
@@ -163,6 +179,7 @@ int Session::pass(int mode, bool compare_old) {
     P.cta_tile_start = d_cta_start_;
     P.mode = mode;
     P.compare_old = compare_old ? 1 : 0;
+    P.bundles = has_bundles_ ? 1 : 0;
     P.k_max = k_max_;
     P.part_stride = (int64_t)k_max_ * d_;
     P.warp_sums = warp_sums_;

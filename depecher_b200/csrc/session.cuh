@@ -64,7 +64,7 @@ public:
 
 private:
     int d_ = 0, k_max_ = 0, total_tiles_ = 0;
-    bool want_sums_ = false;
+    bool want_sums_ = false, has_bundles_ = false;
     std::vector<void*> owned_;
     int32_t* d_cta_start_ = nullptr;
     double* warp_sums_ = nullptr;

@@ -62,6 +62,15 @@ __device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, u
         "r"(parity), "r"(hint_ns)
         : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -196,7 +205,11 @@ __device__ __noinline__ void full_tile_sums(const float* __restrict__ slot, unsi
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-template <int MODE, int kTcGroups>
+struct SetRef {          // what the consumers need of problem p + s of a bundle besides its tables
+    int32_t* labels;
+    const double* mu;    // exact centres (global memory; used when they are not staged in shared memory)
+};
+template <int MODE, int kTcGroups, bool kMulti>
 __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(const PassParams P, const TcPlan T) {
     constexpr int kTcWarps = 4 * kTcGroups;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -210,10 +223,11 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
     uint64_t* a_ready = empty + kTcMaxStages;             // [G] the group's A operands are in tensor memory (one arrival per warp)
     uint64_t* mma_done = a_ready + kTcMaxGroups;                     // [G] products into the group's accumulator finished
     uint64_t* tables_ready = mma_done + kTcMaxGroups;                // the problem's centre tables are in shared memory
-    uint32_t* tmem_word = reinterpret_cast<uint32_t*>(tables_ready + 1);
+    uint64_t* acc_free = tables_ready + 1;                           // [G] bundles: the group has read its accumulator, the next set's products may overwrite it
+    uint32_t* tmem_word = reinterpret_cast<uint32_t*>(acc_free + kTcMaxGroups);
+    SetRef* set_ref = reinterpret_cast<SetRef*>(tmem_word + 2);      // [kTcMaxSets] label / exact-centre pointers of the bundle's problems
+    // kMulti: several centre sets per tile (bundles; assignment-only sessions).  A separate instance: the single-set pass keeps its registers
     CentreHeader* hdr = reinterpret_cast<CentreHeader*>(smem + T.off_hdr);
-    float* cc_s = reinterpret_cast<float*>(smem + T.off_cc);
-    int32_t* orig = reinterpret_cast<int32_t*>(smem + T.off_orig);
     float* bmat = reinterpret_cast<float*>(smem + T.off_b);
     float* stages = reinterpret_cast<float*>(smem + T.off_stages);
     double* mu_s = reinterpret_cast<double*>(smem + T.off_mu);   // the problem's exact centres, for the fp64 re-decisions (when they fit)
@@ -232,6 +246,7 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
         for (int g = 0; g < kTcGroups; ++g) {
             mbar_init(&a_ready[g], 4);
             mbar_init(&mma_done[g], 1);
+            mbar_init(&acc_free[g], 4);
         }
         mbar_init(tables_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -294,7 +309,7 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
     // ================================ the warp that issues the products ================================
     if (warp == kTcWarps) {
         int tile = t_begin;
-        uint32_t it = 0, n_prob = 0;
+        uint32_t it = 0, n_prob = 0, ar_phase = 0, free_phase = 0;   // (phase bits: one per group)
         const uint32_t lbo = (uint32_t)npad * 32u;   // bytes between 8-marker groups of the (2*npad)-row B operand
         const uint64_t desc_b0 = umma_desc(smem_u32(bmat), lbo, 128);
         const uint64_t desc_step = (uint64_t)((2u * lbo) >> 4);   // one K=16 step = two marker groups further
@@ -308,23 +323,79 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
             }
             mbar_wait_hint(tables_ready, n_prob & 1u, T.wait_hint);
             ++n_prob;
-            const int N = hdr->tc_n;
             const uint32_t idesc0 = (1u << 4) | ((uint32_t)(128 >> 4) << 24);           // D fp32, A/B fp16, both K-major, M = 128
-            const uint32_t idesc_hi = idesc0 | ((uint32_t)((npad + N) >> 3) << 17);     // xh * [ch | cl] -> columns [0, npad + N)
-            const uint32_t idesc_lo = idesc0 | ((uint32_t)(N >> 3) << 17);              // xl * ch        -> columns [0, N)
-            for (; tile < p_end; ++tile, ++it) {
-                const uint32_t g = it % kTcGroups, k = it / kTcGroups;
-                mbar_wait_hint(&a_ready[g], k & 1u, T.wait_hint);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t acc = tmem + g * buf_cols, ah = acc + (uint32_t)(2 * npad), al = ah + (uint32_t)acols;
-                    for (int s = 0; s < g16 / 2; ++s) {
-                        umma_f16_ts(acc, ah + 8 * s, desc_b0 + s * desc_step, idesc_hi, s > 0 ? 1u : 0u);
-                        umma_f16_ts(acc, al + 8 * s, desc_b0 + s * desc_step, idesc_lo, 1);
+            if constexpr (!kMulti) {
+                const int N = reinterpret_cast<const CentreHeader*>(smem + T.off_hdr)->tc_n;
+                const uint32_t idesc_hi = idesc0 | ((uint32_t)((npad + N) >> 3) << 17);     // xh * [ch | cl] -> columns [0, npad + N)
+                const uint32_t idesc_lo = idesc0 | ((uint32_t)(N >> 3) << 17);              // xl * ch        -> columns [0, N)
+                for (; tile < p_end; ++tile, ++it) {
+                    const uint32_t g = it % kTcGroups;
+                    mbar_wait_hint(&a_ready[g], (ar_phase >> g) & 1u, T.wait_hint);
+                    ar_phase ^= 1u << g;
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t acc = tmem + g * buf_cols, ah = acc + (uint32_t)(2 * npad), al = ah + (uint32_t)acols;
+                        for (int s = 0; s < g16 / 2; ++s) {
+                            umma_f16_ts(acc, ah + 8 * s, desc_b0 + s * desc_step, idesc_hi, s > 0 ? 1u : 0u);
+                            umma_f16_ts(acc, al + 8 * s, desc_b0 + s * desc_step, idesc_lo, 1);
+                        }
+                        umma_commit(&mma_done[g]);
                     }
-                    umma_commit(&mma_done[g]);
+                    __syncwarp();
                 }
-                __syncwarp();
+            } else {
+                // bundles: every tile is multiplied with NS centre sets, one after the other into the same accumulator.  A group is
+                // ready for its next products when its A operands are in place (first set of a tile) or when it has taken the
+                // previous set's scores out of the accumulator; the groups reach these points in no particular order, so the warp
+                // polls them in turn instead of waiting for one.
+                const int NS = max(1, pr->bundle);
+                const int count = p_end - tile;
+                int left[kTcGroups], q_next[kTcGroups], events = 0;
+#pragma unroll
+                for (int g = 0; g < kTcGroups; ++g) {
+                    const int j0 = (int)((g + kTcGroups - it % kTcGroups) % kTcGroups);   // the group's first tile of the range
+                    left[g] = j0 < count ? (count - j0 + kTcGroups - 1) / kTcGroups : 0;
+                    q_next[g] = 0;
+                    events += left[g] * NS;
+                }
+                const uint64_t desc_set = (uint64_t)((uint32_t)T.set_bytes >> 4);   // the next set's B operand
+                while (events > 0) {
+                    bool any = false;
+#pragma unroll
+                    for (int g = 0; g < kTcGroups; ++g) {
+                        if (left[g] == 0) continue;
+                        const int q = q_next[g];
+                        uint64_t* bar = q == 0 ? &a_ready[g] : &acc_free[g];
+                        const uint32_t par = ((q == 0 ? ar_phase : free_phase) >> g) & 1u;
+                        if (!mbar_test(bar, par)) continue;
+                        if (q == 0) ar_phase ^= 1u << g; else free_phase ^= 1u << g;
+                        tc_fence_after();
+                        const int N = reinterpret_cast<const CentreHeader*>(smem + T.off_hdr + q * T.set_bytes)->tc_n;
+                        const uint32_t idesc_hi = idesc0 | ((uint32_t)((npad + N) >> 3) << 17);
+                        const uint32_t idesc_lo = idesc0 | ((uint32_t)(N >> 3) << 17);
+                        if (elect_one()) {
+                            const uint32_t acc = tmem + g * buf_cols, ah = acc + (uint32_t)(2 * npad), al = ah + (uint32_t)acols;
+                            const uint64_t db = desc_b0 + q * desc_set;
+                            for (int s = 0; s < g16 / 2; ++s) {
+                                umma_f16_ts(acc, ah + 8 * s, db + s * desc_step, idesc_hi, s > 0 ? 1u : 0u);
+                                umma_f16_ts(acc, al + 8 * s, db + s * desc_step, idesc_lo, 1);
+                            }
+                            umma_commit(&mma_done[g]);
+                        }
+                        __syncwarp();
+                        if (q + 1 == NS) {
+                            q_next[g] = 0;
+                            --left[g];
+                        } else {
+                            q_next[g] = q + 1;
+                        }
+                        --events;
+                        any = true;
+                    }
+                    if (!any) __nanosleep(40);
+                }
+                it += (uint32_t)count;
+                tile = p_end;
             }
             ++p;
         }
@@ -368,27 +439,42 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
             continue;
         }
         consumer_barrier<kTcWarps * 32>();   // nobody still reads the previous problem's tables (every group has seen its last products complete)
-        {
-            const int* src = reinterpret_cast<const int*>(pr.hdr);
-            int* dst = reinterpret_cast<int*>(hdr);
+        const int NS = kMulti ? max(1, pr.bundle) : 1;   // centre sets that share this range's cells (problems p .. p + NS - 1)
+        for (int q = 0; q < NS; ++q) {
+            const Problem* pq = P.problems + p + q;
+            unsigned char* base = smem + (size_t)q * T.set_bytes;
+            const float* tab = q ? pq->tc_table : pr.tc_table;
+            const int32_t* torig = q ? pq->tc_orig : pr.tc_orig;
+            const double* mu_g = q ? pq->mu : pr.mu;
+            const int kq = q ? pq->k : pr.k;
+            const int* src = reinterpret_cast<const int*>(q ? pq->hdr : pr.hdr);
+            int* dst = reinterpret_cast<int*>(base + T.off_hdr);
             for (int i = threadIdx.x; i < (int)(sizeof(CentreHeader) / 4); i += kTcWarps * 32) dst[i] = src[i];
-            const float4* bsrc = reinterpret_cast<const float4*>(pr.tc_table + npad);
-            float4* bdst = reinterpret_cast<float4*>(bmat);
+            const float4* bsrc = reinterpret_cast<const float4*>(tab + npad);
+            float4* bdst = reinterpret_cast<float4*>(base + T.off_b);
             for (int i = threadIdx.x; i < 2 * g16 * npad; i += kTcWarps * 32) bdst[i] = bsrc[i];   // g16 groups x 2*npad rows x 16 B
+            float* cq = reinterpret_cast<float*>(base + T.off_cc);
+            int32_t* oq = reinterpret_cast<int32_t*>(base + T.off_orig);
             for (int i = threadIdx.x; i < npad; i += kTcWarps * 32) {
-                cc_s[i] = pr.tc_table[i];
-                orig[i] = pr.tc_orig[i];
+                cq[i] = tab[i];
+                oq[i] = torig[i];
             }
-            if (T.mu_in_smem)
-                for (int i = threadIdx.x; i < pr.k * d; i += kTcWarps * 32) mu_s[(i / d) * (d | 1) + i % d] = pr.mu[i];   // odd row stride: lanes = rows hit different banks
+            if (T.mu_in_smem) {
+                double* mq = reinterpret_cast<double*>(base + T.off_mu);
+                for (int i = threadIdx.x; i < kq * d; i += kTcWarps * 32) mq[(i / d) * (d | 1) + i % d] = mu_g[i];   // odd row stride: lanes = rows hit different banks
+            }
+            if (kMulti && threadIdx.x == 0) {
+                set_ref[q].labels = q ? pq->labels : pr.labels;
+                set_ref[q].mu = mu_g;
+            }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the B operand was written through the generic proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the B operands were written through the generic proxy
         consumer_barrier<kTcWarps * 32>();
         if (threadIdx.x == 0) mbar_arrive(tables_ready);
-        const int N = hdr->tc_n, n_act = hdr->k_act;
+        int N = hdr->tc_n, n_act = hdr->k_act;
         const double* mu_exact = T.mu_in_smem ? mu_s : pr.mu;
         const int mu_ld = T.mu_in_smem ? (d | 1) : d;
-        const bool trivial = hdr->trivial != 0, force_exact = hdr->force_exact != 0;
+        bool trivial = hdr->trivial != 0, force_exact = hdr->force_exact != 0;
         // error bound of a score: the fp16 splits leave at most 3 * 2^-22 (proved: |v - hi - lo| <= 2^-22 |v| for round-to-nearest
         // parts, three cross terms); the fp32 accumulation inside the tensor core is allowed 2^-21 per product step — measured on
         // this part at <= 2^-24 per step, also for same-sign terms where a truncating adder's bias would add up
@@ -398,11 +484,14 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
         // (2 * 2^-19); the absolute part of the split error (fp16 subnormals) comes through tc_abs1 / tc_abs2.
         const float eps = 3.f * 2.3841858e-7f + (float)(g16 + 1) * 4.7683716e-7f + 4.f * 5.9604645e-8f;
         const float tau_c = 2.f * eps + 3.8146973e-6f;
-        const float scale_x = hdr->tc_scale_x, unscale = hdr->tc_unscale, abs1 = hdr->tc_abs1, abs2 = hdr->tc_abs2;
-        const float cc2 = 2.0f * hdr->cc_max;
+        const float scale_x = hdr->tc_scale_x;   // (the same for every set of a bundle: it depends on the cells only)
+        float unscale = hdr->tc_unscale, abs1 = hdr->tc_abs1, abs2 = hdr->tc_abs2;
+        float cc2 = 2.0f * hdr->cc_max;
+        uint32_t set_off = 0;   // byte offset of the current set's tables (bundles)
+        int32_t* labels_q = pr.labels;
         const bool delta = MODE == kPassLloyd && pr.delta;   // (a session that lets finalize set it has allocated the lists)
         const uint32_t list_begin = list_cursor;
-        const bool need_old = (P.compare_old || delta) && pr.labels;
+        const bool need_old = (P.compare_old || delta) && pr.labels;   // (bundles: every member has labels when the leader has)
         int changed = 0;   // per thread: at most one per tile
         const int count = p_end - tile;
 
@@ -418,8 +507,6 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
             const float* slot = stages + (size_t)s * T.stage_floats;
             const int64_t mycell = (int64_t)(tile + j - pr.first_tile) * kSlotCells + mycell_in_tile;
             const bool live = mycell < pr.n;
-            int oldl = 0;
-            if (need_old && live) oldl = pr.labels[mycell];
             const float xx_tile = pr.tile_xx[tile + j - pr.first_tile];
             DPR_PROF(0);
             mbar_wait_hint(&full[s], full_par, T.wait_hint);
@@ -435,11 +522,33 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                 if (lane == 0) mbar_arrive(&a_ready[grp]);
             }
             DPR_PROF(2);
-            // ---- scores -> label (+ sums)
+            // ---- scores -> label (+ sums), once per centre set of the bundle
+            int lab = 0, oldl = 0;
+            bool ch = false;
+#pragma unroll 1
+            for (int q = 0; q < NS; ++q) {
+            if (kMulti && NS > 1) {   // this set's tables and constants
+                const unsigned char* base = smem + (size_t)q * T.set_bytes;
+                const CentreHeader* h = reinterpret_cast<const CentreHeader*>(base + T.off_hdr);
+                N = h->tc_n;
+                n_act = h->k_act;
+                trivial = h->trivial != 0;
+                force_exact = h->force_exact != 0;
+                unscale = h->tc_unscale;
+                abs1 = h->tc_abs1;
+                abs2 = h->tc_abs2;
+                cc2 = 2.0f * h->cc_max;
+                set_off = (uint32_t)q * (uint32_t)T.set_bytes;
+                mu_exact = T.mu_in_smem ? reinterpret_cast<const double*>(base + T.off_mu) : set_ref[q].mu;
+                labels_q = set_ref[q].labels;
+                if (q > 0) ++k_mine;   // (the loop header counts one completion of mma_done per tile)
+            }
+            oldl = 0;
+            if (need_old && live) oldl = labels_q[mycell];
             mbar_wait_hint(&mma_done[grp], k_mine & 1u, T.wait_hint);
             tc_fence_after();
             DPR_PROF(3);
-            int lab = 0;
+            lab = 0;
             if (!trivial) {
                 float best = 3.3e38f, second = 3.3e38f;
                 int bchunk = 0;
@@ -450,7 +559,7 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     DPR_PROF(4);
                     const float prev = best;
-                    const float4* cc4 = reinterpret_cast<const float4*>(cc_s + n0);
+                    const float4* cc4 = reinterpret_cast<const float4*>(smem + set_off + T.off_cc) + (n0 >> 2);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float4 c = cc4[q];
@@ -470,22 +579,29 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                 const float tau = tau_c * (xx_tile + cc2) + (abs1 * sqrtf(xx_tile) + abs2) + 1e-30f;
                 const int a = bchunk + (int)(__float_as_uint(best) & 15u);
                 const bool sure = (second - best > tau) && !force_exact;
-                lab = orig[a < n_act ? a : 0];
+                const int32_t* orig_q = reinterpret_cast<const int32_t*>(smem + set_off + T.off_orig);
+                lab = orig_q[a < n_act ? a : 0];
                 DPR_PROF(5);
                 unsigned redo = __ballot_sync(0xffffffffu, !sure && live);
                 if (redo && P.recheck_count && lane == 0) atomicAdd(P.recheck_count, (unsigned long long)__popc(redo));
                 while (redo) {   // the whole warp re-decides each doubtful cell in fp64
                     const int src = __ffs(redo) - 1;
                     redo &= redo - 1;
-                    const int v = exact_label_warp(slot, wq * 32 + src, d, mu_exact, mu_ld, orig, n_act, lane);
+                    const int v = exact_label_warp(slot, wq * 32 + src, d, mu_exact, mu_ld, orig_q, n_act, lane);
                     if (lane == src) lab = v;
                 }
             }
             DPR_PROF(6);
             if (!live) lab = -1;
-            const bool ch = lab >= 0 && lab != oldl;
+            ch = lab >= 0 && lab != oldl;
             if (P.compare_old) changed += (int)ch;
-            if (pr.labels && live) pr.labels[mycell] = lab;
+            if (labels_q && live) labels_q[mycell] = lab;
+            if (kMulti && q + 1 < NS) {   // the accumulator may take the next set's products
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_free[grp]);
+            }
+            }   // sets
             DPR_PROF(7);
             if (MODE == kPassLloyd && T.gtab && !delta) {
                 // every cell contributes: the four warps of the group publish their labels, meet at the group's barrier, and update
@@ -724,7 +840,7 @@ __global__ void __launch_bounds__(512, 1) delta_sums_kernel(const PassParams P, 
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-int plan_tc_pass(int d, int k_max, TcPlan* plan) {
+int plan_tc_pass(int d, int k_max, int sets_wanted, TcPlan* plan) {
     if (d < 1 || k_max < 1) return 0;
     const int npad = (k_max + 31) & ~31;
     const int g16 = 2 * ((d + 15) >> 4), acols = 4 * g16;
@@ -739,22 +855,27 @@ int plan_tc_pass(int d, int k_max, TcPlan* plan) {
     while (tmem_cols < cols) tmem_cols <<= 1;
     if (tmem_cols > 512) return 0;
     const size_t stage_bytes = (((size_t)(tile_groups(d) + (tile_groups(d) & 1)) * kGroupFloats * 4) + 127) & ~(size_t)127;   // the tile (+ one zero group when its group count is odd)
-    const size_t bars = 256;
+    const size_t bars = 384;   // mbarriers, the tensor-memory address, the bundle's label / centre pointers
     const size_t hdr_bytes = (sizeof(CentreHeader) + 127) & ~(size_t)127;
     const size_t cc_bytes = (size_t)npad * 4, orig_bytes = (size_t)npad * 4;
     const size_t scratch = (((size_t)(2 * k_max + 2) * 4 + 64) + 127) & ~(size_t)127;
     const size_t b_bytes = (size_t)g16 * 2 * npad * 16;
-    size_t fixed = bars + hdr_bytes + cc_bytes + orig_bytes + scratch * 4 * G + b_bytes;
-    if (fixed + 3 * stage_bytes > (size_t)kSmemBudget) return 0;
+    const size_t fixed0 = bars + scratch * 4 * G;
+    size_t set_bytes = hdr_bytes + cc_bytes + orig_bytes + b_bytes;   // one centre set: header, ||c||^2, column -> row map, B operand
+    if (fixed0 + set_bytes + 3 * stage_bytes > (size_t)kSmemBudget) return 0;
     // the exact centres next to the tables when they are small
     const size_t mu_bytes = (((size_t)k_max * (d | 1) * 8) + 127) & ~(size_t)127;
-    const bool mu_in_smem = mu_bytes <= 32 * 1024 && fixed + mu_bytes + 4 * stage_bytes <= (size_t)kSmemBudget;
-    const size_t off_mu = fixed;
-    if (mu_in_smem) fixed += mu_bytes;
-    // Lloyd tables of the consumer groups in shared memory, when at least 4 stages remain
+    const bool mu_in_smem = mu_bytes <= 32 * 1024 && fixed0 + set_bytes + mu_bytes + 4 * stage_bytes <= (size_t)kSmemBudget;
+    if (mu_in_smem) set_bytes += mu_bytes;
+    // centre sets resident at once (bundles of an assignment-only session): as many as leave 4 stages, at most kTcMaxSets
+    int sets = std::max(1, std::min(sets_wanted, kTcMaxSets));
+    if (const char* e = getenv("DPR_TC_SETS")) sets = std::max(1, std::min(sets, atoi(e)));   // tuning aid
+    while (sets > 1 && fixed0 + (size_t)sets * set_bytes + 4 * stage_bytes > (size_t)kSmemBudget) --sets;
+    size_t fixed = fixed0 + (size_t)sets * set_bytes;
+    // Lloyd tables of the consumer groups in shared memory, when at least 4 stages remain (Lloyd sessions hold one set)
     const size_t gtab_bytes = (((size_t)k_max * d + k_max) * 8 + 127) & ~(size_t)127;
     const size_t glist_bytes = 256;   // [2][128] labels
-    const bool gtab = k_max <= 255 && fixed + (gtab_bytes + glist_bytes) * G + 4 * stage_bytes <= (size_t)kSmemBudget;
+    const bool gtab = sets_wanted <= 1 && k_max <= 255 && fixed + (gtab_bytes + glist_bytes) * G + 4 * stage_bytes <= (size_t)kSmemBudget;
     const size_t off_gtab = fixed;
     if (gtab) fixed += (gtab_bytes + glist_bytes) * G;
     int S = (int)(((size_t)kSmemBudget - fixed) / stage_bytes);
@@ -767,14 +888,16 @@ int plan_tc_pass(int d, int k_max, TcPlan* plan) {
     plan->tmem_cols = tmem_cols;
     plan->stages = S;
     plan->stage_floats = (int)(stage_bytes / 4);
-    plan->off_hdr = (int)bars;
+    plan->off_scratch = (int)bars;
+    plan->scratch_bytes = (int)scratch;
+    plan->off_hdr = (int)fixed0;
     plan->off_cc = plan->off_hdr + (int)hdr_bytes;
     plan->off_orig = plan->off_cc + (int)cc_bytes;
-    plan->off_scratch = plan->off_orig + (int)orig_bytes;
-    plan->scratch_bytes = (int)scratch;
-    plan->off_b = plan->off_scratch + (int)(scratch * 4 * G);
+    plan->off_b = plan->off_orig + (int)orig_bytes;
     plan->mu_in_smem = mu_in_smem ? 1 : 0;
-    plan->off_mu = (int)off_mu;
+    plan->off_mu = plan->off_b + (int)b_bytes;
+    plan->sets = sets;
+    plan->set_bytes = (int)set_bytes;
     plan->gtab = gtab ? 1 : 0;
     plan->gtab_bytes = (int)gtab_bytes;
     plan->glist_bytes = (int)glist_bytes;
@@ -789,9 +912,10 @@ int plan_tc_pass(int d, int k_max, TcPlan* plan) {
 int launch_tc_pass(const TcPlan& plan, const PassParams& P, int grid, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-#define DPR_TC_ATTR(G)                                                                                                            \
-    DPR_CUDA(cudaFuncSetAttribute(tc_pass_kernel<kPassAssign, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); \
-    DPR_CUDA(cudaFuncSetAttribute(tc_pass_kernel<kPassLloyd, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+#define DPR_TC_ATTR(G)                                                                                                                   \
+    DPR_CUDA(cudaFuncSetAttribute(tc_pass_kernel<kPassAssign, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); \
+    DPR_CUDA(cudaFuncSetAttribute(tc_pass_kernel<kPassAssign, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));  \
+    DPR_CUDA(cudaFuncSetAttribute(tc_pass_kernel<kPassLloyd, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
         DPR_TC_ATTR(2) DPR_TC_ATTR(3) DPR_TC_ATTR(4)
 #undef DPR_TC_ATTR
         configured = true;
@@ -803,10 +927,11 @@ int launch_tc_pass(const TcPlan& plan, const PassParams& P, int grid, cudaStream
         DPR_CUDA(cudaEventRecord(e0, stream));
     }
     const int threads = (4 * plan.groups + 2) * 32;
-#define DPR_TC_LAUNCH(G)                                                                                                   \
-    if (plan.groups == G) {                                                                                                \
-        if (P.mode == kPassAssign) tc_pass_kernel<kPassAssign, G><<<grid, threads, plan.smem_bytes, stream>>>(P, plan);     \
-        else tc_pass_kernel<kPassLloyd, G><<<grid, threads, plan.smem_bytes, stream>>>(P, plan);                            \
+#define DPR_TC_LAUNCH(G)                                                                                                          \
+    if (plan.groups == G) {                                                                                                       \
+        if (P.mode == kPassAssign && P.bundles) tc_pass_kernel<kPassAssign, G, true><<<grid, threads, plan.smem_bytes, stream>>>(P, plan); \
+        else if (P.mode == kPassAssign) tc_pass_kernel<kPassAssign, G, false><<<grid, threads, plan.smem_bytes, stream>>>(P, plan);       \
+        else tc_pass_kernel<kPassLloyd, G, false><<<grid, threads, plan.smem_bytes, stream>>>(P, plan);                               \
     }
     DPR_TC_LAUNCH(2) DPR_TC_LAUNCH(3) DPR_TC_LAUNCH(4)
 #undef DPR_TC_LAUNCH

@@ -436,13 +436,17 @@ def depeche(inDataFrame, samplingSubset=None, penalties=None, sampleSize="defaul
         if use_ds:
             ds_used.close()
     # clusters renumbered by size (:236-252)
-    labels, counts = np.unique(clusterVector, return_counts=True)
+    cv = np.asarray(clusterVector)
+    hist = np.bincount(cv, minlength=int(reduced.shape[0]) + 1)          # labels are small positive integers: one counting pass, no sort
+    labels = np.flatnonzero(hist)
+    counts = hist[labels]
     order = labels[np.argsort(-counts, kind="stable")]
-    newVec = np.zeros_like(clusterVector)
+    lut = np.zeros(len(hist), dtype=cv.dtype)
     rank_of_label = {}
     for i, lab in enumerate(order, start=1):
-        newVec[clusterVector == lab] = i
+        lut[lab] = i
         rank_of_label[lab] = i
+    newVec = lut[cv]
     sortedLabels = np.sort(order)
     if len(sortedLabels) == reduced.shape[0]:
         reduced = reduced[np.argsort([rank_of_label[l] for l in sortedLabels])]

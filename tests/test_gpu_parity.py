@@ -217,6 +217,26 @@ def test_allocate_many_matches_single(engine, oracle):
     assert np.allclose(np.diag(ari), 1.0)
 
 
+@pytest.mark.parametrize("n,d,k,m", [(70001, 40, 30, 7), (1000, 15, 20, 4), (129, 5, 3, 9)])
+def test_bundled_centre_sets_share_one_pass(engine, oracle, n, d, k, m, monkeypatch):
+    """m centre sets against the same cells: the tensor-core pass keeps up to 4 of them resident and multiplies every landed tile
+    with each (Problem::bundle).  Labels must equal the oracle's for every set — with a set of dead rows, a trivial set (one
+    live row: every label 0, Clusterer.cpp:50-53), duplicate rows — and must not depend on how many sets ride together."""
+    rng = np.random.default_rng(n + m)
+    X = blobs(rng, n, d, 6)
+    mus = [blobs(rng, k, d, 6) for _ in range(m)]
+    mus[1][1:] = 0.0                       # trivial under no_zero
+    mus[2][[0, k - 1]] = 0.0               # dead rows
+    mus[3][k - 1] = mus[3][0]              # duplicate: the lower index wins
+    for nz in (True, False):
+        want = [oracle.allocate_points(X, mu, nz) for mu in mus]
+        for sets in ("4", "3", "1"):
+            monkeypatch.setenv("DPR_TC_SETS", sets)
+            lab, _ = engine.allocate_many(X, mus, nz, want_ari=False)
+            for s in range(m):
+                assert np.array_equal(lab[s], want[s]), f"set {s}, {sets} sets per pass, no_zero={nz}: {(lab[s] != want[s]).sum()} labels differ"
+
+
 # ---------------------------------------------------------------------------------------------- edges of the supported range
 @pytest.mark.parametrize("n,d,k", [(63, 1, 2), (64, 1, 3), (65, 2, 2), (1000, 3, 240), (4097, 64, 31), (300, 200, 7)])
 def test_edge_shapes(engine, oracle, n, d, k):

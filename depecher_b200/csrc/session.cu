@@ -37,7 +37,14 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
     if (!plan_pass(d, k_max_, &plan))
         return fail(DPR_ERR_INVALID, "shape not supported by the sm_100a kernels: d = " + std::to_string(d) + ", k = " +
                                          std::to_string(k_max_) + " (one 128-cell slot of d markers plus the centre table must fit in 227 KB)");
-    use_tc = !ctx().force_ffma && plan_tc_pass(d, k_max_, want_sums ? 1 : kTcMaxSets, &tc_plan) != 0;
+    // assignment-only sessions: how many consecutive problems score the same cells (they can share the landed tiles: bundles)
+    int max_run = 1;
+    if (!want_sums)
+        for (size_t p = 1, run = 1; p < specs.size(); ++p) {
+            run = (specs[p].x == specs[p - 1].x && specs[p].n == specs[p - 1].n && specs[p].tile_xx == specs[p - 1].tile_xx && specs[p].xx_max == specs[p - 1].xx_max) ? run + 1 : 1;
+            max_run = std::max(max_run, (int)run);
+        }
+    use_tc = !ctx().force_ffma && plan_tc_pass(d, k_max_, std::min(max_run, kTcMaxSets), &tc_plan) != 0;
     const int P = (int)specs.size();
     h_problems.assign(P, Problem{});
     // pooled per-problem storage

@@ -508,6 +508,8 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
             const int64_t mycell = (int64_t)(tile + j - pr.first_tile) * kSlotCells + mycell_in_tile;
             const bool live = mycell < pr.n;
             const float xx_tile = pr.tile_xx[tile + j - pr.first_tile];
+            int oldl_early = 0;   // one set per tile: the previous label is fetched here, behind the split
+            if (!kMulti && need_old && live) oldl_early = labels_q[mycell];
             DPR_PROF(0);
             mbar_wait_hint(&full[s], full_par, T.wait_hint);
             DPR_PROF(1);
@@ -543,8 +545,8 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                 labels_q = set_ref[q].labels;
                 if (q > 0) ++k_mine;   // (the loop header counts one completion of mma_done per tile)
             }
-            oldl = 0;
-            if (need_old && live) oldl = labels_q[mycell];
+            oldl = oldl_early;
+            if (kMulti && need_old && live) oldl = labels_q[mycell];
             mbar_wait_hint(&mma_done[grp], k_mine & 1u, T.wait_hint);
             tc_fence_after();
             DPR_PROF(3);

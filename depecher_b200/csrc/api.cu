@@ -1,6 +1,7 @@
 // api.cu — the C ABI (include/depecher_b200.h): context, resident datasets and the entry points that
 // replace the reference's four Rcpp exports (/root/reference/src/InterfaceUtils.cpp:66-161).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>

@@ -211,17 +211,14 @@ __global__ void reduce_partials_kernel(const Problem* problems, const int32_t* c
 // ---------------------------------------------------------------------------------------------------
 // finalize: one CTA per problem.  iter = index i of the assignment that just ran.
 // ---------------------------------------------------------------------------------------------------
-__global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_seg, int k_max, int iter, int max_iter, int table_cap,
-                                int allow_delta, int32_t* n_active_out, int mu_in_smem) {
-    const int p = blockIdx.x;
-    Problem pr = problems[p];
-    if (pr.done) return;
+// `in`: n_seg tables of this problem ([k_max*d sums][k_max counts][1 changed] each), summed in segment order; s_mu: shared memory
+// for the new centres when they fit (mu_in_smem): later phases read them there instead of through L2
+__device__ void finalize_body(Problem* problems, int p, const Problem& pr, const double* in, int n_seg, int k_max, int iter, int max_iter, int table_cap,
+                              int allow_delta, int32_t* n_active_out, int mu_in_smem, double* s_mu) {
     const int k = pr.k, d = pr.d;
     const int64_t stride = (int64_t)k_max * d;
     const int64_t entries = stride + k_max + 1;
-    const double* in = seg_in + (int64_t)p * n_seg * entries;
     __shared__ long long s_changed;
-    extern __shared__ double s_mu[];   // the new centres, when they fit (mu_in_smem): later phases read them here instead of through L2
     // totals in fixed segment order
     for (int64_t e = threadIdx.x; e < entries; e += blockDim.x) {
         double acc = 0.0;
@@ -276,6 +273,97 @@ __global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_s
     __syncthreads();
     build_centre_table(pr, mu_in_smem ? s_mu : pr.mu, pr.no_zero, table_cap);
     if (threadIdx.x == 0 && n_active_out && !(iter + 1 >= max_iter)) atomicAdd(n_active_out, 1);
+}
+
+__global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_seg, int k_max, int iter, int max_iter, int table_cap,
+                                int allow_delta, int32_t* n_active_out, int mu_in_smem) {
+    const int p = blockIdx.x;
+    const Problem pr = problems[p];
+    if (pr.done) return;
+    extern __shared__ double s_dyn[];
+    const int64_t entries = (int64_t)k_max * pr.d + k_max + 1;
+    finalize_body(problems, p, pr, seg_in + (int64_t)p * n_seg * entries, n_seg, k_max, iter, max_iter, table_cap, allow_delta, n_active_out, mu_in_smem, s_dyn);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// reduce + finalize in one launch (single GPU: nothing to exchange between the two).  A cluster of kFuseCtas CTAs per problem:
+// CTA r adds up the r-th eighth of the (CTA, problem) tables the pass wrote, in ascending CTA order, into its shared memory;
+// after the cluster barrier CTA 0 adds the eight partial tables in rank order through distributed shared memory and carries on
+// as finalize_kernel does.  Every order is fixed: results are bit-reproducible.
+// n_active: two counters; iteration i counts the problems still running in n_active[i & 1] and clears the other one.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kFuseCtas = 8;
+__global__ void __cluster_dims__(kFuseCtas, 1, 1) reduce_finalize_kernel(Problem* problems, const int32_t* cta_tile_start, int grid_ctas, const double* cta_tables,
+                                                                        int k_max, int iter, int max_iter, int table_cap, int allow_delta,
+                                                                        int32_t* n_active2, int mu_in_smem) {
+    const int p = blockIdx.y;
+    const unsigned r = blockIdx.x;   // rank in the cluster
+    const Problem pr = problems[p];
+    extern __shared__ double s_dyn[];
+    const int64_t entries = (int64_t)k_max * pr.d + k_max + 1;
+    double* s_mu = s_dyn;
+    double* s_part = s_dyn + (mu_in_smem ? (size_t)k_max * pr.d : 0);   // this CTA's partial table; in CTA 0 later the total
+    if (p == 0 && r == 0 && threadIdx.x == 0) n_active2[(iter + 1) & 1] = 0;
+    if (!pr.done) {
+        const int t0 = pr.first_tile, t1 = pr.first_tile + pr.n_tiles;
+        // the CTAs of the pass whose tile range touches the problem are consecutive: [ca, cb)
+        __shared__ int s_ca, s_cb;
+        if (threadIdx.x == 0) {
+            s_ca = grid_ctas;
+            s_cb = 0;
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < grid_ctas; c += blockDim.x) {
+            const int a = cta_tile_start[c], b = cta_tile_start[c + 1];
+            if (a >= t1 || b <= t0 || a >= b) continue;
+            atomicMin(&s_ca, c);
+            atomicMax(&s_cb, c + 1);
+        }
+        __syncthreads();
+        const int ca = s_ca, cb = max(s_cb, s_ca);
+        const int c0 = ca + (int)((int64_t)(cb - ca) * r / kFuseCtas), c1 = ca + (int)((int64_t)(cb - ca) * (r + 1) / kFuseCtas);
+        for (int64_t e = threadIdx.x; e < entries; e += blockDim.x) {
+            double acc = 0.0;
+            for (int c = c0; c < c1; c += 8) {   // 8 loads in flight, then the fixed-order sum
+                double v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int cc = c + q;
+                    bool use = cc < c1;
+                    if (use) {
+                        const int a = cta_tile_start[cc], b = cta_tile_start[cc + 1];
+                        use = !(a >= t1 || b <= t0 || a >= b);
+                    }
+                    v[q] = use ? cta_tables[(size_t)(cc + p) * entries + e] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc += v[q];
+            }
+            s_part[e] = acc;
+        }
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (r == 0 && !pr.done) {
+        const uint32_t mine = (uint32_t)__cvta_generic_to_shared(s_part);
+        for (int64_t e = threadIdx.x; e < entries; e += blockDim.x) {
+            double v[kFuseCtas];
+#pragma unroll
+            for (int q = 0; q < kFuseCtas; ++q) {   // partial table of CTA q of the cluster
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(mine + (uint32_t)(e * 8)), "r"(q));
+                asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v[q]) : "r"(remote));
+            }
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < kFuseCtas; ++q) acc += v[q];
+            s_part[e] = acc;   // (each thread overwrites only the entries it has just read from its own table)
+        }
+    }
+    // the other CTAs' tables must stay alive until CTA 0 has read them
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (r != 0 || pr.done) return;
+    __syncthreads();
+    finalize_body(problems, p, pr, s_part, 1, k_max, iter, max_iter, table_cap, allow_delta, n_active2 + (iter & 1), mu_in_smem, s_mu);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -353,6 +441,28 @@ int launch_finalize(Problem* d_problems, int n_problems, const double* seg_in, i
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
+}
+
+int launch_reduce_finalize(Problem* d_problems, int n_problems, const int32_t* cta_tile_start, int grid_ctas, const double* cta_tables, int k_max, int d,
+                           int iter, int max_iter, int table_cap, int allow_delta, int32_t* n_active2, cudaStream_t st) {
+    const size_t mu_bytes = (size_t)k_max * d * sizeof(double);
+    const int mu_in_smem = mu_bytes <= 64 * 1024;
+    const size_t part_bytes = ((size_t)k_max * d + k_max + 1) * sizeof(double);
+    const size_t smem = (mu_in_smem ? mu_bytes : 0) + part_bytes;
+    static bool configured = false;
+    if (!configured) {
+        DPR_CUDA(cudaFuncSetAttribute(reduce_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = true;
+    }
+    dim3 g(kFuseCtas, n_problems);
+    reduce_finalize_kernel<<<g, 512, smem, st>>>(d_problems, cta_tile_start, grid_ctas, cta_tables, k_max, iter, max_iter, table_cap, allow_delta, n_active2, mu_in_smem);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+bool reduce_finalize_fits(int k_max, int d) {
+    const size_t mu_bytes = (size_t)k_max * d * sizeof(double);
+    return (mu_bytes <= 64 * 1024 ? mu_bytes : 0) + ((size_t)k_max * d + k_max + 1) * sizeof(double) <= 160 * 1024;
 }
 
 int launch_partition(const Problem* d_problems, int n_problems, int grid_ctas, int total_tiles, int32_t* cta_tile_start, cudaStream_t st) {

@@ -133,7 +133,7 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
         DPR_TRY(alloc(&warp_counts_, wtabs * k_max_, true));
         DPR_TRY(alloc(&cta_tables_, (size_t)(grid + P) * seg_entries, true));
         DPR_TRY(alloc(&seg, (size_t)P * n_seg * seg_entries, true));
-        DPR_TRY(alloc(&d_n_active_, (size_t)1, true));
+        DPR_TRY(alloc(&d_n_active_, (size_t)2, true));   // [0] alone on the two-kernel path; the fused reduce + finalize alternates between the two
         if (use_tc) {
             // lists of moved cells of the delta iterations: one per consumer warp, sized for "every cell of the warp's tiles moves".
             // A warp sees at most ceil(tiles of a problem range / groups) tiles per (CTA, problem) range, 32 cells of each.
@@ -207,10 +207,21 @@ int Session::pass(int mode, bool compare_old) {
 }
 
 int Session::reduce_and_finalize(int iter, int max_iter) {
+    if (fused_finalize()) {   // one GPU: nothing to exchange between the two steps
+        last_active_slot_ = iter & 1;
+        return launch_reduce_finalize(d_problems, n_problems(), d_cta_start_, grid, cta_tables_, k_max_, d_, iter, max_iter, plan.table_floats_cap,
+                                      allow_delta ? 1 : 0, d_n_active_, ctx().stream);
+    }
+    last_active_slot_ = 0;
     DPR_TRY(launch_reduce_partials(d_problems, n_problems(), d_cta_start_, grid, k_max_, d_, cta_tables_, seg, n_seg, d_n_active_, ctx().stream));
     if (ctx().world > 1) DPR_TRY(comm_allreduce_sum_f64(seg, (size_t)n_problems() * n_seg * seg_entries));
     return launch_finalize(d_problems, n_problems(), seg, n_seg, k_max_, d_, iter, max_iter, plan.table_floats_cap, allow_delta ? 1 : 0, d_n_active_,
                            ctx().stream);
+}
+
+bool Session::fused_finalize() const {
+    static const bool off = getenv("DPR_TWO_KERNEL_FINALIZE") != nullptr;   // A/B aid
+    return ctx().world == 1 && !off && reduce_finalize_fits(k_max_, d_);
 }
 
 int Session::zero_labels() {
@@ -227,7 +238,7 @@ int Session::lloyd(int max_iter) {
         DPR_TRY(pass(kPassLloyd, true));
         DPR_TRY(reduce_and_finalize(i, max_iter));
         if (i > 20) {
-            DPR_CUDA(cudaMemcpyAsync(h_n_active_, d_n_active_, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx().stream));
+            DPR_CUDA(cudaMemcpyAsync(h_n_active_, d_n_active_ + last_active_slot_, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx().stream));
             DPR_CUDA(cudaStreamSynchronize(ctx().stream));
             if (*h_n_active_ == 0) break;
             // some fits of the batch have converged: give their CTAs' time to the ones still running

@@ -76,6 +76,8 @@ private:
     int32_t* move_overflow_ = nullptr;
     int64_t move_cap_ = 0;
     int32_t* h_n_active_ = nullptr;  // pinned
+    int last_active_slot_ = 0;       // which of the two device counters the last finalize counted in
+    bool fused_finalize() const;     // single GPU and the tables fit: reduce + finalize in one launch
     template <typename T> int alloc(T** p, size_t count, bool zero);
 };
 

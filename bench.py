@@ -18,7 +18,8 @@ soft-threshold centre update (allocate_clusters + reevaluate_centers, /root/refe
             bounded sample on the host cores, one single-threaded engine per worker like the reference's
             SOCK workers (R/depeche.R:169-174)
 N > 1: rows are sharded (every rank holds its own 10M x 40 shard: weak scaling) and each iteration
-allreduces the K x (D+1) partial sums/counts with NCCL; value = all ranks' cells x K x steps / max time.
+exchanges the K x (D+1) partial sums/counts between the ranks — inside the reduce + finalize launch, through peer-memory
+mailboxes over NVLink (ncclAllReduce when they cannot be set up); value = all ranks' cells x K x steps / max time.
 """
 from __future__ import annotations
 
@@ -325,7 +326,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             line["e2e"] = {"value": float(n_local) * world * K * res["n_iter"] / dt, "unit": UNIT, "h2d_bytes_per_step": int(Xh.nbytes) * world,
                            "d2h_bytes_per_step": int(res["i"].nbytes + res["c"].nbytes) * world, "seconds": dt, "lloyd_iterations": res["n_iter"],
                            "call": "dpr_dataset_create(host double*) + dpr_dataset_find_centers_from(...) on every rank's row shard - H2D, row-sharded "
-                                   "Lloyd loop (NCCL allreduce per iteration), D2H inside; max over ranks"}
+                                   "Lloyd loop (per-iteration exchange of the K x (D+1) tables through peer memory, ncclAllReduce as fallback), D2H inside; max over ranks"}
         del Xh
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -404,5 +404,19 @@ class Engine:
     def comm_init(self, rank: int, world: int, unique_id: bytes | None, nccl_path: str | None = None) -> None:
         self._chk(self.lib.dpr_comm_init(C.c_int32(rank), C.c_int32(world), unique_id, nccl_path.encode() if nccl_path else None))
 
+    def comm_peer_handle(self) -> bytes:
+        """this rank's mailbox for the peer-memory exchange: its 64-byte CUDA IPC handle"""
+        buf = C.create_string_buffer(64)
+        self._chk(self.lib.dpr_comm_peer_handle(buf))
+        return buf.raw
+
+    def comm_peer_attach(self, handles: list[bytes]) -> None:
+        """handles of all ranks in rank order: the per-iteration exchange then goes through peer memory instead of ncclAllReduce"""
+        blob = b"".join(handles)
+        self._chk(self.lib.dpr_comm_peer_attach(blob, C.c_int32(len(handles))))
+
+    def comm_peer_detach(self) -> None:
+        self._chk(self.lib.dpr_comm_peer_detach())
+
     def comm_destroy(self) -> None:
         self._chk(self.lib.dpr_comm_destroy())

@@ -9,6 +9,8 @@
 //   labels did not change AND i > 20; penalty ramp reg*((float)i/(float)20) capped at reg).
 #include "centres.cuh"
 
+#include "comm.cuh"
+
 #include <cuda_fp16.h>
 
 namespace dpr {
@@ -295,7 +297,7 @@ __global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_s
 constexpr int kFuseCtas = 8;
 __global__ void __cluster_dims__(kFuseCtas, 1, 1) reduce_finalize_kernel(Problem* problems, const int32_t* cta_tile_start, int grid_ctas, const double* cta_tables,
                                                                         int k_max, int iter, int max_iter, int table_cap, int allow_delta,
-                                                                        int32_t* n_active2, int mu_in_smem) {
+                                                                        int32_t* n_active2, int mu_in_smem, const PeerExchange px) {
     const int p = blockIdx.y;
     const unsigned r = blockIdx.x;   // rank in the cluster
     const Problem pr = problems[p];
@@ -363,6 +365,46 @@ __global__ void __cluster_dims__(kFuseCtas, 1, 1) reduce_finalize_kernel(Problem
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     if (r != 0 || pr.done) return;
     __syncthreads();
+    if (px.world > 1) {
+        // rows sharded over ranks: this rank's table goes into every rank's mailbox over NVLink (plain peer stores), then the
+        // flag of this (source, problem) is raised there; the tables of all ranks are then read out of the own mailbox and added
+        // in rank order — every rank forms the same sum.  Mailboxes alternate with the parity of the exchange number: a rank can
+        // only be one exchange ahead of the slowest one, because it needs that one's flag to finish its own.
+        const unsigned par = (unsigned)(px.seq & 1ull);
+        const size_t slot = ((size_t)par * kMaxPeers + px.rank) * kPeerDoubles + (size_t)p * entries;
+        for (int q = 0; q < px.world; ++q)
+            for (int64_t e = threadIdx.x; e < entries; e += blockDim.x) px.tables[q][slot + e] = s_part[e];
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < px.world) {
+            unsigned long long* f = px.flags[threadIdx.x] + ((size_t)par * kMaxPeers + px.rank) * kPeerFlags + p;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(px.seq) : "memory");
+        }
+        if (threadIdx.x < px.world) {   // wait for source `threadIdx.x`
+            const unsigned long long* f = px.flags[px.rank] + ((size_t)par * kMaxPeers + threadIdx.x) * kPeerFlags + p;
+            unsigned long long v = 0;
+            const long long t0 = clock64();
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                if (v != px.seq && clock64() - t0 > (20ll << 30)) {   // ~10 s: a rank is missing — give up instead of hanging the GPU
+                    *px.failed = 1;
+                    break;
+                }
+            } while (v != px.seq);
+        }
+        __syncthreads();
+        const double* mine = px.tables[px.rank] + (size_t)par * kMaxPeers * kPeerDoubles + (size_t)p * entries;
+        for (int64_t e = threadIdx.x; e < entries; e += blockDim.x) {
+            double v[kMaxPeers];
+#pragma unroll
+            for (int q = 0; q < kMaxPeers; ++q) v[q] = q < px.world ? __ldcg(mine + (size_t)q * kPeerDoubles + e) : 0.0;
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < kMaxPeers; ++q) acc += v[q];
+            s_part[e] = acc;
+        }
+        __syncthreads();
+    }
     finalize_body(problems, p, pr, s_part, 1, k_max, iter, max_iter, table_cap, allow_delta, n_active2 + (iter & 1), mu_in_smem, s_mu);
 }
 
@@ -445,6 +487,9 @@ int launch_finalize(Problem* d_problems, int n_problems, const double* seg_in, i
 
 int launch_reduce_finalize(Problem* d_problems, int n_problems, const int32_t* cta_tile_start, int grid_ctas, const double* cta_tables, int k_max, int d,
                            int iter, int max_iter, int table_cap, int allow_delta, int32_t* n_active2, cudaStream_t st) {
+    PeerExchange px{};
+    px.world = 1;
+    if (ctx().world > 1) DPR_TRY(peer_exchange_next(&px));
     const size_t mu_bytes = (size_t)k_max * d * sizeof(double);
     const int mu_in_smem = mu_bytes <= 64 * 1024;
     const size_t part_bytes = ((size_t)k_max * d + k_max + 1) * sizeof(double);
@@ -455,10 +500,13 @@ int launch_reduce_finalize(Problem* d_problems, int n_problems, const int32_t* c
         configured = true;
     }
     dim3 g(kFuseCtas, n_problems);
-    reduce_finalize_kernel<<<g, 512, smem, st>>>(d_problems, cta_tile_start, grid_ctas, cta_tables, k_max, iter, max_iter, table_cap, allow_delta, n_active2, mu_in_smem);
+    reduce_finalize_kernel<<<g, 512, smem, st>>>(d_problems, cta_tile_start, grid_ctas, cta_tables, k_max, iter, max_iter, table_cap, allow_delta, n_active2, mu_in_smem, px);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
+}
+bool reduce_finalize_peer_fits(int n_problems, int k_max, int d) {   // the tables of one exchange fit a mailbox slot
+    return n_problems <= kPeerFlags && (size_t)n_problems * ((size_t)k_max * d + k_max + 1) <= kPeerDoubles;
 }
 bool reduce_finalize_fits(int k_max, int d) {
     const size_t mu_bytes = (size_t)k_max * d * sizeof(double);

@@ -207,7 +207,7 @@ int Session::pass(int mode, bool compare_old) {
 }
 
 int Session::reduce_and_finalize(int iter, int max_iter) {
-    if (fused_finalize()) {   // one GPU: nothing to exchange between the two steps
+    if (fused_finalize()) {   // one GPU: nothing to exchange between the two steps; several: exchanged inside, through peer memory
         last_active_slot_ = iter & 1;
         return launch_reduce_finalize(d_problems, n_problems(), d_cta_start_, grid, cta_tables_, k_max_, d_, iter, max_iter, plan.table_floats_cap,
                                       allow_delta ? 1 : 0, d_n_active_, ctx().stream);
@@ -221,7 +221,9 @@ int Session::reduce_and_finalize(int iter, int max_iter) {
 
 bool Session::fused_finalize() const {
     static const bool off = getenv("DPR_TWO_KERNEL_FINALIZE") != nullptr;   // A/B aid
-    return ctx().world == 1 && !off && reduce_finalize_fits(k_max_, d_);
+    if (off || !reduce_finalize_fits(k_max_, d_)) return false;
+    if (ctx().world == 1) return true;
+    return peer_exchange_ready() && reduce_finalize_peer_fits(n_problems(), k_max_, d_);   // several ranks: the exchange happens inside the launch
 }
 
 int Session::zero_labels() {
@@ -252,6 +254,7 @@ int Session::lloyd(int max_iter) {
 }
 
 int Session::check_lists() {
+    if (ctx().world > 1) DPR_TRY(peer_exchange_check());   // (a peer-memory exchange that timed out)
     if (!move_overflow_) return DPR_OK;
     int32_t flag = 0;
     DPR_CUDA(cudaMemcpyAsync(&flag, move_overflow_, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx().stream));

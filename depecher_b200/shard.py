@@ -10,6 +10,8 @@ Two ways the path shards:
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 
@@ -35,12 +37,36 @@ def soft_threshold_update(sums: np.ndarray, counts: np.ndarray, reg: float) -> n
     return np.where(hi < m0, hi, m0)
 
 
-def init_comm(engine, dist, device=None) -> None:
+def init_comm(engine, dist, device=None, peer=True) -> None:
     """rank 0 makes the NCCL unique id, torch.distributed broadcasts it, every rank joins the communicator"""
     rank, world = dist.get_rank(), dist.get_world_size()
     ids = [engine.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0, device=device)
     engine.comm_init(rank, world, ids[0])
+    # ranks of one node: mailboxes in peer memory for the per-iteration exchange (falls back to ncclAllReduce when unavailable)
+    if peer and 1 < world <= 8 and os.environ.get("DPR_NO_PEER_EXCHANGE") is None and hasattr(engine, "comm_peer_handle"):
+        ok, err = True, ""
+        try:
+            mine = engine.comm_peer_handle()
+        except Exception as exc:   # noqa: BLE001
+            mine, ok, err = None, False, repr(exc)
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        if ok and all(h is not None for h in handles):
+            try:
+                engine.comm_peer_attach(handles)
+            except Exception as exc:   # noqa: BLE001
+                ok, err = False, repr(exc)
+        else:
+            ok = False
+        # all ranks or none: a rank on the NCCL path cannot talk to one on the mailbox path
+        oks = [None] * world
+        dist.all_gather_object(oks, ok)
+        if not all(oks):
+            engine.comm_peer_detach()
+            if rank == 0:
+                import warnings
+                warnings.warn(f"peer-memory exchange unavailable, using NCCL ({err or 'another rank failed'})")
 
 
 def allreduce_partials(dist, sums: np.ndarray, counts: np.ndarray):

@@ -181,6 +181,13 @@ int dpr_comm_unique_id(void* id128, const char* nccl_path);
 int dpr_comm_init(int32_t rank, int32_t world, const void* id128, const char* nccl_path);
 int dpr_comm_destroy(void);
 int dpr_comm_info(int32_t* rank, int32_t* world);
+/* Optional, ranks on one node (NVLink): the per-iteration exchange of a row-sharded fit through peer memory instead of
+   ncclAllReduce.  Every rank calls dpr_comm_peer_handle (allocates its mailbox, returns its 64-byte CUDA IPC handle), the host
+   gathers the handles in rank order, every rank calls dpr_comm_peer_attach.  Results are identical on every rank (each adds the
+   ranks' tables in rank order).  Without these calls the NCCL path is used. */
+int dpr_comm_peer_handle(void* handle64);
+int dpr_comm_peer_attach(const void* handles, int32_t world);
+int dpr_comm_peer_detach(void);
 
 #ifdef __cplusplus
 }

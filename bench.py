@@ -283,8 +283,12 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         # (kurtosis test, histogram-peak centring, global sd), full default penalty sweep, solution selection, final allocation
         try:
             from depecher_b200 import rapi
-            t0 = time.perf_counter()
-            dep = rapi.depeche(Xh, nCores=10, engine=eng, seed=SEED + 1)
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                rapi.depeche(np.asfortranarray(Xh[:200_000]), nCores=10, engine=eng, seed=SEED)   # warm-up (kernel modules, staging buffers) on a slice, like the e2e call above
+                t0 = time.perf_counter()
+                dep = rapi.depeche(Xh, nCores=10, engine=eng, seed=SEED + 1)
             line["depeche_call_10Mx40"] = {"seconds": time.perf_counter() - t0, "bestPenalty": dep["penaltyOptList"]["bestPenalty"],
                                            "clusters": int(dep["clusterCenters"].shape[0]),
                                            "workerIterations": dep["penaltyOptList"]["workerIterations"],

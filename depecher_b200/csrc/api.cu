@@ -204,12 +204,19 @@ static void narrow_parallel(const T* src, float* dst, int64_t count, int threads
     for (auto& th : pool) th.join();
 }
 
+// host threads for the narrowing / staging copies: up to 16, and the cores are shared between the ranks of a node
+static int host_copy_threads() {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned per_rank = std::max(2u, hw / (unsigned)std::max(1, ctx().world));
+    return (int)std::min(16u, std::min(hw, per_rank));
+}
+
 template <typename T>
 static int dataset_upload(dpr_dataset* ds, const T* X) {
     const int64_t total = ds->n * ds->d;
     const int64_t chunk = std::min<int64_t>(total, (int64_t)32 << 20);  // elements per stage (128 MB of fp32)
     DPR_TRY(upload_stage(chunk));
-    const int threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const int threads = host_copy_threads();
     int b = 0;
     for (int64_t e0 = 0; e0 < total; e0 += chunk, b ^= 1) {
         const int64_t cnt = std::min(chunk, total - e0);
@@ -613,7 +620,7 @@ int dpr_dataset_create_scaled(const double* X, int64_t n, int32_t d, int32_t log
     {
         const int64_t chunk = std::min<int64_t>(total, (int64_t)16 << 20);
         DPR_TRY(upload_stage(2 * chunk));
-        const int threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        const int threads = host_copy_threads();
         int b = 0;
         for (int64_t e0 = 0; e0 < total; e0 += chunk, b ^= 1) {
             const int64_t cnt = std::min(chunk, total - e0);

@@ -221,7 +221,10 @@ int Session::reduce_and_finalize(int iter, int max_iter) {
 
 bool Session::fused_finalize() const {
     static const bool off = getenv("DPR_TWO_KERNEL_FINALIZE") != nullptr;   // A/B aid
-    if (off || !reduce_finalize_fits(k_max_, d_)) return false;
+    // a few large problems: one launch fewer per iteration matters and the clusters all run at once.  Many small ones (the 440 bootstrap
+    // fits of a penalty-search set): 8 CTAs per problem come in a dozen waves of gang-scheduled clusters — the two plain kernels are faster
+    // (measured: 0.137 vs 0.259 s for the penalty search of depeche() on 10M x 40)
+    if (off || n_problems() > 16 || !reduce_finalize_fits(k_max_, d_)) return false;
     if (ctx().world == 1) return true;
     return peer_exchange_ready() && reduce_finalize_peer_fits(n_problems(), k_max_, d_);   // several ranks: the exchange happens inside the launch
 }

@@ -17,8 +17,11 @@
 //     one group waits for its products the others split or reduce.  tcgen05.ld brings a thread its cell's scores;
 //     the two smallest are kept with the centre index packed into the 4 low mantissa bits, and a cell whose two
 //     best scores are closer than the error bound is re-decided in fp64 exactly as the reference does — labels stay
-//     bit-exact.  Lloyd mode then adds the cell to fp64 tables in a fixed order (group tables in shared memory for
-//     the full-sums first iteration, per-warp tables in global memory for the later delta iterations).
+//     bit-exact.  Lloyd mode: the first iteration of a fit adds every cell to fp64 tables in a fixed order (group tables in
+//     shared memory); every later iteration only RECORDS the cells whose label changed in per-warp lists, and
+//     delta_sums_kernel (below) adds their rows (+ to the new label, - to the old one) afterwards.
+//   * Assignment-only sessions: up to four centre sets that score the same cells (the penalty search's scoring step) ride
+//     on one landed tile (bundles): split once, multiplied with one set after the other.
 //   * Single-thread instructions (tcgen05.mma, cp.async.bulk) are issued under elect.sync from converged warps so
 //     that their operands stay in uniform registers.
 //

@@ -102,3 +102,20 @@ def test_device_prescaling_matches_host(engine, testdata):
     ds.close()
     assert winfo[0] is True and info[0] is True
     assert np.allclose(info[1], winfo[1], atol=1e-9) and np.allclose(got, want, rtol=3e-6, atol=1e-6)
+
+
+def test_peer_mailbox_setup_and_error_paths(engine):
+    """dpr_comm_peer_*: a rank can always make its mailbox and hand out the 64-byte CUDA IPC handle; attaching needs a communicator of
+    2..8 ranks and one handle per rank — anything else fails loudly and leaves the library on the NCCL / single-GPU path"""
+    h = engine.comm_peer_handle()
+    assert isinstance(h, bytes) and len(h) == 64 and any(h)
+    with pytest.raises(Exception):
+        engine.comm_peer_attach([h])            # world is 1: nothing to attach to
+    with pytest.raises(Exception):
+        engine.comm_peer_attach([h, h, h])      # not the communicator's size
+    engine.comm_peer_detach()
+    # the single-GPU path is untouched
+    rng = np.random.default_rng(3)
+    X = rng.normal(size=(3000, 8))
+    res = engine.sparse_k_means(X, 5, 1.0, True, seed_off_set=2)
+    assert res["i"].shape == (3000,)

@@ -112,3 +112,67 @@ def test_grid_split_two_ranks_same_state_machine():
     best, ari, ncl, ncent = res[0][1:]
     pos = [0, 4, 16, 64].index(best)
     assert ncl[pos] == 2 and ari[pos] == 1 and ncent >= 2 * 20
+
+
+class _FakeEngine:
+    """records what shard.init_comm does to an engine; `fail_attach_on` makes one rank's mailbox attach fail"""
+
+    def __init__(self, rank, fail_attach_on=None, fail_handle_on=None):
+        self.rank, self.fail_attach_on, self.fail_handle_on = rank, fail_attach_on, fail_handle_on
+        self.log = []
+
+    def comm_unique_id(self):
+        return b"u" * 128
+
+    def comm_init(self, rank, world, uid):
+        self.log.append(("init", rank, world, uid))
+
+    def comm_peer_handle(self):
+        if self.rank == self.fail_handle_on:
+            raise RuntimeError("no IPC here")
+        return bytes([self.rank]) * 64
+
+    def comm_peer_attach(self, handles):
+        if self.rank == self.fail_attach_on:
+            raise RuntimeError("peer access denied")
+        self.log.append(("attach", tuple(handles)))
+
+    def comm_peer_detach(self):
+        self.log.append(("detach",))
+
+
+def _init_comm_worker(rank, world, port, q, fail_attach_on, fail_handle_on):
+    import warnings
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        eng = _FakeEngine(rank, fail_attach_on, fail_handle_on)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            shard.init_comm(eng, dist)
+        q.put((rank, eng.log))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_attach_on,fail_handle_on", [(None, None), (1, None), (None, 0)])
+def test_init_comm_peer_mailboxes_all_ranks_or_none(fail_attach_on, fail_handle_on):
+    """shard.init_comm: every rank joins the communicator with rank 0's id; the peer-memory mailboxes are attached on ALL ranks (handles in
+    rank order) or, if any rank fails, detached on all — a rank on the NCCL path cannot talk to one on the mailbox path"""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_init_comm_worker, args=(r, world, port, q, fail_attach_on, fail_handle_on)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, log in res:
+        assert log[0] == ("init", rank, world, b"u" * 128)
+        kinds = [e[0] for e in log[1:]]
+        if fail_attach_on is None and fail_handle_on is None:
+            assert kinds == ["attach"] and log[1][1] == (bytes([0]) * 64, bytes([1]) * 64)
+        else:
+            assert kinds[-1] == "detach" and kinds.count("detach") == 1

@@ -485,8 +485,10 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
         // sum|x_j c_j| <= (||x||^2 + ||c||^2) / 2 and doubled by the factor -2.  The sum of the two accumulator halves, the
         // un-scaling fma and cc add 4 * 2^-24; twice all that for a difference of two scores, plus the 4 masked index bits
         // (2 * 2^-19); the absolute part of the split error (fp16 subnormals) comes through tc_abs1 / tc_abs2.
-        const float eps = 3.f * 2.3841858e-7f + (float)(g16 + 1) * 4.7683716e-7f + 4.f * 5.9604645e-8f;
-        const float tau_c = 2.f * eps + 3.8146973e-6f;
+        // Per score k the first two parts are bounded by (||x||^2 + ||c_k||^2), the last part and the index bits by |score| <=
+        // ||x||^2 + 2 ||c_k||^2; for a pair of scores: tau = tau_a (X + cc_max) + tau_b (X + 2 cc_max).
+        const float tau_a = 2.f * (3.f * 2.3841858e-7f + (float)(g16 + 1) * 4.7683716e-7f);
+        const float tau_b = 2.f * (4.f * 5.9604645e-8f) + 3.8146973e-6f;
         const float scale_x = hdr->tc_scale_x;   // (the same for every set of a bundle: it depends on the cells only)
         float unscale = hdr->tc_unscale, abs1 = hdr->tc_abs1, abs2 = hdr->tc_abs2;
         float cc2 = 2.0f * hdr->cc_max;
@@ -581,7 +583,7 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                     }
                     if (best < prev) bchunk = n0;
                 }
-                const float tau = tau_c * (xx_tile + cc2) + (abs1 * sqrtf(xx_tile) + abs2) + 1e-30f;
+                const float tau = tau_a * (xx_tile + 0.5f * cc2) + tau_b * (xx_tile + cc2) + (abs1 * sqrtf(xx_tile) + abs2) + 1e-30f;
                 const int a = bchunk + (int)(__float_as_uint(best) & 15u);
                 const bool sure = (second - best > tau) && !force_exact;
                 const int32_t* orig_q = reinterpret_cast<const int32_t*>(smem + set_off + T.off_orig);

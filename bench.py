@@ -289,7 +289,10 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                 rapi.depeche(np.asfortranarray(Xh[:200_000]), nCores=10, engine=eng, seed=SEED)   # warm-up (kernel modules, staging buffers) on a slice, like the e2e call above
                 t0 = time.perf_counter()
                 dep = rapi.depeche(Xh, nCores=10, engine=eng, seed=SEED + 1)
-            line["depeche_call_10Mx40"] = {"seconds": time.perf_counter() - t0, "bestPenalty": dep["penaltyOptList"]["bestPenalty"],
+                first = time.perf_counter() - t0      # includes growing the device memory pool by the 3.2 GB of raw doubles + the resident matrix
+                t0 = time.perf_counter()
+                dep = rapi.depeche(Xh, nCores=10, engine=eng, seed=SEED + 1)
+            line["depeche_call_10Mx40"] = {"seconds": time.perf_counter() - t0, "first_call_seconds": first, "bestPenalty": dep["penaltyOptList"]["bestPenalty"],
                                            "clusters": int(dep["clusterCenters"].shape[0]),
                                            "workerIterations": dep["penaltyOptList"]["workerIterations"],
                                            "call": "depecher_b200.rapi.depeche(host double matrix, nCores=10): everything inside"}

@@ -1142,6 +1142,7 @@ static int bench_session(dpr_dataset_t ds, const double* mu, uint32_t k, double 
     pr.no_zero = no_zero;
     pr.done = 0;
     pr.delta = 0;
+    g_bench_session->mark_restart();
     DPR_CUDA(cudaMemcpyAsync(g_bench_session->d_problems, &pr, sizeof(Problem), cudaMemcpyHostToDevice, ctx().stream));
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));
     return g_bench_session->prepare();

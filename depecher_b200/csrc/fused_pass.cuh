@@ -8,12 +8,15 @@ constexpr int kPassAssign = 0;  // labels only           (allocate_clusters, Clu
 constexpr int kPassLloyd = 1;   // labels + sums/counts   (+ the scatter-add of reevaluate_centers, :99-102)
 constexpr int kPassSums = 2;    // sums/counts of the labels already stored (reevaluate_centers for given labels)
 
+constexpr int kPassLloydDelta = 3;  // kernel instance only: kPassLloyd when every running problem accumulates deltas (all but a fit's first pass)
+
 struct PassParams {
     const Problem* problems;
     int32_t n_problems;
     const int32_t* cta_tile_start;  // [grid + 1]: contiguous tile range of each CTA in the global tile order
     int32_t mode;
     int32_t compare_old;            // count labels that differ from the previous ones
+    int32_t all_delta;              // Lloyd mode: no running problem needs full sums (the host knows: a finalize has run since the fits started) -> the delta-only instance
     int32_t bundles;                // some problems share their cells with the next ones (Problem::bundle > 1): the tensor-core pass runs its multi-set instance
     int32_t k_max;                  // rows of the widest centre matrix (table strides)
     int64_t part_stride;            // doubles per sum table (k_max * d)

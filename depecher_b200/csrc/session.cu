@@ -187,6 +187,7 @@ int Session::pass(int mode, bool compare_old) {
     P.mode = mode;
     P.compare_old = compare_old ? 1 : 0;
     P.bundles = has_bundles_ ? 1 : 0;
+    P.all_delta = (mode == kPassLloyd && !next_pass_full_ && allow_delta && move_lists_) ? 1 : 0;   // every running problem has had a finalize since its fit began
     P.k_max = k_max_;
     P.part_stride = (int64_t)k_max_ * d_;
     P.warp_sums = warp_sums_;
@@ -207,6 +208,7 @@ int Session::pass(int mode, bool compare_old) {
 }
 
 int Session::reduce_and_finalize(int iter, int max_iter) {
+    next_pass_full_ = false;   // finalize switches every running problem to delta accumulation (when allowed)
     if (fused_finalize()) {   // one GPU: nothing to exchange between the two steps; several: exchanged inside, through peer memory
         last_active_slot_ = iter & 1;
         return launch_reduce_finalize(d_problems, n_problems(), d_cta_start_, grid, cta_tables_, k_max_, d_, iter, max_iter, plan.table_floats_cap,

@@ -42,6 +42,7 @@ public:
     // find_centers loop (Clusterer.cpp:244-252) for all problems; labels must be zeroed by the caller
     int lloyd(int max_iter);
     int fetch_state();                                               // d_problems -> h_problems (synchronises)
+    void mark_restart() { next_pass_full_ = true; }                  // the caller has reset the problems' delta flags: the next Lloyd pass sums all cells again
     int check_lists();                                               // fails when a moved-cell list overflowed (synchronises)
     int zero_labels();
 
@@ -65,6 +66,7 @@ public:
 private:
     int d_ = 0, k_max_ = 0, total_tiles_ = 0;
     bool want_sums_ = false, has_bundles_ = false;
+    bool next_pass_full_ = true;     // no finalize yet since the fits (re)started: their next Lloyd pass is a full one
     std::vector<void*> owned_;
     int32_t* d_cta_start_ = nullptr;
     double* warp_sums_ = nullptr;

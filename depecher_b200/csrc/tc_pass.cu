@@ -215,6 +215,8 @@ struct SetRef {          // what the consumers need of problem p + s of a bundle
 template <int MODE, int kTcGroups, bool kMulti>
 __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(const PassParams P, const TcPlan T) {
     constexpr int kTcWarps = 4 * kTcGroups;
+    constexpr bool kLloyd = MODE == kPassLloyd || MODE == kPassLloydDelta;
+    constexpr bool kDeltaOnly = MODE == kPassLloydDelta;   // no problem of the launch needs full sums: that code is not in this instance
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t_begin = P.cta_tile_start[blockIdx.x], t_end = P.cta_tile_start[blockIdx.x + 1];
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)), "r"((uint32_t)T.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (T.gtab)
+    if (T.gtab && !kDeltaOnly)
         for (int i = threadIdx.x; i < (int)(T.gtab_bytes / 8) * kTcGroups; i += blockDim.x) reinterpret_cast<double*>(smem + T.off_gtab)[i] = 0.0;
     if (groups & 1)   // the split reads marker groups in pairs: the partner of an odd last group is never written by a copy — zero, once
         for (int s = 0; s < S; ++s)
@@ -494,8 +496,9 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
         float cc2 = 2.0f * hdr->cc_max;
         uint32_t set_off = 0;   // byte offset of the current set's tables (bundles)
         int32_t* labels_q = pr.labels;
-        const bool delta = MODE == kPassLloyd && pr.delta;   // (a session that lets finalize set it has allocated the lists)
-        const uint32_t list_begin = list_cursor;
+        const bool delta = kLloyd && (kDeltaOnly || pr.delta);   // (a session that lets finalize set it has allocated the lists)
+        if (delta && lane == 0)   // where this range's entries begin: parked in the warp's scratch (free in delta mode) until the range ends
+            *reinterpret_cast<uint32_t*>(smem + T.off_scratch + (size_t)warp * T.scratch_bytes) = list_cursor;
         const bool need_old = (P.compare_old || delta) && pr.labels;   // (bundles: every member has labels when the leader has)
         int changed = 0;   // per thread: at most one per tile
         const int count = p_end - tile;
@@ -610,14 +613,14 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
             }
             }   // sets
             DPR_PROF(7);
-            if (MODE == kPassLloyd && T.gtab && !delta) {
+            if (kLloyd && !kDeltaOnly && T.gtab && !delta) {
                 // every cell contributes: the four warps of the group publish their labels, meet at the group's barrier, and update
                 // the group's table in shared memory with plain read-modify-writes in a fixed order (no atomics, reproducible)
                 double* gsum = reinterpret_cast<double*>(smem + T.off_gtab + (size_t)grp * T.gtab_bytes);   // this group's table
                 unsigned char* glab = smem + T.off_glist + (size_t)grp * T.glist_bytes;                        // [2][128] labels of a whole tile
                 full_tile_sums(slot, glab + (k_mine & 1u) * 128, gsum, reinterpret_cast<long long*>(gsum + P.part_stride), d, pr.k, grp, wq, lane,
                                mycell_in_tile, lab);
-            } else if (MODE == kPassLloyd && delta) {
+            } else if (kLloyd && delta) {
                 // only the cells whose label changed contribute (+x to the new label, -x to the old one): the warp appends them to
                 // its own list, in tile and lane order; delta_sums_kernel gathers their rows afterwards.  Nothing in this kernel
                 // waits on a moved cell.
@@ -632,7 +635,7 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                     }
                     list_cursor += (uint32_t)__popc(mch);
                 }
-            } else if (MODE == kPassLloyd) {
+            } else if (kLloyd && !kDeltaOnly) {
                 // every cell contributes but the group tables do not fit in shared memory: this warp's private table in global memory
                 const size_t wtab = (size_t)blockIdx.x * kTcWarps + warp;
                 int* wscr = reinterpret_cast<int*>(smem + T.off_scratch + (size_t)warp * T.scratch_bytes);
@@ -657,15 +660,17 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
             const int64_t stride = P.part_stride;
             const int64_t entries = stride + P.k_max + 1;
             double* out = P.cta_tables + (size_t)(blockIdx.x + p) * entries;
-            if (delta) {
+            if (kDeltaOnly || delta) {
                 // sums and counts of this (CTA, problem) come from delta_sums_kernel: hand it the list lengths
-                if (lane == 0) P.move_counts[(size_t)(blockIdx.x + p) * kTcWarps + warp] = (int32_t)(list_cursor - list_begin);
+                if (lane == 0)
+                    P.move_counts[(size_t)(blockIdx.x + p) * kTcWarps + warp] =
+                        (int32_t)(list_cursor - *reinterpret_cast<const uint32_t*>(smem + T.off_scratch + (size_t)warp * T.scratch_bytes));
                 if (threadIdx.x == 0) {
                     long long t = 0;
                     for (int w = 0; w < kTcWarps; ++w) t += s_changed[w];
                     out[entries - 1] = (double)t;
                 }
-            } else {
+            } else if constexpr (!kDeltaOnly) {
                 const size_t wbase = (size_t)blockIdx.x * kTcWarps;
                 const bool wt = !T.gtab && P.warp_sums;   // the per-warp tables in global memory were in use
                 for (int64_t e = threadIdx.x; e < entries; e += kTcWarps * 32) {
@@ -922,7 +927,8 @@ int launch_tc_pass(const TcPlan& plan, const PassParams& P, int grid, cudaStream
 #define DPR_TC_ATTR(G)                                                                                                                   \
     DPR_CUDA(cudaFuncSetAttribute(tc_pass_kernel<kPassAssign, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); \
     DPR_CUDA(cudaFuncSetAttribute(tc_pass_kernel<kPassAssign, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));  \
-    DPR_CUDA(cudaFuncSetAttribute(tc_pass_kernel<kPassLloyd, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    DPR_CUDA(cudaFuncSetAttribute(tc_pass_kernel<kPassLloyd, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));      \
+    DPR_CUDA(cudaFuncSetAttribute(tc_pass_kernel<kPassLloydDelta, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
         DPR_TC_ATTR(2) DPR_TC_ATTR(3) DPR_TC_ATTR(4)
 #undef DPR_TC_ATTR
         configured = true;
@@ -938,6 +944,7 @@ int launch_tc_pass(const TcPlan& plan, const PassParams& P, int grid, cudaStream
     if (plan.groups == G) {                                                                                                       \
         if (P.mode == kPassAssign && P.bundles) tc_pass_kernel<kPassAssign, G, true><<<grid, threads, plan.smem_bytes, stream>>>(P, plan); \
         else if (P.mode == kPassAssign) tc_pass_kernel<kPassAssign, G, false><<<grid, threads, plan.smem_bytes, stream>>>(P, plan);       \
+        else if (P.all_delta) tc_pass_kernel<kPassLloydDelta, G, false><<<grid, threads, plan.smem_bytes, stream>>>(P, plan);                \
         else tc_pass_kernel<kPassLloyd, G, false><<<grid, threads, plan.smem_bytes, stream>>>(P, plan);                               \
     }
     DPR_TC_LAUNCH(2) DPR_TC_LAUNCH(3) DPR_TC_LAUNCH(4)

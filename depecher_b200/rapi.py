@@ -234,7 +234,9 @@ def dAllocate(inDataFrame, depModel, engine=None, columns=None):
         Xr = np.asarray(X)[:, cols]
     if red.ndim == 1:
         red = red[None, :]
-    return eng.allocate_points(Xr, red, 1)["i"].astype(np.int64) + 1             # :127-134
+    lab = eng.allocate_points(Xr, red, 1)["i"].astype(np.int64)
+    lab += 1                                                                     # :127-134 (in place: the vector has one entry per cell)
+    return lab
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -393,11 +395,10 @@ def depeche(inDataFrame, samplingSubset=None, penalties=None, sampleSize="defaul
     else:
         Xs, logCenterSd = depecheLogCenterSd(X, log2Off, center, scale)                         # :141
         n_rows = len(Xs)
-    if samplingSubset is None:
-        samplingSubset = np.arange(n_rows)
-    if len(samplingSubset) > 1e6:                                                               # :150-156
+    n_subset = n_rows if samplingSubset is None else len(samplingSubset)                       # (no index vector for "all rows": 80 MB at 10M rows)
+    if n_subset > 1e6:                                                                          # :150-156
         warnings.warn("This dataset is very large; the reference recommends fitting on a sampling subset and allocating the rest with dAllocate")
-    used = None if device_scaled else Xs[samplingSubset]
+    used = None if device_scaled else (Xs if samplingSubset is None else Xs[samplingSubset])
     n_used = n_rows if device_scaled else len(used)
     if sampleSize == "default":
         sampleSize = n_used if n_used <= 10000 else 10000                                       # :161-167
@@ -425,7 +426,7 @@ def depeche(inDataFrame, samplingSubset=None, penalties=None, sampleSize="defaul
             reduced, cols = r["clusterCenters"], r["cols"]
             if device_scaled and sel is not ds_used:
                 sel.close()
-            ds_all = ds_used if (use_ds and len(samplingSubset) == n_rows) else (eng.dataset(Xs[:, cols]) if use_ds else Xs[:, cols])
+            ds_all = ds_used if (use_ds and n_subset == n_rows) else (eng.dataset(Xs[:, cols]) if use_ds else Xs[:, cols])
             full_cc = np.zeros((reduced.shape[0], X.shape[1]))
             full_cc[:, cols] = reduced
             model_cc = full_cc if ds_all is ds_used else reduced

@@ -376,6 +376,22 @@ def depecheClusterCenterSelection(allSolutions, selectionDataSet, k, nCores=None
     return {"clusterCenters": best[np.ix_(rows, cols)], "rows": rows, "cols": cols, "meanARI": meanARI}
 
 
+def _renumber_by_size(clusterVector, n_centres):
+    """clusters renumbered 1, 2, ... by decreasing size, ties in the order of the old numbers (R/depeche.R:236-252: `sort(table(.), decreasing = TRUE)`
+    and a loop over its names).  Labels are small positive integers, so one counting pass and a lookup table do it - no sort of the vector, no
+    full-length comparison per cluster.  Returns (new vector, old labels in rank order, {old label: new number})."""
+    cv = np.asarray(clusterVector)
+    hist = np.bincount(cv, minlength=n_centres + 1)
+    labels = np.flatnonzero(hist)
+    order = labels[np.argsort(-hist[labels], kind="stable")]
+    lut = np.zeros(len(hist), dtype=cv.dtype)
+    rank_of_label = {}
+    for i, lab in enumerate(order, start=1):
+        lut[lab] = i
+        rank_of_label[lab] = i
+    return lut[cv], order, rank_of_label
+
+
 # --------------------------------------------------------------------------------------------------------
 # depeche: R/depeche.R:127-294
 # --------------------------------------------------------------------------------------------------------
@@ -437,17 +453,7 @@ def depeche(inDataFrame, samplingSubset=None, penalties=None, sampleSize="defaul
         if use_ds:
             ds_used.close()
     # clusters renumbered by size (:236-252)
-    cv = np.asarray(clusterVector)
-    hist = np.bincount(cv, minlength=int(reduced.shape[0]) + 1)          # labels are small positive integers: one counting pass, no sort
-    labels = np.flatnonzero(hist)
-    counts = hist[labels]
-    order = labels[np.argsort(-counts, kind="stable")]
-    lut = np.zeros(len(hist), dtype=cv.dtype)
-    rank_of_label = {}
-    for i, lab in enumerate(order, start=1):
-        lut[lab] = i
-        rank_of_label[lab] = i
-    newVec = lut[cv]
+    newVec, order, rank_of_label = _renumber_by_size(clusterVector, int(reduced.shape[0]))
     sortedLabels = np.sort(order)
     if len(sortedLabels) == reduced.shape[0]:
         reduced = reduced[np.argsort([rank_of_label[l] for l in sortedLabels])]

@@ -114,3 +114,24 @@ def test_testdata_scaling_matches_stored_fixture(testdata):
     Xs, info = rapi.depecheLogCenterSd(X)
     assert info[0] is False and Xs.shape == (20000, 14)
     assert abs(10000 * np.sqrt(14) / 1450 - 25.80) < 0.01
+
+
+def test_renumber_by_size_matches_sort_based_definition():
+    """depeche() renumbers the clusters by decreasing size (R/depeche.R:236-252); the counting implementation must equal the definition
+    through np.unique + one comparison per cluster, including ties in size (old number decides) and unused cluster numbers"""
+    from depecher_b200.rapi import _renumber_by_size
+    rng = np.random.default_rng(8)
+    for trial in range(20):
+        k = int(rng.integers(2, 12))
+        present = np.sort(rng.choice(np.arange(1, k + 1), size=int(rng.integers(1, k + 1)), replace=False))
+        sizes = rng.integers(1, 6, size=len(present)) * 10          # few distinct sizes: ties are common
+        cv = rng.permutation(np.repeat(present, sizes)).astype(np.int64)
+        got, order, rank = _renumber_by_size(cv, k)
+        labels, counts = np.unique(cv, return_counts=True)
+        want_order = labels[np.argsort(-counts, kind="stable")]
+        want = np.zeros_like(cv)
+        for i, lab in enumerate(want_order, start=1):
+            want[cv == lab] = i
+        assert np.array_equal(got, want) and np.array_equal(order, want_order)
+        assert rank == {int(lab): i for i, lab in enumerate(want_order, start=1)}
+        assert got.dtype == cv.dtype and np.array_equal(np.bincount(got)[1:], np.sort(counts)[::-1])

@@ -6,6 +6,6 @@ Only what the path needs lives here:
   rapi.py      host-side mirror of the reference's R callers of the path: depeche(), dAllocate(),
                depechePenaltyOpt(), depecheAllData(), depecheClusterCenterSelection()
 """
-from ._capi import ARI_EXACT, ARI_MONTE_CARLO, Dataset, DepecherError, DeviceError, Engine, declared_symbols, load_library  # noqa: F401
+from ._capi import ARI_EXACT, ARI_MONTE_CARLO, Dataset, DepecherError, DeviceError, Engine, PenaltyOpt, declared_symbols, load_library  # noqa: F401
 
-__all__ = ["Engine", "Dataset", "DepecherError", "DeviceError", "ARI_EXACT", "ARI_MONTE_CARLO", "declared_symbols", "load_library"]
+__all__ = ["Engine", "Dataset", "PenaltyOpt", "DepecherError", "DeviceError", "ARI_EXACT", "ARI_MONTE_CARLO", "declared_symbols", "load_library"]

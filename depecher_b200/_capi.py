@@ -83,6 +83,73 @@ class Dataset:
         self.close()
 
 
+class PenaltyOpt:
+    """depechePenaltyOpt's state machine (dpr_penalty_opt_*; R/depechePenaltyOpt.R:14-265).  Pure host code inside the library:
+    usable without a device, with any producer of the sets (`used()` -> results of one set -> `feed()`)."""
+
+    def __init__(self, penalties, k: int, d: int, sampleSize: int, nCores: int, maxIter: int, minARIImprovement: float, optimARI: float,
+                 lib: C.CDLL | None = None):
+        self.lib = lib or load_library()
+        self.penalties = np.ascontiguousarray(np.atleast_1d(penalties), dtype=np.float64)
+        self.k, self.d, self.nCores = int(k), int(d), int(nCores)
+        self.handle = C.c_void_p()
+        self._chk(self.lib.dpr_penalty_opt_create(_ptr(self.penalties, _dp), C.c_int32(len(self.penalties)), C.c_int32(k), C.c_int32(d),
+                                                  C.c_uint32(sampleSize), C.c_int32(nCores), C.c_int32(maxIter), C.c_double(minARIImprovement),
+                                                  C.c_double(optimARI), C.byref(self.handle)))
+
+    def _chk(self, rc: int) -> None:
+        if rc != 0:
+            raise DepecherError(f"[{rc}] {(self.lib.dpr_last_error() or b'').decode()}")
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.dpr_penalty_opt_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def used(self):
+        """(positions of the penalties still in use, their scaled values for grid_search, loop continues?)"""
+        n, cont = C.c_int32(), C.c_int32()
+        pos = np.empty(len(self.penalties), np.int32)
+        reg = np.empty(len(self.penalties), np.float64)
+        self._chk(self.lib.dpr_penalty_opt_used(self.handle, C.byref(n), _ptr(pos, _ip), _ptr(reg, _dp), C.byref(cont)))
+        return pos[:n.value].copy(), reg[:n.value].copy(), bool(cont.value)
+
+    def feed(self, ari_each, nclust_each, centres=None) -> bool:
+        """one set: (nCores, n_used) ARI and cluster-count arrays, centres (nCores, n_used, 2, k, d) or None; returns `continue`"""
+        a = np.ascontiguousarray(ari_each, dtype=np.float64)
+        m = np.ascontiguousarray(nclust_each, dtype=np.float64)
+        cont = C.c_int32()
+        n_used = len(self.used()[0])
+        if a.shape != (self.nCores, n_used) or m.shape != (self.nCores, n_used):
+            raise DepecherError(f"feed: expected {(self.nCores, n_used)} ARI / cluster-count arrays, got {a.shape} and {m.shape}")
+        cp = None
+        if centres is not None:
+            if np.shape(centres) != (self.nCores, n_used, 2, self.k, self.d):
+                raise DepecherError(f"feed: expected centres of shape {(self.nCores, n_used, 2, self.k, self.d)}, got {np.shape(centres)}")
+            cen = np.ascontiguousarray(np.asarray(centres, dtype=np.float64).transpose(0, 1, 2, 4, 3))   # k x d col-major per matrix
+            cp = _ptr(cen, _dp)
+        self._chk(self.lib.dpr_penalty_opt_feed(self.handle, _ptr(a, _dp), _ptr(m, _dp), cp, C.byref(cont)))
+        return bool(cont.value)
+
+    def result(self) -> dict:
+        n_pen = len(self.penalties)
+        best, pos, wi, ns, warn = C.c_double(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        ari, ncl = np.empty(n_pen), np.empty(n_pen)
+        self._chk(self.lib.dpr_penalty_opt_result(self.handle, C.byref(best), C.byref(pos), _ptr(ari, _dp), _ptr(ncl, _dp), C.byref(wi), C.byref(ns),
+                                                  C.byref(warn)))
+        sol = np.empty((ns.value, self.d, self.k), np.float64)
+        if ns.value:
+            self._chk(self.lib.dpr_penalty_opt_solutions(self.handle, _ptr(sol, _dp)))
+        return {"bestPenalty": best.value, "bestPenaltyPosition": pos.value, "meanARI": ari, "meanClust": ncl, "workerIterations": wi.value,
+                "bestClusterCenters": [np.array(m.T) for m in sol], "warn": warn.value}
+
+
 class Engine:
     """Thin object wrapper over the C ABI; one per process (the library keeps one CUDA context)."""
 
@@ -296,6 +363,36 @@ class Engine:
                     per.append(mats + mats)
             c.append(per)
         return {"d": z, "z": z, "n": m, "m": m, "c": c}
+
+    def grid_search_range(self, ds: Dataset, k: int, reg, iterations: int, bootstrapSamples: int, seed_off_set: int, first: int, count: int):
+        """problems [first, first + count) of the (worker, penalty) grid of one k -> (ari[count], nclust[count], centres[count, 2, k, d])"""
+        reg = np.ascontiguousarray(np.atleast_1d(reg), dtype=np.float64)
+        kk = _i32([k])
+        ari, ncl = np.empty(count), np.empty(count)
+        cen = np.empty((count, 2, ds.d, k), np.float64)
+        self._chk(self.lib.dpr_dataset_grid_search_range(ds.handle, _ptr(kk, _ip), C.c_int32(1), _ptr(reg, _dp), C.c_int32(len(reg)), C.c_uint32(iterations),
+                                                         C.c_uint32(bootstrapSamples), C.c_uint64(seed_off_set), C.c_int32(first), C.c_int32(count),
+                                                         _ptr(ari, _dp), _ptr(ncl, _dp), _ptr(cen, _dp)))
+        return ari, ncl, cen.transpose(0, 1, 3, 2).copy()
+
+    def penalty_opt(self, ds: Dataset, opt: PenaltyOpt, seed: int = 0, split_over_ranks: bool = False) -> None:
+        """the whole adaptive search of depechePenaltyOpt on a resident dataset in ONE call (dpr_dataset_penalty_opt)"""
+        self._chk(self.lib.dpr_dataset_penalty_opt(ds.handle, opt.handle, C.c_uint64(seed), C.c_int32(int(split_over_ranks))))
+
+    def select_solution(self, selection_set, solutions):
+        """depecheClusterCenterSelection.R:11-37 -> (index of the most central solution, mean ARI of each)"""
+        sols = [np.asarray(m, dtype=np.float64) for m in solutions]
+        m, k = len(sols), sols[0].shape[0]
+        flat = np.concatenate([np.asfortranarray(mm).ravel(order="F") for mm in sols])
+        ds, own = self._as_ds(selection_set)
+        try:
+            best = C.c_int32()
+            mean = np.empty(m, np.float64)
+            self._chk(self.lib.dpr_dataset_select_solution(ds.handle, _ptr(flat, _dp), C.c_int32(m), C.c_int32(k), C.byref(best), _ptr(mean, _dp)))
+        finally:
+            if own:
+                ds.close()
+        return best.value, mean
 
     def rand_index(self, inds1, inds2, k) -> float:
         """rand_index(inds1, inds2, k) -> double   (src/InterfaceUtils.cpp:151-161)"""

@@ -8,6 +8,7 @@
 #include <thread>
 #include <vector>
 
+#include "api_internal.cuh"
 #include "aux_kernels.cuh"
 #include "comm.cuh"
 #include "common.cuh"
@@ -278,7 +279,7 @@ static int copy_labels_out(const int32_t* d_labels, int64_t n, int32_t* host) {
 }
 
 // cluster_norm (Clusterer.cpp:198-211) for problem p of a session
-static int cluster_norm_dev(const Problem& pr, int d, double reg, double* out) {
+static int cluster_norm_dev(const Problem& pr, int d, double reg, double* out, bool row_sharded = false) {
     const int blocks = (int)std::min<int64_t>(148 * 4, (pr.n + 255) / 256);
     DevBuf part;
     DPR_TRY(part.alloc(sizeof(double) * blocks));
@@ -289,6 +290,12 @@ static int cluster_norm_dev(const Problem& pr, int d, double reg, double* out) {
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));
     double ssq = 0.0;
     for (double v : hp) ssq += v;
+    if (row_sharded && ctx().world > 1) {            // rows sharded over ranks: the squared distances of all ranks' cells
+        DPR_CUDA(cudaMemcpyAsync(part.p, &ssq, sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
+        DPR_TRY(comm_allreduce_sum_f64(part.as<double>(), 1));
+        DPR_CUDA(cudaMemcpyAsync(&ssq, part.p, sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+        DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
     for (int j = 0; j < d; ++j)                      // column by column, like the reference (:204-208)
         for (int c = 0; c < pr.k; ++c) ssq += mu[(size_t)c * d + j] * reg;
     *out = ssq;
@@ -371,6 +378,10 @@ static int find_centers_dev(dpr_dataset* ds, const double* init_mu_colmajor, uin
     if (k < 2) return fail(DPR_ERR_INVALID, "k must be >= 2 (initialize_mu writes two rows, Clusterer.cpp:157-162)");
     if (max_iter < 1) return fail(DPR_ERR_INVALID, "max_iter must be >= 1");
     Session s;
+    // several ranks: a fit from GIVEN centres is the row-sharded one (every rank holds a shard and the same initial centres, the tables
+    // are summed over the ranks each iteration); a fit that seeds itself (sparse_k_means) draws its centres from the local cells and
+    // stays local
+    s.row_sharded = init_mu_colmajor != nullptr;
     DPR_TRY(single_session(ds, (int)k, reg, no_zero, true, s));
     if (init_mu_colmajor) {
         std::vector<double> rm;
@@ -393,7 +404,7 @@ static int find_centers_dev(dpr_dataset* ds, const double* init_mu_colmajor, uin
         DPR_TRY(s.get_centres(0, rm.data()));
         rowmajor_to_colmajor(rm, (int)k, ds->d, centers_out);
     }
-    if (norm_out) DPR_TRY(cluster_norm_dev(pr, ds->d, reg, norm_out));
+    if (norm_out) DPR_TRY(cluster_norm_dev(pr, ds->d, reg, norm_out, s.row_sharded));
     return DPR_OK;
 }
 
@@ -872,6 +883,7 @@ int dpr_dataset_reevaluate_centers(dpr_dataset_t ds, const int32_t* idx, uint32_
     for (int64_t i = 0; i < ds->n; ++i)
         if (idx[i] < 0 || (uint32_t)idx[i] >= k) return fail(DPR_ERR_INVALID, "label outside [0, k)");
     Session s;
+    s.row_sharded = true;   // several ranks: one update from the labels of every rank's shard
     DPR_TRY(single_session(ds, (int)k, reg, 0, true, s));
     DPR_CUDA(cudaMemcpyAsync(ds->labels, idx, sizeof(int32_t) * ds->n, cudaMemcpyHostToDevice, ctx().stream));
     DPR_TRY(s.prepare());
@@ -952,31 +964,35 @@ int dpr_rand_index(const int32_t* a, const int32_t* b, int64_t n, uint32_t k, do
 // are discarded (:373-374) are not performed.
 }  // extern "C"
 
-static int grid_search_impl(dpr_dataset_t ds, const int32_t* k, int32_t nk, const double* reg, int32_t nreg, uint32_t iterations,
-                            uint32_t boot_n, uint64_t seed, double* ari_each, double* nclust_each, double* centers_out) {
-    if (!ds || !k || !reg || !ari_each || !nclust_each || nk < 1 || nreg < 1 || iterations < 1 || boot_n < 1)
+// `cells`: the problems [c_lo, c_hi) of the grid in the reference's loop order c = (it * nk + j) * nreg + l; results are written
+// compactly (index c - c_lo): ari / nclust one value per problem, centres ret1, ret2 per problem.
+static int grid_search_range(dpr_dataset_t ds, const int32_t* k, int32_t nk, const double* reg, int32_t nreg, uint32_t iterations,
+                             uint32_t boot_n, uint64_t seed, int c_lo, int c_hi, double* ari_out, double* nclust_out, double* centers_out) {
+    if (!ds || !k || !reg || !ari_out || !nclust_out || nk < 1 || nreg < 1 || iterations < 1 || boot_n < 1)
         return fail(DPR_ERR_INVALID, "grid_search: bad arguments");
     for (int j = 0; j < nk; ++j)
         if (k[j] < 2) return fail(DPR_ERR_INVALID, "grid_search: every k must be >= 2");
+    if (c_lo < 0 || c_hi > (int)iterations * nk * nreg || c_lo >= c_hi) return fail(DPR_ERR_INVALID, "grid_search: bad problem range");
     DPR_TRY(ensure_ready());
     const int d = ds->d;
-    const int cells = (int)iterations * nk * nreg;
+    const int cells = c_hi - c_lo;
     const int F = 2 * cells;
+    const uint32_t fit0 = 2u * (uint32_t)c_lo;   // global number of the first fit: fit f = 2 * problem + which
     const int64_t ldb = ((int64_t)boot_n + kSlotCells - 1) / kSlotCells * kSlotCells;
-    // 1. bootstrap samples (bootstrap_data, :354-355): fit f = 2 * problem + which
+    // 1. bootstrap samples (bootstrap_data, :354-355)
     DevBuf xb, lab_b;
     const int64_t tiles_b = ldb / kSlotCells;
     const int64_t fit_floats = tiles_b * (int64_t)tile_floats(d);   // floats of one bootstrap matrix
     DPR_TRY(xb.alloc(sizeof(float) * (size_t)F * fit_floats, true));
     DPR_TRY(lab_b.alloc(sizeof(int32_t) * (size_t)F * ldb, true));
-    DPR_TRY(launch_gather(ds->x, ds->n, d, nullptr, seed, 0, boot_n, xb.as<float>(), F, fit_floats, ctx().stream));
+    DPR_TRY(launch_gather(ds->x, ds->n, d, nullptr, seed, fit0, boot_n, xb.as<float>(), F, fit_floats, ctx().stream));
     DevBuf xb_xx;   // the F bootstrap matrices are back to back and each is a whole number of tiles
     DPR_TRY(xb_xx.alloc(sizeof(float) * (size_t)F * tiles_b));
     DPR_TRY(launch_tile_norms(xb.as<float>(), (int64_t)F * tiles_b, d, xb_xx.as<float>(), ctx().stream));
     // 2. the fits (find_centers with zero-centre removal, :361-362)
     std::vector<ProblemSpec> specs(F);
     auto cell_of = [&](int f, int& it, int& j, int& l) {
-        const int c = f / 2;
+        const int c = c_lo + f / 2;
         l = c % nreg;
         j = (c / nreg) % nk;
         it = c / (nreg * nk);
@@ -991,7 +1007,7 @@ static int grid_search_impl(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
     DPR_TRY(fits.init(specs, d, true));
     {
         std::vector<SeedJob> jobs(F);
-        for (int f = 0; f < F; ++f) jobs[f] = SeedJob{specs[f].x, (int64_t)boot_n, (uint32_t)f, fits.h_problems[f].mu, nullptr};
+        for (int f = 0; f < F; ++f) jobs[f] = SeedJob{specs[f].x, (int64_t)boot_n, fit0 + (uint32_t)f, fits.h_problems[f].mu, nullptr};
         // seeding rounds are batched per k (the number of rounds is k - 1)
         for (int j = 0; j < nk; ++j) {
             std::vector<SeedJob> sub;
@@ -1009,8 +1025,8 @@ static int grid_search_impl(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
     // distinct labels of each bootstrap fit (n_used_clusters, :379-380) = clusters with a non-zero count
     std::vector<long long> counts((size_t)F * fits.k_max());
     DPR_CUDA(cudaMemcpyAsync(counts.data(), fits.h_problems[0].counts, sizeof(long long) * counts.size(), cudaMemcpyDeviceToHost, ctx().stream));
-    // 3. score on the full data, no_zero = false (:370-371), and 4. ARI per cell.  The label arrays of a batch of
-    //    cells are bounded (4 GB), so a 100M-cell matrix is scored a few cells at a time instead of all 2 * cells at once.
+    // 3. score on the full data, no_zero = false (:370-371), and 4. ARI per problem.  The label arrays of a batch of
+    //    problems are bounded (4 GB), so a 100M-cell matrix is scored a few problems at a time instead of all at once.
     int kmax = 0;
     for (int j = 0; j < nk; ++j) kmax = std::max(kmax, (int)k[j]);
     std::vector<double> ari(cells);
@@ -1029,15 +1045,14 @@ static int grid_search_impl(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
         DPR_TRY(score.prepare());
         DPR_TRY(score.pass(kPassAssign, false));
         std::vector<PairJob> pairs(nc);
-        for (int c = 0; c < nc; ++c) pairs[c] = PairJob{sspecs[2 * c].labels, sspecs[2 * c + 1].labels, ds->n, (uint32_t)(c0 + c)};
+        for (int c = 0; c < nc; ++c) pairs[c] = PairJob{sspecs[2 * c].labels, sspecs[2 * c + 1].labels, ds->n, (uint32_t)(c_lo + c0 + c)};
         DPR_TRY(run_ari(pairs, (uint32_t)kmax, seed, ari.data() + c0));
     }
-    // 5. per-iteration results: ARI of the cell and the mean number of used clusters of its two fits
+    // 5. per-problem results: its ARI and the mean number of used clusters of its two fits
     size_t coff = 0;
     for (int c = 0; c < cells; ++c) {
-        const int l = c % nreg, j = (c / nreg) % nk, it = c / (nreg * nk);
-        const size_t o = (size_t)it * nk * nreg + (size_t)l * nk + j;
-        ari_each[o] = ari[c];
+        const int j = ((c_lo + c) / nreg) % nk;
+        ari_out[c] = ari[c];
         int used = 0;
         for (int w = 0; w < 2; ++w) {
             for (int q = 0; q < k[j]; ++q) used += counts[(size_t)(2 * c + w) * fits.k_max() + q] > 0;
@@ -1048,10 +1063,53 @@ static int grid_search_impl(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
                 coff += (size_t)k[j] * d;
             }
         }
-        nclust_each[o] = used / 2.0;
+        nclust_out[c] = used / 2.0;
     }
     return DPR_OK;
 }
+
+// the whole grid; ari_each / nclust_each: `iterations` matrices nk x nreg col-major
+static int grid_search_impl(dpr_dataset_t ds, const int32_t* k, int32_t nk, const double* reg, int32_t nreg, uint32_t iterations,
+                            uint32_t boot_n, uint64_t seed, double* ari_each, double* nclust_each, double* centers_out) {
+    if (!ari_each || !nclust_each || nk < 1 || nreg < 1 || iterations < 1) return fail(DPR_ERR_INVALID, "grid_search: bad arguments");
+    const int cells = (int)iterations * nk * nreg;
+    std::vector<double> a(cells), c(cells);
+    DPR_TRY(grid_search_range(ds, k, nk, reg, nreg, iterations, boot_n, seed, 0, cells, a.data(), c.data(), centers_out));
+    for (int q = 0; q < cells; ++q) {
+        const int l = q % nreg, j = (q / nreg) % nk, it = q / (nreg * nk);
+        const size_t o = (size_t)it * nk * nreg + (size_t)l * nk + j;
+        ari_each[o] = a[q];
+        nclust_each[o] = c[q];
+    }
+    return DPR_OK;
+}
+
+namespace dpr {
+int grid_search_cells(dpr_dataset* ds, int32_t k, const double* reg, int32_t nreg, uint32_t iterations, uint32_t boot_n, uint64_t seed, int c_lo,
+                      int c_hi, double* ari_out, double* nclust_out, double* centers_out) {
+    return grid_search_range(ds, &k, 1, reg, nreg, iterations, boot_n, seed, c_lo, c_hi, ari_out, nclust_out, centers_out);
+}
+int comm_allreduce_host_f64(std::initializer_list<std::vector<double>*> bufs) {
+    if (ctx().world <= 1) return DPR_OK;
+    size_t total = 0;
+    for (auto* b : bufs) total += b->size();
+    DevBuf dev;
+    DPR_TRY(dev.alloc(sizeof(double) * total));
+    size_t off = 0;
+    for (auto* b : bufs) {
+        DPR_CUDA(cudaMemcpyAsync(dev.as<double>() + off, b->data(), sizeof(double) * b->size(), cudaMemcpyHostToDevice, ctx().stream));
+        off += b->size();
+    }
+    DPR_TRY(comm_allreduce_sum_f64(dev.as<double>(), total));
+    off = 0;
+    for (auto* b : bufs) {
+        DPR_CUDA(cudaMemcpyAsync(b->data(), dev.as<double>() + off, sizeof(double) * b->size(), cudaMemcpyDeviceToHost, ctx().stream));
+        off += b->size();
+    }
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    return DPR_OK;
+}
+}  // namespace dpr
 
 extern "C" {
 
@@ -1078,6 +1136,12 @@ int dpr_dataset_grid_search(dpr_dataset_t ds, const int32_t* k, int32_t nk, cons
 int dpr_dataset_grid_search_each(dpr_dataset_t ds, const int32_t* k, int32_t nk, const double* reg, int32_t nreg, uint32_t iterations,
                                  uint32_t boot_n, uint64_t seed, double* ari_each, double* nclust_each, double* centers_out) {
     return grid_search_impl(ds, k, nk, reg, nreg, iterations, boot_n, seed, ari_each, nclust_each, centers_out);
+}
+// a contiguous range of the grid's problems, numbered c = (it * nk + j) * nreg + l like the reference's loops (:349-352)
+int dpr_dataset_grid_search_range(dpr_dataset_t ds, const int32_t* k, int32_t nk, const double* reg, int32_t nreg, uint32_t iterations,
+                                  uint32_t boot_n, uint64_t seed, int32_t first_problem, int32_t n_problems, double* ari_out, double* nclust_out,
+                                  double* centers_out) {
+    return grid_search_range(ds, k, nk, reg, nreg, iterations, boot_n, seed, first_problem, first_problem + n_problems, ari_out, nclust_out, centers_out);
 }
 int dpr_grid_search(const double* X, int64_t n, int32_t d, const int32_t* k, int32_t nk, const double* reg, int32_t nreg,
                     uint32_t iterations, uint32_t boot_n, uint64_t seed, double* ari_out, double* nclust_out, double* centers_out) {
@@ -1129,6 +1193,7 @@ int dpr_dataset_allocate_many(dpr_dataset_t ds, const double* mus, int32_t m, in
 static int bench_session(dpr_dataset_t ds, const double* mu, uint32_t k, double reg, int no_zero, bool sums) {
     if (!g_bench_session || g_bench_ds != ds || g_bench_k != (int)k || g_bench_mode != (int)sums) {
         g_bench_session.reset(new Session());
+        g_bench_session->row_sharded = true;   // several ranks: the iterations of one fit over all ranks' shards
         DPR_TRY(single_session(ds, (int)k, reg, no_zero, sums, *g_bench_session));
         g_bench_ds = ds;
         g_bench_k = (int)k;

@@ -486,10 +486,10 @@ int launch_finalize(Problem* d_problems, int n_problems, const double* seg_in, i
 }
 
 int launch_reduce_finalize(Problem* d_problems, int n_problems, const int32_t* cta_tile_start, int grid_ctas, const double* cta_tables, int k_max, int d,
-                           int iter, int max_iter, int table_cap, int allow_delta, int32_t* n_active2, cudaStream_t st) {
+                           int iter, int max_iter, int table_cap, int allow_delta, int32_t* n_active2, bool exchange, cudaStream_t st) {
     PeerExchange px{};
     px.world = 1;
-    if (ctx().world > 1) DPR_TRY(peer_exchange_next(&px));
+    if (exchange && ctx().world > 1) DPR_TRY(peer_exchange_next(&px));   // (row-sharded sessions only: Session::exchanges)
     const size_t mu_bytes = (size_t)k_max * d * sizeof(double);
     const int mu_in_smem = mu_bytes <= 64 * 1024;
     const size_t part_bytes = ((size_t)k_max * d + k_max + 1) * sizeof(double);

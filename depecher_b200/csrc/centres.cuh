@@ -11,7 +11,7 @@ int launch_finalize(Problem* d_problems, int n_problems, const double* seg_in, i
 // both of the above in one launch (a cluster of 8 CTAs per problem); with several ranks and attached peer mailboxes (comm.cuh) the tables
 // of all ranks are exchanged inside it over NVLink.  n_active2: two counters, iteration i uses [i & 1]
 int launch_reduce_finalize(Problem* d_problems, int n_problems, const int32_t* cta_tile_start, int grid_ctas, const double* cta_tables, int k_max, int d,
-                           int iter, int max_iter, int table_cap, int allow_delta, int32_t* n_active2, cudaStream_t st);
+                           int iter, int max_iter, int table_cap, int allow_delta, int32_t* n_active2, bool exchange, cudaStream_t st);
 bool reduce_finalize_fits(int k_max, int d);
 bool reduce_finalize_peer_fits(int n_problems, int k_max, int d);
 int launch_partition(const Problem* d_problems, int n_problems, int grid_ctas, int total_tiles, int32_t* cta_tile_start, cudaStream_t st);

@@ -212,11 +212,11 @@ int Session::reduce_and_finalize(int iter, int max_iter) {
     if (fused_finalize()) {   // one GPU: nothing to exchange between the two steps; several: exchanged inside, through peer memory
         last_active_slot_ = iter & 1;
         return launch_reduce_finalize(d_problems, n_problems(), d_cta_start_, grid, cta_tables_, k_max_, d_, iter, max_iter, plan.table_floats_cap,
-                                      allow_delta ? 1 : 0, d_n_active_, ctx().stream);
+                                      allow_delta ? 1 : 0, d_n_active_, exchanges(), ctx().stream);
     }
     last_active_slot_ = 0;
     DPR_TRY(launch_reduce_partials(d_problems, n_problems(), d_cta_start_, grid, k_max_, d_, cta_tables_, seg, n_seg, d_n_active_, ctx().stream));
-    if (ctx().world > 1) DPR_TRY(comm_allreduce_sum_f64(seg, (size_t)n_problems() * n_seg * seg_entries));
+    if (exchanges()) DPR_TRY(comm_allreduce_sum_f64(seg, (size_t)n_problems() * n_seg * seg_entries));
     return launch_finalize(d_problems, n_problems(), seg, n_seg, k_max_, d_, iter, max_iter, plan.table_floats_cap, allow_delta ? 1 : 0, d_n_active_,
                            ctx().stream);
 }
@@ -227,7 +227,7 @@ bool Session::fused_finalize() const {
     // fits of a penalty-search set): 8 CTAs per problem come in a dozen waves of gang-scheduled clusters — the two plain kernels are faster
     // (measured: 0.137 vs 0.259 s for the penalty search of depeche() on 10M x 40)
     if (off || n_problems() > 16 || !reduce_finalize_fits(k_max_, d_)) return false;
-    if (ctx().world == 1) return true;
+    if (!exchanges()) return true;
     return peer_exchange_ready() && reduce_finalize_peer_fits(n_problems(), k_max_, d_);   // several ranks: the exchange happens inside the launch
 }
 
@@ -259,7 +259,7 @@ int Session::lloyd(int max_iter) {
 }
 
 int Session::check_lists() {
-    if (ctx().world > 1) DPR_TRY(peer_exchange_check());   // (a peer-memory exchange that timed out)
+    if (exchanges()) DPR_TRY(peer_exchange_check());   // (a peer-memory exchange that timed out)
     if (!move_overflow_) return DPR_OK;
     int32_t flag = 0;
     DPR_CUDA(cudaMemcpyAsync(&flag, move_overflow_, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx().stream));

@@ -57,6 +57,12 @@ public:
     TcPlan tc_plan{};
     bool use_tc = false;       // shape fits the tcgen05 pass (tc_pass.cu); otherwise the FFMA pass runs
     bool allow_delta = true;   // let finalize switch a problem to delta accumulation when few labels change
+    // Several ranks (dpr_comm_init): the problems of THIS session are row shards of fits that every rank runs in step, so each
+    // iteration's tables are summed over the ranks.  Opt-in: only the row-sharded entry points (dpr_dataset_find_centers_from,
+    // dpr_dataset_lloyd_iterations, dpr_dataset_reevaluate_centers) set it; every other session — bootstrap fits of a penalty search,
+    // scoring, a rank-local sparse_k_means — stays local whatever the communicator (summing unrelated fits over ranks).
+    bool row_sharded = false;
+    bool exchanges() const { return row_sharded && ctx().world > 1; }
 
     // raw device buffers (exposed for the multi-GPU allreduce between reduce and finalize)
     double* seg = nullptr;

@@ -228,8 +228,14 @@ def dAllocate(inDataFrame, depModel, engine=None, columns=None):
     if columns is not None:
         Xr = np.asarray(X)[:, columns] if not hasattr(X, "handle") else X
     elif hasattr(X, "handle"):
-        Xr = X                                    # resident dataset: zero-sum columns stay (they add the same to every distance)
-        red = cc[rows]
+        # resident dataset: its columns cannot be dropped, so the centre columns R would drop (colSums == 0, :99-103 — also a column
+        # that only sums to zero by cancellation) are zeroed instead; they then add the same x_j^2 to every distance.  Labels equal R's
+        # except at fp64 near-ties of the distances (the extra term can change the last bit of a sum).
+        Xr = X
+        red = cc[rows].copy()
+        drop = np.ones(cc.shape[1], bool)
+        drop[cols] = False
+        red[:, drop] = 0.0
     else:
         Xr = np.asarray(X)[:, cols]
     if red.ndim == 1:
@@ -242,11 +248,6 @@ def dAllocate(inDataFrame, depModel, engine=None, columns=None):
 # --------------------------------------------------------------------------------------------------------
 # depechePenaltyOpt (and its legacy twin dOptPenalty): R/depechePenaltyOpt.R:14-265
 # --------------------------------------------------------------------------------------------------------
-def _sd(v):
-    v = np.asarray(v, float)
-    return float(np.std(v, ddof=1)) if len(v) > 1 else float("nan")
-
-
 def _grid_search_set(eng, X, k, regs, nCores, sampleSize, seed, dist=None):
     """One set of the search = nCores workers x grid_search(X, k, regs, 1, sampleSize, .) (R/depechePenaltyOpt.R:50-55).
     Single process: one batched call.  With a torch.distributed group (`dist`) the workers are dealt round-robin over the
@@ -271,64 +272,56 @@ def _grid_search_set(eng, X, k, regs, nCores, sampleSize, seed, dist=None):
 
 def depechePenaltyOpt(inDataFrameUsed, k, maxIter, minARIImprovement, sampleSize, penalties, createOutput=False, disableWarnings=False,
                       optimARI=0.95, nCores=None, plotDir=".", engine=None, seed=0, verbose=False, dist=None):
+    """R/depechePenaltyOpt.R:14-265.  The state machine (loop rule :47-48, trivial-solution zeroing :75-78, mean / sd per penalty
+    :89-100, pruning with the k1 / k2 schedule :123-140, stdChange :145-156, best penalty :184-192, warnings :173-207, outputs
+    :242-264) runs inside the library behind the C ABI (dpr_penalty_opt_*, csrc/penalty_opt.cu).  With the CUDA engine and a
+    resident matrix the whole search is ONE call (dpr_dataset_penalty_opt: every set one batch of problems on the device; with a
+    torch.distributed group the problems of a set are dealt over the ranks).  Any other engine (the CPU oracle of the tests)
+    supplies the sets through `grid_search_each` and feeds them to the same state machine."""
+    from ._capi import PenaltyOpt
     eng = _engine(engine)
     nCores = nCores or default_ncores()
     X = inDataFrameUsed
     d = X.d if hasattr(X, "handle") else np.asarray(X).shape[1]
     penalties = np.asarray(penalties, float)
-    penaltyConstant = sampleSize * math.sqrt(d) / 1450.0                                       # :22
-    realPenalties = penalties * penaltyConstant
-    roundPenalties = np.round(penalties, 1)
-    it, lastStd, stdChange, iterTimesNCores = 1, 1.0, 1.0, 1
-    usedPos = np.arange(len(penalties))
-    full = []          # one entry per worker-iteration: {penalty position -> (ARI, nClust, [ret1 centres, ret2 centres])}
-    while iterTimesNCores < 20 or (iterTimesNCores < maxIter and stdChange >= minARIImprovement):     # :47-48
-        # nCores workers x grid_search(dataMat, k, usedPenalties, 1, sampleSize, i)  (:50-55) as ONE batched call
-        res = _grid_search_set(eng, X, k, realPenalties[usedPos], nCores, sampleSize, seed + 7919 * it, dist)
-        for w in range(nCores):
-            ari = np.array(res["z"][w]).ravel()
-            ncl = np.array(res["m"][w]).ravel()
-            ari = np.where(ncl == 1, 0.0, ari)                                                 # :75-78
-            full.append({int(p): (ari[q], ncl[q], res["c"][w][q][:2]) for q, p in enumerate(usedPos)})
-        ariVecs = [[e[p][0] for e in full if p in e] for p in range(len(penalties))]           # :89-97 (keyed by position)
-        meanARI = np.array([np.mean(v) if v else np.nan for v in ariVecs])
-        stdOpt = np.array([_sd(v) if v else np.nan for v in ariVecs])
-        maxPos = int(np.nanargmax(meanARI))                                                    # :103
-        meanMinus2StdMax = meanARI[maxPos] - 2 * stdOpt[maxPos]
-        meanPlus2StdAll = meanARI + 2 * stdOpt
-        localIter = min(it, 3)
-        k1, k2 = (2, 1, 0)[localIter - 1], (4, 3, 2)[localIter - 1]                            # :123-125
-        with np.errstate(invalid="ignore"):
-            keep = (meanPlus2StdAll >= meanMinus2StdMax - k1 * stdOpt[maxPos]) | (meanARI >= np.nanmax(meanARI) - (1 - optimARI) * k2)
-        usedPos = np.array([p for p in usedPos if keep[p]], dtype=int)                         # :126-140
-        if len(usedPos) > 1:                                                                   # :145-154
-            stdChange = ((lastStd - stdOpt[maxPos]) / lastStd) / math.sqrt(it * nCores) if lastStd != 0 else 0.0
-            if np.isnan(stdChange):
-                stdChange = 0.0
+    opt = PenaltyOpt(penalties, k, d, sampleSize, nCores, maxIter, minARIImprovement, optimARI, lib=getattr(eng, "lib", None))
+    try:
+        if hasattr(eng, "penalty_opt"):
+            split = dist is not None and dist.get_world_size() > 1
+            ds, own = eng._as_ds(X)
+            try:
+                eng.penalty_opt(ds, opt, seed, split_over_ranks=split)
+            finally:
+                if own:
+                    ds.close()
         else:
-            stdChange = 0.0
-        lastStd = stdOpt[maxPos]
-        iterTimesNCores = it * nCores
-        if verbose:
-            print(f"Set {it} with {nCores} iterations completed; {len(usedPos)} penalties kept")
-        it += 1
-    if it * nCores >= maxIter and stdChange > minARIImprovement and not disableWarnings:        # :173-177
-        warnings.warn("The maximum number of iterations was reached before stable optimal solution was found")
-    with np.errstate(invalid="ignore"):
-        optimal = np.flatnonzero(meanARI >= np.nanmax(meanARI) - (1 - optimARI))               # :184-185
-    bestPos = int(optimal[int(round(np.mean(np.arange(1, len(optimal) + 1)))) - 1])            # :192 (R rounds half to even, like Python)
-    bestPenalty = float(roundPenalties[bestPos])
-    if len(penalties) > 1 and not disableWarnings:                                             # :196-207
-        if bestPos == 0:
+            it = 1
+            while True:
+                usedPos, regs, cont = opt.used()
+                if not cont:
+                    break
+                # nCores workers x grid_search(dataMat, k, usedPenalties, 1, sampleSize, i)  (:50-55) as ONE batched call
+                res = _grid_search_set(eng, X, k, regs, nCores, sampleSize, seed + 7919 * it, dist)
+                ari = np.array([np.array(res["z"][w]).ravel() for w in range(nCores)])
+                ncl = np.array([np.array(res["m"][w]).ravel() for w in range(nCores)])
+                cen = np.array([[[np.asarray(m, float) for m in res["c"][w][q][:2]] for q in range(len(usedPos))] for w in range(nCores)])
+                opt.feed(ari, ncl, cen)
+                if verbose:
+                    print(f"Set {it} with {nCores} iterations completed; {len(opt.used()[0])} penalties kept")
+                it += 1
+        r = opt.result()
+    finally:
+        opt.close()
+    if not disableWarnings:
+        if r["warn"] & 1:                                                                        # :173-177
+            warnings.warn("The maximum number of iterations was reached before stable optimal solution was found")
+        if r["warn"] & 2:                                                                        # :196-207
             warnings.warn("The lowest penalty was the most optimal in the range.")
-        if bestPos == len(penalties) - 1:
+        if r["warn"] & 4:
             warnings.warn("The highest penalty was the most optimal in the range.")
-    meanClust = np.array([np.nanmean([e[p][1] for e in full if p in e]) if any(p in e for e in full) else np.nan
-                          for p in range(len(penalties))])                                     # :242-249
-    bestCenters = [c for e in full if bestPos in e for c in e[bestPos][2]]                     # :255-258
-    return {"bestPenalty": bestPenalty, "bestPenaltyPosition": bestPos,
-            "meanOptimDf": {"penalty": roundPenalties, "ARI": meanARI, "nClust": meanClust},
-            "bestClusterCenters": bestCenters, "workerIterations": (it - 1) * nCores}
+    return {"bestPenalty": r["bestPenalty"], "bestPenaltyPosition": r["bestPenaltyPosition"],
+            "meanOptimDf": {"penalty": np.round(penalties, 1), "ARI": r["meanARI"], "nClust": r["meanClust"]},
+            "bestClusterCenters": r["bestClusterCenters"], "workerIterations": r["workerIterations"]}
 
 
 dOptPenalty = depechePenaltyOpt       # R/dOptPenalty.R is the same function under its old name
@@ -358,6 +351,13 @@ def depecheAllData(inDataFrameUsed, penalty, k, nCores=None, engine=None, seed=0
 # --------------------------------------------------------------------------------------------------------
 def depecheClusterCenterSelection(allSolutions, selectionDataSet, k, nCores=None, engine=None):
     eng = _engine(engine)
+    if hasattr(eng, "select_solution"):
+        # the whole selection behind the C ABI (dpr_dataset_select_solution): every solution's dAllocate (:11-16) and all
+        # rand_index pairs (:24-29) in one pass over the selection set
+        pick, meanARI = eng.select_solution(selectionDataSet, allSolutions)
+        best = np.asarray(allSolutions[pick], float)
+        rows, cols = _reduce_centres(best)                                                         # :41-45
+        return {"clusterCenters": best[np.ix_(rows, cols)], "rows": rows, "cols": cols, "meanARI": meanARI}
     if hasattr(eng, "allocate_many"):
         # every solution's dAllocate (:11-16) and all rand_index pairs (:24-29) in one pass over the selection set.
         # dAllocate drops zero-sum rows; the labels it returns index the kept rows, 1-based.
@@ -442,7 +442,10 @@ def depeche(inDataFrame, samplingSubset=None, penalties=None, sampleSize="defaul
             reduced, cols = r["clusterCenters"], r["cols"]
             if device_scaled and sel is not ds_used:
                 sel.close()
-            ds_all = ds_used if (use_ds and n_subset == n_rows) else (eng.dataset(Xs[:, cols]) if use_ds else Xs[:, cols])
+            # the final allocation is of the FULL matrix in its original row order (dAllocate(inDataFrameScaled, ...), R/depeche.R:228-232):
+            # the resident matrix can serve only when it IS that matrix — not a samplingSubset of the same length (a permutation or a
+            # resample), whose rows are in another order
+            ds_all = ds_used if (use_ds and samplingSubset is None) else (eng.dataset(Xs[:, cols]) if use_ds else Xs[:, cols])
             full_cc = np.zeros((reduced.shape[0], X.shape[1]))
             full_cc[:, cols] = reduced
             model_cc = full_cc if ds_all is ds_used else reduced

@@ -134,6 +134,15 @@ int dpr_dataset_grid_search_each(dpr_dataset_t ds, const int32_t* k, int32_t nk,
                                  uint32_t iterations, uint32_t boot_n, uint64_t seed, double* ari_each,
                                  double* nclust_each, double* centers_out);
 
+/* A contiguous range of the grid's problems (grid split over processes or GPUs): problem c = (iteration * nk + j) * nreg + l in
+ * the reference's loop order (src/Clusterer.cpp:349-352).  Random streams are addressed by the problem's number in the whole
+ * grid, so a range computed on its own gives the labels, ARI and cluster counts of that range of the whole grid exactly, and its
+ * centres to the rounding of their fp64 sums (the order of those additions follows the launch's partition of the tiles).  ari_out / nclust_out: n_problems values;
+ * centers_out (nullable): ret1, ret2 (k[j] x d col-major) per problem. */
+int dpr_dataset_grid_search_range(dpr_dataset_t ds, const int32_t* k, int32_t nk, const double* reg, int32_t nreg,
+                                  uint32_t iterations, uint32_t boot_n, uint64_t seed, int32_t first_problem,
+                                  int32_t n_problems, double* ari_out, double* nclust_out, double* centers_out);
+
 /* ---- stage-level entry points (parity hooks; each is one deterministic stage of the reference) ----- */
 
 /* Lloyd loop from injected initial centres: find_centers (src/Clusterer.cpp:244-252) without
@@ -163,6 +172,44 @@ int dpr_n_used_clusters(const int32_t* idx, int64_t n, uint32_t k, uint32_t* out
 int dpr_dataset_allocate_many(dpr_dataset_t ds, const double* mus, int32_t m, int32_t k, int32_t no_zero,
                               int32_t* labels_out, double* ari_out);
 
+/* ---- depechePenaltyOpt and depecheClusterCenterSelection behind the ABI ------------------------------------------------
+ * The reference keeps the adaptive penalty search in R (R/depechePenaltyOpt.R:14-265) and returns to R between its sets, each
+ * set a foreach over SOCK workers that receive the whole matrix (:37-38,50-55).  With these entry points a one-process driver
+ * runs the whole search, and the selection of the most central solution (R/depecheClusterCenterSelection.R:11-37), without
+ * leaving the library between sets.  The state machine itself (create / used / feed / result / solutions) is plain host code
+ * and needs no device: a caller that computes the sets elsewhere can drive it step by step. */
+typedef struct dpr_penalty_opt* dpr_penalty_opt_t;
+/* arguments as depechePenaltyOpt's: penalties (unscaled, e.g. 2^seq(0, 5, by = 0.5)), k, d = ncol(inDataFrameUsed), sampleSize,
+ * nCores (worker results per set), maxIter, minARIImprovement, optimARI */
+int dpr_penalty_opt_create(const double* penalties, int32_t n_pen, int32_t k, int32_t d, uint32_t sample_size, int32_t n_cores,
+                           int32_t max_iter, double min_ari_improvement, double optim_ari, dpr_penalty_opt_t* out);
+int dpr_penalty_opt_destroy(dpr_penalty_opt_t opt);
+/* the next set: how many penalties are still in use, their positions (0-based) and scaled values penalty * sampleSize *
+ * sqrt(d) / 1450 (:22-23), and whether the loop rule (:47-48) asks for another set.  pos_out / reg_out hold n_pen entries. */
+int dpr_penalty_opt_used(dpr_penalty_opt_t opt, int32_t* n_used_out, int32_t* pos_out, double* reg_out, int32_t* continue_out);
+/* results of one set: n_cores rows of n_used values each (worker-major: the layout of dpr_dataset_grid_search_each for one
+ * k), centres (nullable) [worker][penalty][2] matrices k x d col-major.  Applies :75-165 (trivial solutions zeroed, mean /
+ * sd per penalty, pruning with the k1 / k2 schedule, stdChange). */
+int dpr_penalty_opt_feed(dpr_penalty_opt_t opt, const double* ari_each, const double* nclust_each, const double* centres,
+                         int32_t* continue_out);
+/* :173-264: best penalty (rounded to one digit like the reference's names) and its position, mean ARI / mean cluster count
+ * per penalty (n_pen values each, nullable), worker-iterations run, number of centre matrices stored at the best penalty,
+ * warn_flags bit 0: iteration cap reached before stability, bit 1 / 2: the best penalty is the lowest / highest given */
+int dpr_penalty_opt_result(dpr_penalty_opt_t opt, double* best_penalty_out, int32_t* best_pos_out, double* mean_ari_out,
+                           double* mean_nclust_out, int32_t* worker_iterations_out, int32_t* n_solutions_out,
+                           int32_t* warn_flags_out);
+/* bestClusterCenters (:255-258): n_solutions matrices k x d col-major, in worker-iteration order, ret1 then ret2 */
+int dpr_penalty_opt_solutions(dpr_penalty_opt_t opt, double* centres_out);
+/* the whole loop on a resident dataset: while (continue) { used -> one batched set (dpr_dataset_grid_search_each) -> feed }.
+ * split_over_ranks != 0 (after dpr_comm_init; every rank holds the same matrix and makes this call): the (worker, penalty)
+ * problems of a set are dealt over the ranks and their small results summed into place with one allreduce per set; ARI and
+ * cluster counts do not depend on the number of ranks (the stored centres agree to the rounding of their fp64 sums). */
+int dpr_dataset_penalty_opt(dpr_dataset_t ds, dpr_penalty_opt_t opt, uint64_t seed, int32_t split_over_ranks);
+/* depecheClusterCenterSelection: allocate the selection set to each of the m solutions (zero-sum rows dropped as dAllocate
+ * does, R/dAllocate.R:99-103), all-pairs rand_index, first solution with the highest mean ARI.  mean_ari_out: m, nullable. */
+int dpr_dataset_select_solution(dpr_dataset_t selection_set, const double* solutions, int32_t m, int32_t k, int32_t* best_out,
+                                double* mean_ari_out);
+
 /* ---- device-resident Lloyd iterations (bench: the timed hot loop, nothing crosses PCIe) --------- */
 /* Runs `iters` fused iterations (assignment + sums/counts + soft-threshold update) from mu_inout without the
  * convergence exit.  ramp_i >= 0: continue a fit with the penalty ramp frozen at iteration ramp_i (steady state).
@@ -174,7 +221,11 @@ int dpr_dataset_lloyd_iterations(dpr_dataset_t ds, double* mu_inout, uint32_t k,
 int dpr_dataset_assign_iterations(dpr_dataset_t ds, const double* mu, uint32_t k, int32_t no_zero,
                                   int32_t iters);
 
-/* ---- multi-GPU (one process per GPU; rows of X sharded; NCCL allreduce of K x (D+1) partials) ------ */
+/* ---- multi-GPU (one process per GPU; rows of X sharded; NCCL allreduce of K x (D+1) partials) ------
+ * The exchange is opt-in per call: only the row-sharded entry points — dpr_dataset_find_centers_from (every rank: its shard
+ * and the same initial centres), dpr_dataset_lloyd_iterations, dpr_dataset_reevaluate_centers — sum their tables over the
+ * ranks; everything else (sparse_k_means, grid_search, allocate_*, rand_index) works on the calling rank's data alone whatever
+ * the communicator, and dpr_dataset_penalty_opt(split_over_ranks) deals independent problems over the ranks. */
 /* unique_id: the 128-byte ncclUniqueId made by rank 0 (dpr_comm_unique_id) and broadcast by the host
  * layer (torch.distributed / MPI / R sockets).  nccl_path: library to dlopen (NULL = "libnccl.so.2"). */
 int dpr_comm_unique_id(void* id128, const char* nccl_path);

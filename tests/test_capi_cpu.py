@@ -59,3 +59,24 @@ def test_version_and_error_text():
     lib.dpr_set_ari_mode.argtypes = [ctypes.c_int32]
     assert lib.dpr_set_ari_mode(7) == -1
     assert b"ARI mode" in lib.dpr_last_error()
+
+
+def test_rcpp_layer_compiles_against_the_abi():
+    """rpkg/src/InterfaceUtils.cpp (the Rcpp host layer a DepecheR maintainer drops in) is checked for syntax and against the
+    declarations of include/depecher_b200.h; R and Rcpp are not in the image, so a stub of the few names it uses stands in
+    (rpkg/compile_check/Rcpp.h).  Every [[Rcpp::export]] must have its wrapper in rpkg/R/RcppExports.R."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "rpkg", "src", "InterfaceUtils.cpp")
+    subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-Wall", "-Werror", "-I" + os.path.join(root, "rpkg", "compile_check"),
+                    "-I" + os.path.join(root, "include"), src], check=True)
+    text = open(src).read()
+    exports = re.findall(r"// \[\[Rcpp::export\]\]\n[^\n(]*?(\w+)\(", text)
+    assert {"sparse_k_means", "grid_search", "allocate_points", "rand_index"} <= set(exports)          # the reference's four
+    assert {"dataset_create", "grid_search_each", "penalty_opt", "select_solution", "set_engine_seed"} <= set(exports)
+    rside = open(os.path.join(root, "rpkg", "R", "RcppExports.R")).read()
+    for name in exports:
+        assert f"'_DepecheR_{name}'" in rside, name
+    # the seed handed to the library varies from call to call (ADVICE r1: the unchanged R caller repeats seed_off_set = 1..nCores in every set)
+    assert "next_seed(seed_off_set)" in text and "(uint64_t)seed_off_set," not in text

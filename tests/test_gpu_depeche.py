@@ -75,6 +75,23 @@ def test_testdata_against_stored_depeche_result(engine, testdata):
     assert np.all(np.abs(sizes - stored) < 0.05 * 20000)
 
 
+def test_depeche_full_length_sampling_subset_keeps_row_order(engine):
+    """a samplingSubset as long as the data (here a permutation) fits on the permuted rows, but the cluster vector is
+    the allocation of the FULL matrix in its original order (dAllocate(inDataFrameScaled, ...), R/depeche.R:228-232)."""
+    rng = np.random.default_rng(8)
+    n, d = 12000, 6
+    cent = np.array([[6.0] * d, [-6.0] * d, [6.0, -6.0] * (d // 2)])
+    ids = np.sort(rng.integers(0, 3, n))                   # truth is sorted by row: a permuted result cannot match it
+    X = cent[ids] + rng.normal(size=(n, d))
+    out = rapi.depeche(X, samplingSubset=rng.permutation(n), nCores=2, maxIter=8, center=False, engine=engine, seed=4)   # (no blob at the origin)
+    cv = out["clusterVector"]
+    assert cv.shape == (n,)
+    # every cluster lies inside one true blob (the blobs are 12 sd apart); labels in the subset's order would mix all three
+    table = np.zeros((cv.max() + 1, 3), np.int64)
+    np.add.at(table, (cv, ids), 1)
+    assert (table.max(axis=1) == table.sum(axis=1)).all()
+
+
 def test_device_prescaling_matches_host(engine, testdata):
     """depecheLogCenterSd on the device (dpr_dataset_create_scaled) against the numpy restatement: same peak centres,
     same sd, scaled cells equal up to the last fp32 bit; also the mean / given-centre / log2 paths."""
@@ -119,3 +136,59 @@ def test_peer_mailbox_setup_and_error_paths(engine):
     X = rng.normal(size=(3000, 8))
     res = engine.sparse_k_means(X, 5, 1.0, True, seed_off_set=2)
     assert res["i"].shape == (3000,)
+
+
+def test_penalty_opt_one_call_equals_stepwise_and_split(engine, testdata):
+    """SURVEY f-1: depechePenaltyOpt's loop inside the library (dpr_dataset_penalty_opt) against the same state machine driven from
+    outside with one grid_search_each per set (what rapi did in round 1), and against the sets computed as three separate ranges of
+    problems (the grid split: a range equals that range of the whole grid bit for bit)."""
+    import depecher_b200 as dp
+    Xs, _ = rapi.depecheLogCenterSd(testdata["X"])
+    k, S, nCores, seed = 30, 5000, 4, 9
+    pens = 2.0 ** np.arange(0, 5.5, 0.5)
+    with engine.dataset(Xs) as ds:
+        a = dp.PenaltyOpt(pens, k, ds.d, S, nCores, 100, 0.01, 0.95)
+        engine.penalty_opt(ds, a, seed)
+        ra = a.result()
+        b = dp.PenaltyOpt(pens, k, ds.d, S, nCores, 100, 0.01, 0.95)
+        c = dp.PenaltyOpt(pens, k, ds.d, S, nCores, 100, 0.01, 0.95)
+        it = 1
+        while b.used()[2]:
+            used, regs, _ = b.used()
+            res = engine.grid_search_each(ds, [k], regs, nCores, S, seed + 7919 * it)
+            ari = np.array([np.array(res["z"][w]).ravel() for w in range(nCores)])
+            ncl = np.array([np.array(res["m"][w]).ravel() for w in range(nCores)])
+            cen = np.array([[[m for m in res["c"][w][q][:2]] for q in range(len(used))] for w in range(nCores)])
+            b.feed(ari, ncl, cen)
+            cells = nCores * len(used)                      # the same set as three ranges of its problems
+            cuts = [0, cells // 3, cells // 3 + 1, cells]
+            parts = [engine.grid_search_range(ds, k, regs, nCores, S, seed + 7919 * it, lo, hi - lo) for lo, hi in zip(cuts[:-1], cuts[1:])]
+            ari_s = np.concatenate([p[0] for p in parts]).reshape(nCores, len(used))
+            ncl_s = np.concatenate([p[1] for p in parts]).reshape(nCores, len(used))
+            cen_s = np.concatenate([p[2] for p in parts]).reshape(nCores, len(used), 2, k, ds.d)
+            # labels, and with them ARI and cluster counts, are identical; the centres agree to the rounding of their fp64 sums
+            # (the order in which a fit's sums are added follows the launch's partition of the tiles over the SMs)
+            assert np.array_equal(ari_s, ari, equal_nan=True) and np.array_equal(ncl_s, ncl)
+            assert np.array_equal(cen_s == 0, cen == 0)
+            np.testing.assert_allclose(cen_s, cen, rtol=1e-11, atol=1e-13)
+            c.feed(ari_s, ncl_s, cen_s)
+            it += 1
+        rb, rc = b.result(), c.result()
+        for r in (rb, rc):
+            assert r["bestPenalty"] == ra["bestPenalty"] and r["workerIterations"] == ra["workerIterations"] and r["warn"] == ra["warn"]
+            assert np.array_equal(r["meanARI"], ra["meanARI"], equal_nan=True) and np.array_equal(r["meanClust"], ra["meanClust"])
+            assert len(r["bestClusterCenters"]) == len(ra["bestClusterCenters"]) == 2 * ra["workerIterations"]
+            for x, y in zip(r["bestClusterCenters"], ra["bestClusterCenters"]):
+                np.testing.assert_allclose(x, y, rtol=1e-11, atol=1e-13)
+        assert all(np.array_equal(x, y) for x, y in zip(rb["bestClusterCenters"], ra["bestClusterCenters"]))   # same launches: bit for bit
+        assert ra["bestPenalty"] in (11.3, 16.0, 22.6, 32.0) and ra["workerIterations"] >= 20
+        # depecheClusterCenterSelection behind the ABI against the allocate_many route of round 1
+        sel = engine.gather(ds, np.random.default_rng(0).integers(0, ds.n, 5000))
+        pick, mean = engine.select_solution(sel, ra["bestClusterCenters"])
+        masked = [np.where((m.sum(axis=1) == 0)[:, None], 0.0, m) for m in ra["bestClusterCenters"]]
+        _, ari = engine.allocate_many(sel, masked, True, want_labels=False, want_ari=True)
+        sel.close()
+        np.testing.assert_allclose(mean, ari.mean(axis=0), rtol=1e-12)
+        assert pick == int(np.flatnonzero(mean == np.nanmax(mean))[0])
+        for o in (a, b, c):
+            o.close()

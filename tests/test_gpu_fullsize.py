@@ -30,8 +30,10 @@ def test_c2_sparse_k_means_1m_x_15(engine, oracle):
         assert abs(fit["n"] - engine.cluster_norm(ds, fit["c"], fit["i"], reg)) <= 1e-9 * abs(fit["n"])
 
 
-def test_c3_lloyd_10m_x_40(engine):
-    """configs[2] shape: 10M x 40, K = 30 — conservation and determinism of the fused iteration"""
+def test_c3_lloyd_10m_x_40(engine, oracle):
+    """configs[2] shape (the bench workload): 10M x 40, K = 30 — conservation and determinism of the fused iteration, and
+    the oracle's word on it: a 20 000-cell sample of the labels (allocate_clusters, Clusterer.cpp:56-66) and the centre update
+    of ALL 10M rows (reevaluate_centers, :99-107; one CPU sweep)"""
     n, d, k = 10_000_000, 40, 30
     reg = 1.0 * n * np.sqrt(d) / 1450.0
     with engine.synthetic(n, d, 24, 2.5, 20261021) as ds:
@@ -46,6 +48,15 @@ def test_c3_lloyd_10m_x_40(engine):
         # delta-accumulated sums (6 iterations) must equal a from-scratch update of the same labels
         mu_c, _ = engine.lloyd_iterations(ds, mu_a, reg, True, 20, 1)
         np.testing.assert_allclose(mu_c, full, rtol=1e-9, atol=1e-12)
+        # the oracle on the same cells
+        Xh = engine.read(ds, 0, n)
+        rows = np.sort(np.random.default_rng(1).choice(n, 20000, replace=False))
+        assert np.array_equal(oracle.allocate_points(Xh[rows], mu_a, True), lab[rows])          # bit-exact labels
+        want, wcnt = oracle.reevaluate_centers(Xh, lab, k, reg)
+        assert np.array_equal(wcnt, cnt)
+        assert np.array_equal(want == 0, full == 0)                                               # identical zero pattern
+        np.testing.assert_allclose(full, want, rtol=1e-9, atol=1e-12)                             # (north_star asks for 1e-5)
+        np.testing.assert_allclose(mu_c, want, rtol=1e-9, atol=1e-12)                             # 6 delta iterations + 1, against a from-scratch CPU update
 
 
 def test_c4_dallocate_100m_x_40(engine, oracle):

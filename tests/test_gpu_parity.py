@@ -369,3 +369,70 @@ def test_lloyd_is_bit_reproducible(engine):
         assert r["n_iter"] == runs[0]["n_iter"]
         assert np.array_equal(r["i"], runs[0]["i"])
         assert np.array_equal(r["c"].view(np.uint64), runs[0]["c"].view(np.uint64)), "centres differ bitwise between runs"
+
+
+# ---------------------------------------------------------------------------------------------- near ties at the error bound
+def near_tie_cells(rng, mu, n, eps_lo=1e-9, eps_hi=1e-4):
+    """cells on the bisector plane of two centres, pushed off it by +-eps * |cb - ca| along the line that joins them, eps
+    log-uniform in [eps_lo, eps_hi]: the two best distances then differ by about 2 eps relative — from far inside the
+    doubtful band of the fp32-grade scores (tau ~ 1e-6) to far outside it.  A small component inside the bisector plane
+    keeps the cells distinct; everything is rounded to fp32 (which moves a cell by ~6e-8 relative: the margins end up
+    spread densely around the bound rather than on a lattice)."""
+    k, d = mu.shape
+    a = rng.integers(0, k, n)
+    b = (a + 1 + rng.integers(0, k - 1, n)) % k
+    ca, cb = mu[a], mu[b]
+    u = cb - ca
+    un = np.linalg.norm(u, axis=1, keepdims=True)
+    noise = rng.normal(size=(n, d)) * 0.05
+    noise -= (noise * u).sum(1, keepdims=True) / un ** 2 * u          # stays in the bisector plane
+    eps = np.exp(rng.uniform(np.log(eps_lo), np.log(eps_hi), n)) * rng.choice([-1.0, 1.0], n)
+    X = (ca + cb) / 2 + noise + eps[:, None] * u
+    return X.astype(np.float32).astype(np.float64)
+
+
+@pytest.mark.parametrize("d,k", [(15, 20), (40, 30), (50, 30), (40, 8)])
+def test_near_ties_at_the_error_bound(engine, oracle, d, k):
+    """the tensor-core accumulation allowance inside tau is measured, not proved — so construct cells whose
+    top-2 margin straddles tau and demand zero mislabels (allocate_clusters' first minimum of the fp64 sqrt distances,
+    Clusterer.cpp:56-66), on the single-set pass, the bundled scoring pass and the FFMA pass; the exact path must have been
+    exercised (dpr_recheck_count) without swallowing everything."""
+    rng = np.random.default_rng(1000 * d + k)
+    mu = (rng.normal(size=(k, d)) * 1.5).astype(np.float32).astype(np.float64)
+    mu[rng.random((k, d)) < 0.3] = 0.0                                       # sparse centres, like fitted ones
+    n = 200_000
+    X = near_tie_cells(rng, mu, n)
+    want = oracle.allocate_points(X, mu, False)
+    margin = oracle.assignment_margin(X, mu, False)
+    assert (margin < 1e-7).sum() > n // 20 and (margin > 1e-5).sum() > n // 20    # both sides of the bound are populated
+    with engine.dataset(X) as ds:
+        engine.recheck_count(reset=True)
+        got = engine.allocate_points(ds, mu, False)["i"]
+        redone = engine.recheck_count(reset=True)
+        assert np.array_equal(got, want), f"{(got != want).sum()} mislabels, worst oracle margin {margin[got != want].max():.3e}"
+        assert n // 50 < redone < n, f"{redone} of {n} cells took the exact path"
+        # the same cells through a bundle of centre sets (the scoring instance of the pass): every member must agree too
+        mus = [mu, mu[::-1].copy(), np.roll(mu, 3, axis=0), mu * 1.0]
+        lab, _ = engine.allocate_many(ds, mus, False, want_labels=True, want_ari=False)
+        for m, l in zip(mus, lab):
+            w = oracle.allocate_points(X, m, False)
+            assert np.array_equal(l, w), f"bundle member: {(l != w).sum()} mislabels"
+        engine.set_pass_kernel(1)   # DPR_PASS_FFMA
+        try:
+            assert np.array_equal(engine.allocate_points(ds, mu, False)["i"], want)
+        finally:
+            engine.set_pass_kernel(0)
+
+
+def test_near_ties_scaled_operands(engine, oracle):
+    """the same construction with cells and centres far outside fp16's range (the pass scales both by powers of two) and with a
+    handful of tiny cells among large ones (the absolute part of the split error, tc_abs1 / tc_abs2)"""
+    rng = np.random.default_rng(77)
+    d, k, n = 40, 30, 100_000
+    for scale in (2.0 ** 20, 2.0 ** -20):
+        mu = (rng.normal(size=(k, d)) * 1.5).astype(np.float32).astype(np.float64) * scale
+        X = near_tie_cells(rng, mu, n)
+        X[::1000] *= 2.0 ** -12
+        got = engine.allocate_points(X, mu, False)["i"]
+        want = oracle.allocate_points(X, mu, False)
+        assert np.array_equal(got, want), f"scale {scale}: {(got != want).sum()} mislabels"

@@ -85,7 +85,7 @@ def test_penalty_scaling_and_best_rule(eng):
             nreg = len(reg)
             ari = np.linspace(0.5, 0.99, nreg)[None, :]
             return {"z": [ari.copy() for _ in range(iterations)], "m": [np.full((1, nreg), 5.0) for _ in range(iterations)],
-                    "c": [[[np.eye(3), np.eye(3)] * 2 for _ in range(nreg)] for _ in range(iterations)]}
+                    "c": [[[np.eye(3, 16), np.eye(3, 16)] * 2 for _ in range(nreg)] for _ in range(iterations)]}
 
     X = np.zeros((50, 16))
     r = rapi.depechePenaltyOpt(X, k=3, maxIter=20, minARIImprovement=0.01, sampleSize=50, penalties=[1, 2, 4, 8], optimARI=0.95, nCores=4,

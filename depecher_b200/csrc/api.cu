@@ -1030,11 +1030,35 @@ static int grid_search_range(dpr_dataset_t ds, const int32_t* k, int32_t nk, con
     int kmax = 0;
     for (int j = 0; j < nk; ++j) kmax = std::max(kmax, (int)k[j]);
     std::vector<double> ari(cells);
+    bool scored = false;
+    if (ctx().ari_mode == DPR_ARI_EXACT) {
+        // the scoring pass takes the K x K contingency counts of each (ret1, ret2) pair itself (score_pass.cu): every problem of the
+        // range in ONE session, no label ever written to HBM, then one small launch turns the tables into ARI values
+        std::vector<ProblemSpec> sspecs(2 * cells);
+        for (int q = 0; q < 2 * cells; ++q)
+            sspecs[q] = ProblemSpec{ds->x, ds->tile_xx, ds->tile_xx + ds->n_pad / kSlotCells, ds->n, specs[q].k, 0.0, 0, nullptr};
+        Session score;
+        const int kk = kmax + 1;
+        DPR_TRY(score.init(sspecs, d, false, kk));
+        if (score.fuse_pairs) {
+            DevBuf tables, out;
+            DPR_TRY(tables.alloc(sizeof(unsigned long long) * (size_t)cells * kk * kk, true));
+            DPR_TRY(out.alloc(sizeof(double) * cells));
+            score.pair_tables = tables.as<unsigned long long>();
+            for (int q = 0; q < 2 * cells; ++q) DPR_TRY(score.set_centres_device(q, fits.h_problems[q].mu));
+            DPR_TRY(score.prepare());
+            DPR_TRY(score.pass(kPassAssign, false));
+            DPR_TRY(launch_ari_from_tables(cells, ds->n, kk, tables.as<unsigned long long>(), out.as<double>(), ctx().stream));
+            DPR_CUDA(cudaMemcpyAsync(ari.data(), out.p, sizeof(double) * cells, cudaMemcpyDeviceToHost, ctx().stream));
+            DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+            scored = true;
+        }
+    }
     const size_t per_cell_bytes = 2 * sizeof(int32_t) * (size_t)ds->n_pad;
     const int batch_cells = (int)std::max<size_t>(1, std::min<size_t>((size_t)cells, ((size_t)4 << 30) / per_cell_bytes));
     DevBuf lab_full;
-    DPR_TRY(lab_full.alloc(per_cell_bytes * (size_t)batch_cells));
-    for (int c0 = 0; c0 < cells; c0 += batch_cells) {
+    if (!scored) DPR_TRY(lab_full.alloc(per_cell_bytes * (size_t)batch_cells));
+    for (int c0 = 0; c0 < cells && !scored; c0 += batch_cells) {   // (Monte-Carlo ARI, or tables too wide for shared memory: labels to HBM, counted afterwards)
         const int nc = std::min(batch_cells, cells - c0);
         std::vector<ProblemSpec> sspecs(2 * nc);
         for (int q = 0; q < 2 * nc; ++q)

@@ -319,6 +319,51 @@ __global__ void ari_from_tables_kernel(const AriPair* pairs, int kk, const unsig
     out[p] = (ri - e) / (1.0 - e);
 }
 
+// the same for tables that every pair fills from the same n cells (the scoring pass counted them: score_pass.cu)
+__global__ void ari_from_tables_n_kernel(long long n, int kk, const unsigned long long* tables, double* out) {
+    const int p = blockIdx.x;
+    const unsigned long long* t = tables + (size_t)p * kk * kk;
+    double same12 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int a = threadIdx.x; a < kk; a += blockDim.x) {   // thread a: row a and column a (integer sums: any order gives the same value)
+        unsigned long long r = 0, c = 0;
+        for (int b = 0; b < kk; ++b) {
+            const unsigned long long v = t[(size_t)a * kk + b];
+            r += v;
+            c += t[(size_t)b * kk + a];
+            same12 += (double)v * (double)(v ? v - 1 : 0);
+        }
+        s1 += (double)r * (double)(r ? r - 1 : 0);
+        s2 += (double)c * (double)(c ? c - 1 : 0);
+    }
+    // products of integers below 2^53 are exact in fp64 only up to 2^53: add them in a fixed order (lane order, then warp order)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        same12 += __shfl_down_sync(0xffffffffu, same12, o);
+        s1 += __shfl_down_sync(0xffffffffu, s1, o);
+        s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    }
+    __shared__ double s_w[3][8];
+    if ((threadIdx.x & 31) == 0) {
+        s_w[0][threadIdx.x >> 5] = same12;
+        s_w[1][threadIdx.x >> 5] = s1;
+        s_w[2][threadIdx.x >> 5] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double q12 = 0.0, q1 = 0.0, q2 = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            q12 += s_w[0][w];
+            q1 += s_w[1][w];
+            q2 += s_w[2][w];
+        }
+        const double N = (double)n, denom = N * (N - 1.0);
+        const double A = q1 / denom, B = q2 / denom, both = q12 / denom;
+        const double ri = both + (1.0 - A - B + both);
+        const double e = A * B + (1.0 - A) * (1.0 - B);
+        out[p] = (ri - e) / (1.0 - e);
+    }
+}
+
 // Monte-Carlo estimate: pair `num` is (w0 % n, w1 % n) of Philox(seed, PAIR, pair_id, num, attempt), redrawn
 // while i == j (:291-295); `stab` counts agreeing pairs (:296-300).
 __global__ void ari_mc_count_kernel(const AriPair* pairs, uint64_t seed, unsigned int* stab, int32_t* bad, int kk) {
@@ -512,6 +557,12 @@ int launch_ari(const AriPair* d_pairs, int n_pairs, int64_t n_max, int kk, int m
         ari_from_tables_kernel<<<n_pairs, 32, 0, st>>>(d_pairs, kk, d_tables, d_out);
         count_launch();
     }
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_ari_from_tables(int n_pairs, int64_t n, int kk, const unsigned long long* d_tables, double* d_out, cudaStream_t st) {
+    ari_from_tables_n_kernel<<<n_pairs, 64, 0, st>>>((long long)n, kk, d_tables, d_out);
+    count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
 }

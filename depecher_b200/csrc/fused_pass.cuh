@@ -30,6 +30,9 @@ struct PassParams {
     int32_t* move_counts;           // [(grid + n_problems) * warps]: entries of each (CTA, problem, warp)
     int64_t move_cap;               // entries per warp
     int32_t* move_overflow;         // set when a list ran out of room (a sizing bug: the host fails loudly)
+    // scoring pass with fused contingency counts (score_pass.cu): problems 2c, 2c + 1 are the (ret1, ret2) pair of penalty cell c;
+    // the pass adds the (label under 2c, label under 2c + 1) counts of every cell into table c ([pair_kk x pair_kk] each)
+    unsigned long long* pair_tables;   // nullable
     // filled from the plan
     int32_t warps, slots_per_warp, slot_floats, off_hdr, off_table, off_orig, off_scratch, scratch_bytes, off_slots;
 };
@@ -62,6 +65,26 @@ int plan_tc_pass(int d, int k_max, int sets_wanted, TcPlan* plan);
 int launch_tc_pass(const TcPlan& plan, const PassParams& P, int grid, cudaStream_t stream);
 // sums/counts of the moved cells recorded by a tensor-core Lloyd pass in delta mode (tc_pass.cu)
 int launch_delta_sums(const TcPlan& plan, const PassParams& P, int grid, cudaStream_t stream);
+
+// scoring pass (score_pass.cu): up to 4 centre sets stacked along N per tile, role-split CTA (split / products / reduce)
+constexpr int kScMaxStages = 10;
+constexpr int kScMaxSets = 4;
+struct ScorePlan {
+    int32_t d, k16;          // markers; K = 16 * k16 per product chain
+    int32_t ncol_max;        // accumulator columns reserved per set (k_max rounded up to 16)
+    int32_t sets;            // centre sets per bundle: 4 (ncol_max <= 32) or 2
+    int32_t b_rows;          // rows of the stacked B operands = sets * ncol_max
+    int32_t acols;           // TMEM columns of one fp16 A operand
+    int32_t wait_hint;
+    int32_t kk;              // width of the fused contingency tables (k_max + 1); 0: not fused
+    int32_t stages, stage_floats;
+    int32_t off_sets, off_cc, off_orig, off_bh, off_bl, off_pairs, off_stages;
+    size_t smem_bytes;
+};
+// returns 1 when the shape fits (d <= 64, k_max <= 64, >= 2 sets share their cells); fuse_kk > 0 asks for the contingency tables
+// of the pairs in shared memory (plan->kk stays 0 when they do not fit)
+int plan_score_pass(int d, int k_max, int sets_wanted, int fuse_kk, ScorePlan* plan);
+int launch_score_pass(const ScorePlan& plan, const PassParams& P, int grid, cudaStream_t stream);
 
 // returns 1 and fills the plan when a d-marker slot per warp fits in shared memory, 0 otherwise
 int plan_pass(int d, int k_max, PassPlan* plan);

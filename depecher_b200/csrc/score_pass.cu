@@ -1,0 +1,513 @@
+// score_pass.cu — the scoring pass of the penalty search on the 5th-generation tensor cores: the SAME cells assigned to many
+// centre sets (Clusterer::optimize_param scores every fitted pair on the full data, /root/reference/src/Clusterer.cpp:370-371:
+// 2 sets per penalty and worker, 220 per set of depeche()'s default sweep), optionally with the K x K contingency counts of each
+// (ret1, ret2) pair taken inside the pass so that no label ever goes to HBM (cluster_distance's inputs, :376 and :267-305).
+//
+// Same arithmetic as tc_pass.cu (fp16-split operands, fp32 accumulation, exact fp64 re-decision of every near tie: labels are
+// bit-exact), different shape — the round-1 bundled instance of tc_pass_kernel ran at 29 % of its HBM roofline, bound by a chain
+// of latencies per (tile, set) inside a consumer group and by reading two accumulator halves per score:
+//   * the centre sets of a bundle (up to 4) are STACKED along N: one B operand of sum(n_q) rows, so one round of products per
+//     tile serves every set (one wait per tile instead of one per set);
+//   * the three partial products xh*ch, xh*cl, xl*ch accumulate into the SAME columns (3 tcgen05.mma per K = 16 step), so a
+//     score is one TMEM column, not the sum of two: tensor-memory reads (64 B/cycle/SM, the tightest resource of this pass at
+//     K = 30) are halved and the add disappears; a set only occupies round16(active centres) columns;
+//   * roles: one group of four warps only SPLITS tiles (fp32 -> fp16 high/low parts into one of two A buffers in tensor memory),
+//     three groups of four warps only REDUCE (tcgen05.ld -> two smallest scores -> label), one accumulator each, so the products of
+//     tile t+1 and t+2 run while tile t is reduced; one warp issues the products, one keeps the ring of bulk copies in flight.
+//     512 TMEM columns = 3 accumulators x 128 + 2 x (xh + xl);
+//   * the two smallest scores come from a tournament over 16-column blocks (independent compare/selects) instead of a serial scan.
+#include "common.cuh"
+#include "fused_pass.cuh"
+#include "pass_device.cuh"
+#include "tc_device.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace dpr {
+
+constexpr int kScAccs = 3;          // accumulators = reducing groups
+constexpr int kScABufs = 2;         // A-operand buffers (tiles split but not yet multiplied)
+constexpr int kScAccCols = 128;     // TMEM columns per accumulator: the stacked sets of a bundle
+constexpr int kScConsumerWarps = 4 * (kScAccs + 1);   // 12 reducing + 4 splitting
+constexpr int kScThreads = (kScConsumerWarps + 2) * 32;
+
+struct ScoreSet {          // one centre set of the current bundle (shared memory)
+    int32_t col0, ncols;   // its accumulator columns: [col0, col0 + ncols), ncols a multiple of 16
+    int32_t n_act, trivial, force_exact, pad_;
+    float unscale, abs1, abs2, cc2;
+    int32_t* labels;       // nullable: scoring with fused contingency counts stores no labels
+    const double* mu;      // exact centres (global memory; only the rare fp64 re-decisions read them)
+};
+
+// the two smallest of a sorted pair (a0 <= a1) and a sorted pair (b0 <= b1), sorted
+__device__ __forceinline__ void merge2(float a0, float a1, float b0, float b1, float& lo, float& hi) {
+    lo = fminf(a0, b0);
+    hi = fmin3(fmaxf(a0, b0), a1, b1);
+}
+
+template <bool kPairs>
+__global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassParams P, const ScorePlan T) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t_begin = P.cta_tile_start[blockIdx.x], t_end = P.cta_tile_start[blockIdx.x + 1];
+    if (t_begin >= t_end) return;
+
+    const int S = T.stages;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [S] tile landed
+    uint64_t* empty = full + kScMaxStages;                // [S] tile reduced (one arrival per warp of the reducing group)
+    uint64_t* a_ready = empty + kScMaxStages;             // [2] A buffer written (one arrival per splitting warp)
+    uint64_t* a_free = a_ready + kScABufs;                // [2] the products that read the A buffer are complete
+    uint64_t* acc_full = a_free + kScABufs;               // [3] products into the accumulator complete
+    uint64_t* acc_free = acc_full + kScAccs;              // [3] the accumulator has been read (one arrival per reducing warp)
+    uint64_t* tables_ready = acc_free + kScAccs;          // the bundle's centre tables are in shared memory
+    uint32_t* tmem_word = reinterpret_cast<uint32_t*>(tables_ready + 1);
+    int32_t* n_total_s = reinterpret_cast<int32_t*>(tmem_word + 1);   // accumulator columns the current bundle uses
+    ScoreSet* sets = reinterpret_cast<ScoreSet*>(smem + T.off_sets);
+    float* cc_s = reinterpret_cast<float*>(smem + T.off_cc);          // [b_rows] ||c||^2 per accumulator column (padding: +huge)
+    int32_t* orig_s = reinterpret_cast<int32_t*>(smem + T.off_orig);  // [b_rows] column -> row of its set's mu (padding: -1)
+    float4* bh = reinterpret_cast<float4*>(smem + T.off_bh);          // stacked high parts, K-major canonical layout
+    float4* bl = reinterpret_cast<float4*>(smem + T.off_bl);          // stacked low parts
+    unsigned int* pair_s = reinterpret_cast<unsigned int*>(smem + T.off_pairs);   // [sets / 2][kk * kk] contingency counts of this CTA
+    float* stages = reinterpret_cast<float*>(smem + T.off_stages);
+    const int d = T.d, groups = tile_groups(d), k16 = T.k16;
+    const size_t tile_fl = tile_floats(d);
+    const uint32_t tile_bytes = (uint32_t)(tile_fl * 4);
+    const int acols = T.acols;                                        // TMEM columns of one fp16 A operand (2 markers each)
+    const uint32_t a_base = (uint32_t)(kScAccs * kScAccCols);
+    const int kk = T.kk, kk2 = kk * kk;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 4);
+        }
+        for (int b = 0; b < kScABufs; ++b) {
+            mbar_init(&a_ready[b], 4);
+            mbar_init(&a_free[b], 1);
+        }
+        for (int c = 0; c < kScAccs; ++c) {
+            mbar_init(&acc_full[c], 1);
+            mbar_init(&acc_free[c], 4);
+        }
+        mbar_init(tables_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (kPairs)
+        for (int i = threadIdx.x; i < (T.sets / 2) * kk2; i += blockDim.x) pair_s[i] = 0u;
+    if (groups & 1)   // the split reads marker groups in pairs: the partner of an odd last group is never written by a copy — zero, once
+        for (int s = 0; s < S; ++s)
+            for (int i = threadIdx.x; i < kGroupFloats; i += blockDim.x) stages[(size_t)s * T.stage_floats + (size_t)groups * kGroupFloats + i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_word;
+
+    int p = 0;
+    {
+        int lo = 0, hi = P.n_problems - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (P.problems[mid].first_tile <= t_begin) lo = mid; else hi = mid - 1;
+        }
+        p = lo;
+    }
+    int tile = t_begin;
+
+    // ================================ producer warp: the ring of bulk copies ================================
+    if (warp == kScConsumerWarps + 1) {
+        int s = 0, issued = 0;
+        uint32_t phase = 0;
+        while (tile < t_end) {
+            const Problem* pr = P.problems + p;
+            const int first_tile = pr->first_tile, p_end = min(t_end, first_tile + pr->n_tiles);
+            if (pr->done || p_end <= tile) {
+                tile = max(tile, p_end);
+                ++p;
+                continue;
+            }
+            const float* src = pr->x + (size_t)(tile - first_tile) * tile_fl;
+            for (; tile < p_end; ++tile, src += tile_fl) {
+                if (issued >= S) {
+                    mbar_wait_hint(&empty[s], (phase >> s) & 1u, T.wait_hint);
+                    phase ^= 1u << s;
+                }
+                if (elect_one()) {
+                    mbar_expect_tx(&full[s], tile_bytes);
+                    bulk_g2s(smem_u32(stages + (size_t)s * T.stage_floats), src, tile_bytes, smem_u32(&full[s]));
+                }
+                __syncwarp();
+                ++issued;
+                s = (s + 1 == S) ? 0 : s + 1;
+            }
+            ++p;
+        }
+        return;
+    }
+
+    // ================================ the warp that issues the products ================================
+    if (warp == kScConsumerWarps) {
+        uint32_t seq = 0, n_range = 0, c = 0;     // tiles walked; ranges walked; accumulator of tile seq (= seq % 3)
+        uint32_t u3 = 0;                          // use number of accumulator c (= seq / 3)
+        const uint32_t lbo = (uint32_t)T.b_rows * 16u;   // bytes between the 8-marker groups of a stacked B operand
+        const uint64_t desc_h0 = umma_desc(smem_u32(bh), lbo, 128), desc_l0 = umma_desc(smem_u32(bl), lbo, 128);
+        const uint64_t desc_step = (uint64_t)((2u * lbo) >> 4);   // one K = 16 step = two marker groups further
+        while (tile < t_end) {
+            const Problem* pr = P.problems + p;
+            const int p_end = min(t_end, pr->first_tile + pr->n_tiles);
+            if (pr->done || p_end <= tile) {
+                tile = max(tile, p_end);
+                ++p;
+                continue;
+            }
+            mbar_wait_hint(tables_ready, n_range & 1u, T.wait_hint);
+            ++n_range;
+            const uint32_t n_total = (uint32_t)*reinterpret_cast<volatile int32_t*>(n_total_s);
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 4) << 24) | ((n_total >> 3) << 17);   // D fp32, A/B fp16, both K-major, M = 128, N = n_total
+            for (; tile < p_end; ++tile, ++seq) {
+                const uint32_t b = seq & 1u, ub = seq >> 1;
+                mbar_wait_hint(&a_ready[b], ub & 1u, T.wait_hint);
+                if (u3 > 0) mbar_wait_hint(&acc_free[c], (u3 - 1u) & 1u, T.wait_hint);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t acc = tmem + c * (uint32_t)kScAccCols;
+                    const uint32_t ah = tmem + a_base + b * (uint32_t)(2 * acols), al = ah + (uint32_t)acols;
+                    for (int s = 0; s < k16; ++s) {
+                        umma_f16_ts(acc, ah + 8 * s, desc_h0 + s * desc_step, idesc, s > 0 ? 1u : 0u);   // xh * ch
+                        umma_f16_ts(acc, ah + 8 * s, desc_l0 + s * desc_step, idesc, 1);                  // xh * cl
+                        umma_f16_ts(acc, al + 8 * s, desc_h0 + s * desc_step, idesc, 1);                  // xl * ch
+                    }
+                    umma_commit(&acc_full[c]);
+                    umma_commit(&a_free[b]);
+                }
+                __syncwarp();
+                if (++c == kScAccs) {
+                    c = 0;
+                    ++u3;
+                }
+            }
+            ++p;
+        }
+        return;
+    }
+
+    // ================================ consumer warps: 3 reducing groups + 1 splitting group ================================
+    const int grp = warp >> 2, wq = warp & 3;   // group; TMEM lane quarter this warp may touch
+    const bool splitter = grp == kScAccs;
+    const int mycell_in_tile = wq * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(wq * 32) << 16);
+    const int steps8 = (d + 7) >> 3;   // 8-marker steps that hold data
+    if (splitter) {   // zero padding of the last K = 16 step, in both parts of both A buffers: written once
+        const uint32_t z[4] = {0u, 0u, 0u, 0u};
+        for (int b = 0; b < kScABufs; ++b)
+            for (int c = 4 * steps8; c < acols; c += 4) {
+                tmem_st4(lane_base + a_base + (uint32_t)(b * 2 * acols + c), z);
+                tmem_st4(lane_base + a_base + (uint32_t)(b * 2 * acols + acols + c), z);
+            }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    // error bound of a score: see tc_pass.cu.  Here 3 * k16 products accumulate into one column (2^-21 allowed per step, measured
+    // <= 2^-24), and there is no sum of two accumulator halves.
+    const float tau_a = 2.f * (3.f * 2.3841858e-7f + (float)(3 * k16 + 1) * 4.7683716e-7f);
+    const float tau_b = 2.f * (4.f * 5.9604645e-8f) + 3.8146973e-6f;
+
+    uint32_t seq = 0;               // tiles this CTA has walked past
+    int s_idx = 0;                  // stage of tile seq (= seq % S)
+    uint32_t s_use = 0;             // seq / S
+    uint32_t r3 = 0, u3 = 0;        // seq % 3, seq / 3
+    int prev_pair0 = -1, prev_pairs = 0;   // the pair tables in shared memory belong to these global pairs (kPairs)
+    const int tid = threadIdx.x;    // < 512
+
+    while (tile < t_end) {
+        const Problem pr = P.problems[p];
+        const int p_end = min(t_end, pr.first_tile + pr.n_tiles);
+        if (pr.done || p_end <= tile) {
+            tile = max(tile, p_end);
+            ++p;
+            continue;
+        }
+        const int NS = max(1, pr.bundle);   // centre sets that share this range's cells (problems p .. p + NS - 1)
+        consumer_barrier<kScConsumerWarps * 32>();   // every group is past the previous range: its tables and counts are final
+        if (kPairs && prev_pairs > 0) {   // this CTA's counts of the previous bundle's pairs -> the global tables
+            for (int e = tid; e < prev_pairs * kk2; e += kScConsumerWarps * 32) {
+                const unsigned int v = pair_s[e];
+                if (v) {
+                    atomicAdd(P.pair_tables + (size_t)(prev_pair0 + e / kk2) * kk2 + (e % kk2), (unsigned long long)v);
+                    pair_s[e] = 0u;
+                }
+            }
+        }
+        prev_pair0 = p >> 1;
+        prev_pairs = NS >> 1;
+        {   // the bundle's tables: stacked B operands, ||c||^2 and the column -> row maps, per-set constants
+            int col0[kScMaxSets + 1];
+            col0[0] = 0;
+#pragma unroll
+            for (int q = 0; q < kScMaxSets; ++q) col0[q + 1] = col0[q] + (q < NS ? P.problems[p + q].hdr->tc_n : 0);
+#pragma unroll
+            for (int q = 0; q < kScMaxSets; ++q) {
+                if (q >= NS) break;
+                const Problem* pq = P.problems + p + q;
+                const int nq = col0[q + 1] - col0[q], npad = pq->tc_npad;
+                const float* tab = pq->tc_table;
+                const float4* bsrc = reinterpret_cast<const float4*>(tab + npad);   // per 8-marker group: npad high rows, npad low rows (16 B each)
+                for (int i = tid; i < 2 * k16 * nq; i += kScConsumerWarps * 32) {
+                    const int g = i / nq, r = i - g * nq;
+                    bh[(size_t)g * T.b_rows + col0[q] + r] = bsrc[(size_t)g * 2 * npad + r];
+                    bl[(size_t)g * T.b_rows + col0[q] + r] = bsrc[(size_t)g * 2 * npad + npad + r];
+                }
+                for (int i = tid; i < nq; i += kScConsumerWarps * 32) {
+                    cc_s[col0[q] + i] = tab[i];
+                    orig_s[col0[q] + i] = pq->tc_orig[i];
+                }
+                if (tid == 32 * q) {
+                    const CentreHeader* h = pq->hdr;
+                    ScoreSet st;
+                    st.col0 = col0[q];
+                    st.ncols = nq;
+                    st.n_act = h->k_act;
+                    st.trivial = h->trivial;
+                    st.force_exact = h->force_exact;
+                    st.pad_ = 0;
+                    st.unscale = h->tc_unscale;
+                    st.abs1 = h->tc_abs1;
+                    st.abs2 = h->tc_abs2;
+                    st.cc2 = 2.0f * h->cc_max;
+                    st.labels = pq->labels;
+                    st.mu = pq->mu;
+                    sets[q] = st;
+                }
+            }
+            if (tid == 0) *n_total_s = col0[NS];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the B operands were written through the generic proxy
+        consumer_barrier<kScConsumerWarps * 32>();
+        if (tid == 0) mbar_arrive(tables_ready);
+        const float scale_x = pr.hdr->tc_scale_x;   // (the same for every set of a bundle: it depends on the cells only)
+
+        if (splitter) {
+            // ---- fp32 cells -> fp16 high / low parts, parked in tensor memory as the A operands of tile seq
+            for (; tile < p_end; ++tile, ++seq) {
+                const uint32_t b = seq & 1u, ub = seq >> 1;
+                mbar_wait_hint(&full[s_idx], s_use & 1u, T.wait_hint);
+                if (ub > 0) mbar_wait_hint(&a_free[b], (ub - 1u) & 1u, T.wait_hint);
+                tc_fence_after();
+                const float* slot = stages + (size_t)s_idx * T.stage_floats;
+                const float4* st4 = reinterpret_cast<const float4*>(slot) + mycell_in_tile;
+                const uint32_t a_hi = lane_base + a_base + b * (uint32_t)(2 * acols), a_lo = a_hi + (uint32_t)acols;
+                if (scale_x == 1.f) split_tile<false>(st4, steps8, 1.f, a_hi, a_lo);
+                else split_tile<true>(st4, steps8, scale_x, a_hi, a_lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[b]);
+                if (++s_idx == S) {
+                    s_idx = 0;
+                    ++s_use;
+                }
+            }
+        } else {
+            // ---- scores of tile seq (accumulator grp) -> labels of every set (+ contingency counts of the pairs)
+            for (; tile < p_end; ++tile, ++seq) {
+                const bool mine = r3 == (uint32_t)grp;
+                if (mine) {
+                    const float* slot = stages + (size_t)s_idx * T.stage_floats;
+                    const int64_t mycell = (int64_t)(tile - pr.first_tile) * kSlotCells + mycell_in_tile;
+                    const bool live = mycell < pr.n;
+                    const float xx_tile = pr.tile_xx[tile - pr.first_tile];
+                    const float sq_xx = sqrtf(xx_tile);
+                    mbar_wait_hint(&acc_full[grp], u3 & 1u, T.wait_hint);
+                    tc_fence_after();
+                    int lab[kScMaxSets] = {0, 0, 0, 0};
+                    unsigned doubt = 0;   // bit q: this cell's decision for set q needs the exact path
+#pragma unroll
+                    for (int q = 0; q < kScMaxSets; ++q) {
+                        if (q >= NS) break;
+                        const ScoreSet* st = sets + q;
+                        if (st->trivial) continue;   // fewer than two active rows: every label 0 (Clusterer.cpp:50-53)
+                        const int c0 = st->col0, nq = st->ncols;
+                        const float unscale = st->unscale;
+                        float best = 3.3e38f, second = 3.3e38f;
+                        int bchunk = 0;
+                        for (int n0 = 0; n0 < nq; n0 += 16) {
+                            uint32_t v[16];
+                            asm volatile(
+                                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                                : "r"(lane_base + (uint32_t)(grp * kScAccCols + c0 + n0))
+                                : "memory");
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                            const float4* cc4 = reinterpret_cast<const float4*>(cc_s + c0 + n0);
+                            float lo[8], hi[8];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {   // scores of 4 columns, index in the low mantissa bits, as two sorted pairs
+                                const float4 c = cc4[j];
+                                const float s0 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * j + 0]), c.x), 4 * j + 0);
+                                const float s1 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * j + 1]), c.y), 4 * j + 1);
+                                const float s2 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * j + 2]), c.z), 4 * j + 2);
+                                const float s3 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * j + 3]), c.w), 4 * j + 3);
+                                lo[2 * j] = fminf(s0, s1);
+                                hi[2 * j] = fmaxf(s0, s1);
+                                lo[2 * j + 1] = fminf(s2, s3);
+                                hi[2 * j + 1] = fmaxf(s2, s3);
+                            }
+                            float l4[4], h4[4], l2[2], h2[2], l1, h1;   // tournament: 8 sorted pairs -> 4 -> 2 -> 1
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) merge2(lo[2 * j], hi[2 * j], lo[2 * j + 1], hi[2 * j + 1], l4[j], h4[j]);
+                            merge2(l4[0], h4[0], l4[1], h4[1], l2[0], h2[0]);
+                            merge2(l4[2], h4[2], l4[3], h4[3], l2[1], h2[1]);
+                            merge2(l2[0], h2[0], l2[1], h2[1], l1, h1);
+                            if (l1 < best) bchunk = n0;   // (strict: an equal score of a later block never displaces an earlier one)
+                            const float nb = fminf(best, l1);
+                            second = fmin3(fmaxf(best, l1), second, h1);
+                            best = nb;
+                        }
+                        const float cc2 = st->cc2;
+                        const float tau = tau_a * (xx_tile + 0.5f * cc2) + tau_b * (xx_tile + cc2) + (st->abs1 * sq_xx + st->abs2) + 1e-30f;
+                        const int a = bchunk + (int)(__float_as_uint(best) & 15u);
+                        const bool sure = (second - best > tau) && !st->force_exact;
+                        lab[q] = orig_s[c0 + (a < st->n_act ? a : 0)];
+                        if (!sure) doubt |= 1u << q;
+                    }
+                    // the accumulator may take the products of tile seq + 3
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_free[grp]);
+                    // near ties: the whole warp re-decides the cell in fp64 with the reference's arithmetic (exact_label_warp)
+                    if (__any_sync(0xffffffffu, doubt != 0 && live)) {
+#pragma unroll
+                        for (int q = 0; q < kScMaxSets; ++q) {
+                            if (q >= NS) break;
+                            unsigned redo = __ballot_sync(0xffffffffu, ((doubt >> q) & 1u) && live);
+                            if (!redo) continue;
+                            if (P.recheck_count && lane == 0) atomicAdd(P.recheck_count, (unsigned long long)__popc(redo));
+                            const ScoreSet* st = sets + q;
+                            while (redo) {
+                                const int src = __ffs(redo) - 1;
+                                redo &= redo - 1;
+                                const int v = exact_label_warp(slot, wq * 32 + src, d, st->mu, d, orig_s + st->col0, st->n_act, lane);
+                                if (lane == src) lab[q] = v;
+                            }
+                        }
+                    }
+                    if (live) {
+#pragma unroll
+                        for (int q = 0; q < kScMaxSets; ++q) {
+                            if (q >= NS) break;
+                            int32_t* out = sets[q].labels;
+                            if (out) out[mycell] = lab[q];
+                        }
+                        if (kPairs) {   // (ret1, ret2) of a penalty cell are neighbours in the bundle
+                            if (NS >= 2) atomicAdd(&pair_s[lab[0] * kk + lab[1]], 1u);
+                            if (NS >= 4) atomicAdd(&pair_s[kk2 + lab[2] * kk + lab[3]], 1u);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[s_idx]);
+                }
+                if (++s_idx == S) {
+                    s_idx = 0;
+                    ++s_use;
+                }
+                if (++r3 == kScAccs) {
+                    r3 = 0;
+                    ++u3;
+                }
+            }
+        }
+        tile = p_end;
+        ++p;
+    }
+    tc_fence_before();
+    consumer_barrier<kScConsumerWarps * 32>();
+    if (kPairs && prev_pairs > 0) {
+        for (int e = tid; e < prev_pairs * kk2; e += kScConsumerWarps * 32) {
+            const unsigned int v = pair_s[e];
+            if (v) atomicAdd(P.pair_tables + (size_t)(prev_pair0 + e / kk2) * kk2 + (e % kk2), (unsigned long long)v);
+        }
+    }
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+int plan_score_pass(int d, int k_max, int sets_wanted, int fuse_kk, ScorePlan* plan) {
+    static const bool off = getenv("DPR_SCORE_OLD") != nullptr;   // A/B aid: keep the bundled instance of tc_pass_kernel
+    if (off || d < 1 || k_max < 2 || sets_wanted < 2) return 0;
+    const int k16 = (d + 15) >> 4;
+    if (k16 > 4) return 0;   // beside the 3 accumulators tensor memory holds 2 A buffers of 2 x 8 * k16 columns
+    const int ncol = (k_max + 15) & ~15;
+    if (ncol > 64) return 0;
+    const int sets = (kScAccCols / ncol >= 4 && sets_wanted >= 4) ? 4 : 2;
+    const int b_rows = sets * ncol;
+    const int acols = 8 * k16;
+    const size_t stage_bytes = (((size_t)(tile_groups(d) + (tile_groups(d) & 1)) * kGroupFloats * 4) + 127) & ~(size_t)127;
+    const size_t bars = 512;
+    const size_t sets_bytes = 512;   // kScMaxSets x ScoreSet (64 B)
+    const size_t cc_bytes = ((size_t)b_rows * 4 + 127) & ~(size_t)127;
+    const size_t b_bytes = (size_t)2 * k16 * b_rows * 16;
+    size_t pair_bytes = 0;
+    int kk = 0;
+    if (fuse_kk > 0) {
+        pair_bytes = (((size_t)(sets / 2) * fuse_kk * fuse_kk * 4) + 127) & ~(size_t)127;
+        if (pair_bytes <= 40 * 1024) kk = fuse_kk; else pair_bytes = 0;   // wide tables: the labels go to HBM and contingency_kernel counts them
+    }
+    const size_t fixed = bars + sets_bytes + 2 * cc_bytes + 2 * b_bytes + pair_bytes;
+    if (fixed + 5 * stage_bytes > (size_t)kSmemBudget) return 0;
+    int S = (int)(((size_t)kSmemBudget - fixed) / stage_bytes);
+    if (S > kScMaxStages) S = kScMaxStages;
+    plan->d = d;
+    plan->k16 = k16;
+    plan->ncol_max = ncol;
+    plan->sets = sets;
+    plan->b_rows = b_rows;
+    plan->acols = acols;
+    plan->wait_hint = 2000;
+    plan->kk = kk;
+    plan->stages = S;
+    plan->stage_floats = (int)(stage_bytes / 4);
+    plan->off_sets = (int)bars;
+    plan->off_cc = plan->off_sets + (int)sets_bytes;
+    plan->off_orig = plan->off_cc + (int)cc_bytes;
+    plan->off_bh = plan->off_orig + (int)cc_bytes;
+    plan->off_bl = plan->off_bh + (int)b_bytes;
+    plan->off_pairs = plan->off_bl + (int)b_bytes;
+    plan->off_stages = plan->off_pairs + (int)pair_bytes;
+    plan->smem_bytes = (size_t)plan->off_stages + (size_t)S * stage_bytes;
+    return 1;
+}
+
+int launch_score_pass(const ScorePlan& plan, const PassParams& P, int grid, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        DPR_CUDA(cudaFuncSetAttribute(score_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        DPR_CUDA(cudaFuncSetAttribute(score_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        configured = true;
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx().time_passes) {
+        DPR_CUDA(cudaEventCreate(&e0));
+        DPR_CUDA(cudaEventCreate(&e1));
+        DPR_CUDA(cudaEventRecord(e0, stream));
+    }
+    if (P.pair_tables && plan.kk > 0) score_pass_kernel<true><<<grid, kScThreads, plan.smem_bytes, stream>>>(P, plan);
+    else score_pass_kernel<false><<<grid, kScThreads, plan.smem_bytes, stream>>>(P, plan);
+    count_launch();
+    if (e0) {
+        DPR_CUDA(cudaEventRecord(e1, stream));
+        ctx().pass_events.emplace_back(e0, e1);
+    }
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+
+}  // namespace dpr

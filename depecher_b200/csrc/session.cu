@@ -24,7 +24,7 @@ int Session::alloc(T** p, size_t count, bool zero) {
     return DPR_OK;
 }
 
-int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) {
+int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums, int pair_kk) {
     DPR_TRY(ensure_ready());
     if (specs.empty()) return fail(DPR_ERR_INVALID, "no problems");
     d_ = d;
@@ -45,6 +45,10 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
             max_run = std::max(max_run, (int)run);
         }
     use_tc = !ctx().force_ffma && plan_tc_pass(d, k_max_, std::min(max_run, kTcMaxSets), &tc_plan) != 0;
+    // several sets over the same cells: the scoring pass (its own bundle size; it reads the tensor-core tables of the problems)
+    use_score = use_tc && !want_sums && max_run >= 2 && plan_score_pass(d, k_max_, max_run, pair_kk, &score_plan) != 0;
+    fuse_pairs = use_score && pair_kk > 0 && score_plan.kk == pair_kk && specs.size() % 2 == 0;
+    const int bundle_sets = use_score ? score_plan.sets : tc_plan.sets;
     const int P = (int)specs.size();
     h_problems.assign(P, Problem{});
     // pooled per-problem storage
@@ -99,7 +103,7 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums) 
             --bundle_left;
         } else {
             leader = p;
-            bundle_left = use_tc && !want_sums ? tc_plan.sets - 1 : 0;
+            bundle_left = use_tc && !want_sums ? bundle_sets - 1 : 0;
             pr.bundle = 1;
             pr.first_tile = tile;
             pr.n_tiles = (int)((s.n + kSlotCells - 1) / kSlotCells);
@@ -198,6 +202,11 @@ int Session::pass(int mode, bool compare_old) {
     P.move_counts = move_counts_;
     P.move_cap = move_cap_;
     P.move_overflow = move_overflow_;
+    P.pair_tables = fuse_pairs ? pair_tables : nullptr;
+    if (use_score && has_bundles_ && mode == kPassAssign) {
+        if (fuse_pairs && !pair_tables) return fail(DPR_ERR_STATE, "scoring session: the pair tables were not set");
+        return launch_score_pass(score_plan, P, grid, ctx().stream);
+    }
     if (use_tc && mode != kPassSums) {
         DPR_TRY(launch_tc_pass(tc_plan, P, grid, ctx().stream));
         // delta iterations (every Lloyd pass of a fit but the first, where it finds nothing to do): the pass recorded the moved cells, this sums their rows

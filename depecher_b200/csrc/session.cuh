@@ -32,7 +32,9 @@ public:
     Session& operator=(const Session&) = delete;
 
     // d is common to all problems.  want_sums: allocate the Lloyd partial tables.
-    int init(const std::vector<ProblemSpec>& specs, int d, bool want_sums);
+    // pair_kk > 0 (assignment-only sessions whose problems 2c, 2c + 1 are the pairs of a penalty search): ask for the contingency
+    // counts of each pair to be taken inside the pass, tables pair_kk wide (fuse_pairs tells whether the plan granted it)
+    int init(const std::vector<ProblemSpec>& specs, int d, bool want_sums, int pair_kk = 0);
     int set_centres(int p, const double* mu_rowmajor_host);        // H2D of one centre matrix
     int set_centres_device(int p, const double* mu_rowmajor_dev);   // D2D
     int get_centres(int p, double* mu_rowmajor_host);
@@ -56,6 +58,10 @@ public:
     PassPlan plan{};
     TcPlan tc_plan{};
     bool use_tc = false;       // shape fits the tcgen05 pass (tc_pass.cu); otherwise the FFMA pass runs
+    ScorePlan score_plan{};
+    bool use_score = false;    // assignment-only session with bundles that fits the scoring pass (score_pass.cu)
+    bool fuse_pairs = false;   // ... which also takes the pairs' contingency counts
+    unsigned long long* pair_tables = nullptr;   // device, [n_problems / 2][pair_kk^2], zeroed by the caller (fuse_pairs)
     bool allow_delta = true;   // let finalize switch a problem to delta accumulation when few labels change
     // Several ranks (dpr_comm_init): the problems of THIS session are row shards of fits that every rank runs in step, so each
     // iteration's tables are summed over the ranks.  Opt-in: only the row-sharded entry points (dpr_dataset_find_centers_from,

@@ -57,8 +57,8 @@ __device__ __forceinline__ float pack_idx(float s, int idx) {
 // takes active slots a, a+32, ...; the (distance, slot) pairs are then reduced lexicographically, which is
 // the sequential first-minimum scan (a NaN distance is never chosen unless it is the first one, like there).
 // ---------------------------------------------------------------------------------------------------
-static __device__ __noinline__ int exact_label_warp(const float* __restrict__ slot, int cell, int d, const double* __restrict__ mu, int ld,
-                                                    const int32_t* __restrict__ orig, int n_slots, int lane) {   // ld: doubles between rows of mu
+static __device__ __forceinline__ int exact_label_warp_inline(const float* __restrict__ slot, int cell, int d, const double* __restrict__ mu, int ld,
+                                                              const int32_t* __restrict__ orig, int n_slots, int lane) {   // ld: doubles between rows of mu
     double bv = INFINITY;
     int bi = 0x7fffffff;
     bool first_nan = false;
@@ -105,6 +105,12 @@ static __device__ __noinline__ int exact_label_warp(const float* __restrict__ sl
     first_nan = __shfl_sync(0xffffffffu, (int)first_nan, 0) != 0;
     if (first_nan || bi == 0x7fffffff) bi = 0;   // nothing compares below a NaN / every distance is NaN or +inf: the first row stays
     return n_slots > 0 ? orig[bi] : 0;
+}
+// out of line: the path is rare and the pass kernels are short of registers (score_pass.cu, whose warp roles run under different
+// register limits, inlines it into the role that calls it instead)
+static __device__ __noinline__ int exact_label_warp(const float* __restrict__ slot, int cell, int d, const double* __restrict__ mu, int ld,
+                                                    const int32_t* __restrict__ orig, int n_slots, int lane) {
+    return exact_label_warp_inline(slot, cell, d, mu, ld, orig, n_slots, lane);
 }
 
 __device__ __forceinline__ void red_add(double* p, double v) { atomicAdd(p, v); }

@@ -22,7 +22,9 @@
 #include "tc_device.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 namespace dpr {
 
@@ -30,21 +32,53 @@ constexpr int kScAccs = 3;          // accumulators = reducing groups
 constexpr int kScABufs = 2;         // A-operand buffers (tiles split but not yet multiplied)
 constexpr int kScAccCols = 128;     // TMEM columns per accumulator: the stacked sets of a bundle
 constexpr int kScConsumerWarps = 4 * (kScAccs + 1);   // 12 reducing + 4 splitting
-constexpr int kScThreads = (kScConsumerWarps + 2) * 32;
+constexpr int kScThreads = (kScConsumerWarps + 4) * 32;   // + one warpgroup of service warps: products, bulk copies, two idle
+// Registers per thread after the prologue (setmaxnreg works on warpgroups = 4 consecutive warps; every sub-partition of the SM holds one
+// warp of each warpgroup, so 3 * reduce + split + service <= 512): the reducing warps hold two 16-column blocks of scores
+constexpr int kScRegsReduce = 112, kScRegsSplit = 88, kScRegsService = 56;
+static_assert(kScAccs * kScRegsReduce + kScRegsSplit + kScRegsService <= 480, "the CTA owns 5 warps x 96 registers per SM sub-partition");
 
-struct ScoreSet {          // one centre set of the current bundle (shared memory)
-    int32_t col0, ncols;   // its accumulator columns: [col0, col0 + ncols), ncols a multiple of 16
-    int32_t n_act, trivial, force_exact, pad_;
-    float unscale, abs1, abs2, cc2;
+struct ScoreSet {          // one centre set of the current bundle (shared memory); the first 32 bytes are what the end of a set's reduction reads
+    int32_t col0, n_act;   // its first accumulator column; active centres
+    float tk_a, tk_b;      // near-tie bound in key units: tk_a * X + tk_b * sqrt(X) + tk_c, X = the tile's bound of ||x||^2 (+inf: always exact)
+    float tk_c;
+    int32_t ncols, trivial, pad_;   // columns (a multiple of 16); fewer than two active rows: every label 0
     int32_t* labels;       // nullable: scoring with fused contingency counts stores no labels
     const double* mu;      // exact centres (global memory; only the rare fp64 re-decisions read them)
 };
+
+static_assert(sizeof(ScoreSet) == 48, "the reducer reads a set's first 16 bytes as one float4");
 
 // the two smallest of a sorted pair (a0 <= a1) and a sorted pair (b0 <= b1), sorted
 __device__ __forceinline__ void merge2(float a0, float a1, float b0, float b1, float& lo, float& hi) {
     lo = fminf(a0, b0);
     hi = fmin3(fmaxf(a0, b0), a1, b1);
 }
+
+// 16 accumulator columns of this warp's 32 lanes; the registers are valid after tmem_wait_ld16 (which names them, so that no use
+// can be scheduled above the wait)
+__device__ __forceinline__ void tmem_ld16_raw(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]),
+                   "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
+}
+
+#ifdef DPR_SC_PROFILE
+#define SC_PROF_DECL long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pa_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pn_ = 0
+#define SC_PROF(i) do { pt_[i] = clock64(); if (i > 0) pa_[i] += pt_[i] - pt_[i - 1]; } while (0)
+#define SC_PROF_TILE ++pn_
+#else
+#define SC_PROF_DECL
+#define SC_PROF(i)
+#define SC_PROF_TILE
+#endif
 
 template <bool kPairs>
 __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassParams P, const ScorePlan T) {
@@ -63,6 +97,8 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
     uint64_t* tables_ready = acc_free + kScAccs;          // the bundle's centre tables are in shared memory
     uint32_t* tmem_word = reinterpret_cast<uint32_t*>(tables_ready + 1);
     int32_t* n_total_s = reinterpret_cast<int32_t*>(tmem_word + 1);   // accumulator columns the current bundle uses
+    int32_t* n_chunks_s = n_total_s + 1;                               // blocks of 16 columns that hold scores (trivial sets have none)
+    uint2* chunk_s = reinterpret_cast<uint2*>(n_chunks_s + 2);   // (8-byte aligned)   // [<= 8] .x: column | set << 8 | first of its set << 12 | last << 13; .y: its set's un-scaling factor
     ScoreSet* sets = reinterpret_cast<ScoreSet*>(smem + T.off_sets);
     float* cc_s = reinterpret_cast<float*>(smem + T.off_cc);          // [b_rows] ||c||^2 per accumulator column (padding: +huge)
     int32_t* orig_s = reinterpret_cast<int32_t*>(smem + T.off_orig);  // [b_rows] column -> row of its set's mu (padding: -1)
@@ -118,6 +154,12 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
     }
     int tile = t_begin;
 
+    // ---- hand the registers to the warps that need them
+    if (warp >= kScConsumerWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kScRegsService));
+        if (warp >= kScConsumerWarps + 2) return;   // (the warpgroup's two spare warps)
+    }
+
     // ================================ producer warp: the ring of bulk copies ================================
     if (warp == kScConsumerWarps + 1) {
         int s = 0, issued = 0;
@@ -156,6 +198,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
         const uint32_t lbo = (uint32_t)T.b_rows * 16u;   // bytes between the 8-marker groups of a stacked B operand
         const uint64_t desc_h0 = umma_desc(smem_u32(bh), lbo, 128), desc_l0 = umma_desc(smem_u32(bl), lbo, 128);
         const uint64_t desc_step = (uint64_t)((2u * lbo) >> 4);   // one K = 16 step = two marker groups further
+        SC_PROF_DECL;
         while (tile < t_end) {
             const Problem* pr = P.problems + p;
             const int p_end = min(t_end, pr->first_tile + pr->n_tiles);
@@ -170,8 +213,11 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
             const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 4) << 24) | ((n_total >> 3) << 17);   // D fp32, A/B fp16, both K-major, M = 128, N = n_total
             for (; tile < p_end; ++tile, ++seq) {
                 const uint32_t b = seq & 1u, ub = seq >> 1;
+                SC_PROF(0);
                 mbar_wait_hint(&a_ready[b], ub & 1u, T.wait_hint);
+                SC_PROF(1);
                 if (u3 > 0) mbar_wait_hint(&acc_free[c], (u3 - 1u) & 1u, T.wait_hint);
+                SC_PROF(2);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t acc = tmem + c * (uint32_t)kScAccCols;
@@ -185,6 +231,8 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
                     umma_commit(&a_free[b]);
                 }
                 __syncwarp();
+                SC_PROF(3);
+                SC_PROF_TILE;
                 if (++c == kScAccs) {
                     c = 0;
                     ++u3;
@@ -192,16 +240,22 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
             }
             ++p;
         }
+#ifdef DPR_SC_PROFILE
+        if (blockIdx.x == 3 && lane == 0 && pn_) printf("issuer  tiles %lld: wait_a_ready %lld wait_acc_free %lld issue %lld\n", pn_, pa_[1] / pn_, pa_[2] / pn_, pa_[3] / pn_);
+#endif
         return;
     }
 
     // ================================ consumer warps: 3 reducing groups + 1 splitting group ================================
+    // The two roles run under different register limits (setmaxnreg): each gets its own copy of the walk over the ranges, so that the
+    // compiler never has to fit the reducing code under the splitting warps' limit.
     const int grp = warp >> 2, wq = warp & 3;   // group; TMEM lane quarter this warp may touch
-    const bool splitter = grp == kScAccs;
+    auto consumer = [&](auto role) {
+    constexpr bool splitter = decltype(role)::value;
     const int mycell_in_tile = wq * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(wq * 32) << 16);
     const int steps8 = (d + 7) >> 3;   // 8-marker steps that hold data
-    if (splitter) {   // zero padding of the last K = 16 step, in both parts of both A buffers: written once
+    if constexpr (splitter) {   // zero padding of the last K = 16 step, in both parts of both A buffers: written once
         const uint32_t z[4] = {0u, 0u, 0u, 0u};
         for (int b = 0; b < kScABufs; ++b)
             for (int c = 4 * steps8; c < acols; c += 4) {
@@ -213,12 +267,13 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
     // error bound of a score: see tc_pass.cu.  Here 3 * k16 products accumulate into one column (2^-21 allowed per step, measured
     // <= 2^-24), and there is no sum of two accumulator halves.
     const float tau_a = 2.f * (3.f * 2.3841858e-7f + (float)(3 * k16 + 1) * 4.7683716e-7f);
-    const float tau_b = 2.f * (4.f * 5.9604645e-8f) + 3.8146973e-6f;
+    const float tau_b = 2.f * (4.f * 5.9604645e-8f);   // (the index packing has its own, absolute term: ScoreSet::tau_q)
 
+    SC_PROF_DECL;
     uint32_t seq = 0;               // tiles this CTA has walked past
     int s_idx = 0;                  // stage of tile seq (= seq % S)
     uint32_t s_use = 0;             // seq / S
-    uint32_t r3 = 0, u3 = 0;        // seq % 3, seq / 3
+    uint32_t r3 = 0;                // seq % 3
     int prev_pair0 = -1, prev_pairs = 0;   // the pair tables in shared memory belong to these global pairs (kPairs)
     const int tid = threadIdx.x;    // < 512
 
@@ -246,8 +301,27 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
         {   // the bundle's tables: stacked B operands, ||c||^2 and the column -> row maps, per-set constants
             int col0[kScMaxSets + 1];
             col0[0] = 0;
+            float ccm = 0.f;   // largest ||c||^2 of the bundle
 #pragma unroll
-            for (int q = 0; q < kScMaxSets; ++q) col0[q + 1] = col0[q] + (q < NS ? P.problems[p + q].hdr->tc_n : 0);
+            for (int q = 0; q < kScMaxSets; ++q) {
+                col0[q + 1] = col0[q] + (q < NS ? P.problems[p + q].hdr->tc_n : 0);
+                if (q < NS) ccm = fmaxf(ccm, P.problems[p + q].hdr->cc_max);
+            }
+            // Sortable integer keys with the column number inside, built on the FMA pipe (min / max share the half-rate ALU pipe with
+            // all logic; the less of it the reduction needs, the better).  With q a power of two >= 2^-19 x (largest |score| of the
+            // matrix under any set of the bundle) and M = 1.5 * 2^23 * q,
+            //     w   = fma(unscale, D, cc + M)          the score rounded to a multiple of q, plus M: every w lies in the binade of M,
+            //                                            so its bit pattern is  const + score / q  (one rounding)
+            //     key = bits(w) * 16 + i                 i = the column's number in its block of 16 (IMAD); int32 arithmetic wraps, but
+            //                                            all keys of a cell lie within 2^25 of one another
+            // Signed integer min / max on the keys order the scores to within q and carry the winner's column; a difference of two keys
+            // times q / 16 is the difference of the scores up to 3 q (cc + M rounds cc: q / 2; the fma: q / 2; twice; the column numbers: < q).
+            const float smax = *pr.xx_max + 2.0f * ccm;
+            int e2 = 0;
+            frexpf(smax, &e2);                                   // smax < 2^e2
+            const bool q_ok = smax > 0.f && smax < 1e30f && e2 > -90;
+            const float qq = q_ok ? ldexpf(1.f, e2 - 19) : 1.f;
+            const float big_m = q_ok ? 12582912.f * qq : 0.f;     // 1.5 * 2^23 * q
 #pragma unroll
             for (int q = 0; q < kScMaxSets; ++q) {
                 if (q >= NS) break;
@@ -261,40 +335,55 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
                     bl[(size_t)g * T.b_rows + col0[q] + r] = bsrc[(size_t)g * 2 * npad + npad + r];
                 }
                 for (int i = tid; i < nq; i += kScConsumerWarps * 32) {
-                    cc_s[col0[q] + i] = tab[i];
+                    // (padding columns: M + 2^20 q, above every real score and still inside the binade of M)
+                    cc_s[col0[q] + i] = i < pq->hdr->k_act ? tab[i] + big_m : big_m + 1048576.f * qq;
                     orig_s[col0[q] + i] = pq->tc_orig[i];
                 }
                 if (tid == 32 * q) {
                     const CentreHeader* h = pq->hdr;
+                    const float cc2 = 2.0f * h->cc_max, iq16 = 16.f / qq;
                     ScoreSet st;
                     st.col0 = col0[q];
-                    st.ncols = nq;
                     st.n_act = h->k_act;
+                    st.ncols = nq;
                     st.trivial = h->trivial;
-                    st.force_exact = h->force_exact;
                     st.pad_ = 0;
-                    st.unscale = h->tc_unscale;
-                    st.abs1 = h->tc_abs1;
-                    st.abs2 = h->tc_abs2;
-                    st.cc2 = 2.0f * h->cc_max;
+                    // tau = tau_a (X + cc2 / 2) + tau_b (X + cc2) + abs1 sqrt(X) + abs2 + 3 q   (tc_pass.cu's bound without its index-bit
+                    // term, plus the 3 q of the keys), divided by the key unit q / 16
+                    st.tk_a = (tau_a + tau_b) * iq16;
+                    st.tk_b = h->tc_abs1 * iq16;
+                    st.tk_c = (h->force_exact || !q_ok) ? INFINITY : (tau_a * 0.5f * cc2 + tau_b * cc2 + h->tc_abs2 + 3.f * qq) * iq16;
                     st.labels = pq->labels;
                     st.mu = pq->mu;
                     sets[q] = st;
                 }
             }
-            if (tid == 0) *n_total_s = col0[NS];
+            if (tid == 0) {
+                *n_total_s = col0[NS];
+                int nch = 0;
+                for (int q = 0; q < NS; ++q) {
+                    if (P.problems[p + q].hdr->trivial) continue;
+                    for (int c = col0[q]; c < col0[q + 1]; c += 16)
+                        chunk_s[nch++] = make_uint2((uint32_t)c | ((uint32_t)q << 8) | (c == col0[q] ? 1u << 12 : 0u) | (c + 16 == col0[q + 1] ? 1u << 13 : 0u),
+                                                    __float_as_uint(P.problems[p + q].hdr->tc_unscale));
+                }
+                *n_chunks_s = nch;
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the B operands were written through the generic proxy
         consumer_barrier<kScConsumerWarps * 32>();
         if (tid == 0) mbar_arrive(tables_ready);
         const float scale_x = pr.hdr->tc_scale_x;   // (the same for every set of a bundle: it depends on the cells only)
 
-        if (splitter) {
+        if constexpr (splitter) {
             // ---- fp32 cells -> fp16 high / low parts, parked in tensor memory as the A operands of tile seq
             for (; tile < p_end; ++tile, ++seq) {
                 const uint32_t b = seq & 1u, ub = seq >> 1;
+                SC_PROF(0);
                 mbar_wait_hint(&full[s_idx], s_use & 1u, T.wait_hint);
+                SC_PROF(1);
                 if (ub > 0) mbar_wait_hint(&a_free[b], (ub - 1u) & 1u, T.wait_hint);
+                SC_PROF(2);
                 tc_fence_after();
                 const float* slot = stages + (size_t)s_idx * T.stage_floats;
                 const float4* st4 = reinterpret_cast<const float4*>(slot) + mycell_in_tile;
@@ -305,6 +394,8 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_ready[b]);
+                SC_PROF(3);
+                SC_PROF_TILE;
                 if (++s_idx == S) {
                     s_idx = 0;
                     ++s_use;
@@ -312,72 +403,103 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
             }
         } else {
             // ---- scores of tile seq (accumulator grp) -> labels of every set (+ contingency counts of the pairs)
-            for (; tile < p_end; ++tile, ++seq) {
-                const bool mine = r3 == (uint32_t)grp;
-                if (mine) {
-                    const float* slot = stages + (size_t)s_idx * T.stage_floats;
-                    const int64_t mycell = (int64_t)(tile - pr.first_tile) * kSlotCells + mycell_in_tile;
+            // this group's tiles of the range: every third one (tile seq goes to accumulator seq % 3).  The tile's norm bound comes from
+            // global memory: fetched one own tile ahead, so that its latency is never waited for
+            const int count = p_end - tile, t0 = tile - pr.first_tile;
+            const int j0 = (int)((uint32_t)grp + kScAccs - r3) % kScAccs;
+            int s_mine = s_idx + j0;
+            while (s_mine >= S) s_mine -= S;
+            uint32_t u_mine = (seq + (uint32_t)j0) / kScAccs;
+            float xx_next = j0 < count ? pr.tile_xx[t0 + j0] : 0.f;
+            for (int j = j0; j < count; j += kScAccs, ++u_mine) {
+                {
+                    const float* slot = stages + (size_t)s_mine * T.stage_floats;
+                    const int s_cur = s_mine;
+                    s_mine += kScAccs;
+                    while (s_mine >= S) s_mine -= S;
+                    const int64_t mycell = (int64_t)(t0 + j) * kSlotCells + mycell_in_tile;
                     const bool live = mycell < pr.n;
-                    const float xx_tile = pr.tile_xx[tile - pr.first_tile];
+                    const float xx_tile = xx_next;
+                    if (j + kScAccs < count) xx_next = pr.tile_xx[t0 + j + kScAccs];
                     const float sq_xx = sqrtf(xx_tile);
-                    mbar_wait_hint(&acc_full[grp], u3 & 1u, T.wait_hint);
+                    SC_PROF(0);
+                    mbar_wait_hint(&acc_full[grp], u_mine & 1u, T.wait_hint);
                     tc_fence_after();
-                    int lab[kScMaxSets] = {0, 0, 0, 0};
+                    SC_PROF(1);
+                    // The bundle's scores are walked in blocks of 16 accumulator columns (chunk list built with the tables; the sets of a
+                    // bundle follow one another, trivial sets have no block).  The tcgen05.ld of block c + 1 is in flight while block c is
+                    // reduced: two register buffers, the loop unrolled by two.
+                    uint32_t labs = 0;    // labels of the bundle's sets, 8 bits each (k <= 64 in this kernel)
                     unsigned doubt = 0;   // bit q: this cell's decision for set q needs the exact path
+                    int best = 0x7fffffff, second = 0x7fffffff, bcol = 0;
+                    const int nch = *n_chunks_s;
+                    const uint32_t acc_base = lane_base + (uint32_t)(grp * kScAccCols);
+                    auto release_acc = [&]() {   // every score of the tile is in registers: the accumulator may take the products of tile seq + 3
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_free[grp]);
+                    };
+                    auto reduce = [&](const uint32_t (&v)[16], int c) {
+                        const uint2 ci = chunk_s[c];   // .x: column | set << 8 | first block of its set << 12 | last << 13; .y: the set's un-scaling factor
+                        const uint32_t info = ci.x;
+                        const float unscale = __uint_as_float(ci.y);
+                        const int col = (int)(info & 255u);
+                        const float4* cc4 = reinterpret_cast<const float4*>(cc_s + col);
+                        int w[16];
 #pragma unroll
-                    for (int q = 0; q < kScMaxSets; ++q) {
-                        if (q >= NS) break;
-                        const ScoreSet* st = sets + q;
-                        if (st->trivial) continue;   // fewer than two active rows: every label 0 (Clusterer.cpp:50-53)
-                        const int c0 = st->col0, nq = st->ncols;
-                        const float unscale = st->unscale;
-                        float best = 3.3e38f, second = 3.3e38f;
-                        int bchunk = 0;
-                        for (int n0 = 0; n0 < nq; n0 += 16) {
-                            uint32_t v[16];
-                            asm volatile(
-                                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                                : "r"(lane_base + (uint32_t)(grp * kScAccCols + c0 + n0))
-                                : "memory");
-                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                            const float4* cc4 = reinterpret_cast<const float4*>(cc_s + c0 + n0);
-                            float lo[8], hi[8];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {   // scores of 4 columns, index in the low mantissa bits, as two sorted pairs
-                                const float4 c = cc4[j];
-                                const float s0 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * j + 0]), c.x), 4 * j + 0);
-                                const float s1 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * j + 1]), c.y), 4 * j + 1);
-                                const float s2 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * j + 2]), c.z), 4 * j + 2);
-                                const float s3 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * j + 3]), c.w), 4 * j + 3);
-                                lo[2 * j] = fminf(s0, s1);
-                                hi[2 * j] = fmaxf(s0, s1);
-                                lo[2 * j + 1] = fminf(s2, s3);
-                                hi[2 * j + 1] = fmaxf(s2, s3);
-                            }
-                            float l4[4], h4[4], l2[2], h2[2], l1, h1;   // tournament: 8 sorted pairs -> 4 -> 2 -> 1
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) merge2(lo[2 * j], hi[2 * j], lo[2 * j + 1], hi[2 * j + 1], l4[j], h4[j]);
-                            merge2(l4[0], h4[0], l4[1], h4[1], l2[0], h2[0]);
-                            merge2(l4[2], h4[2], l4[3], h4[3], l2[1], h2[1]);
-                            merge2(l2[0], h2[0], l2[1], h2[1], l1, h1);
-                            if (l1 < best) bchunk = n0;   // (strict: an equal score of a later block never displaces an earlier one)
-                            const float nb = fminf(best, l1);
-                            second = fmin3(fmaxf(best, l1), second, h1);
-                            best = nb;
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 cq = cc4[j];
+                            w[4 * j + 0] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 0]), cq.x)) * 16u + (unsigned)(4 * j + 0));
+                            w[4 * j + 1] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 1]), cq.y)) * 16u + (unsigned)(4 * j + 1));
+                            w[4 * j + 2] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 2]), cq.z)) * 16u + (unsigned)(4 * j + 2));
+                            w[4 * j + 3] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 3]), cq.w)) * 16u + (unsigned)(4 * j + 3));
                         }
-                        const float cc2 = st->cc2;
-                        const float tau = tau_a * (xx_tile + 0.5f * cc2) + tau_b * (xx_tile + cc2) + (st->abs1 * sq_xx + st->abs2) + 1e-30f;
-                        const int a = bchunk + (int)(__float_as_uint(best) & 15u);
-                        const bool sure = (second - best > tau) && !st->force_exact;
-                        lab[q] = orig_s[c0 + (a < st->n_act ? a : 0)];
-                        if (!sure) doubt |= 1u << q;
+                        // the smallest key b: a tree of 3-input mins (8 instructions for 16 keys).  The second smallest: the keys are distinct
+                        // (column number inside), so key - b - 1 as an UNSIGNED number is huge for the smallest key and (key - b - 1) for
+                        // every other one: second = b + 1 + unsigned-min of those (16 adds that may run on the FMA pipe, 8 more 3-input mins)
+                        const int b = min(__vimin3_s32(__vimin3_s32(w[0], w[1], w[2]), __vimin3_s32(w[3], w[4], w[5]), __vimin3_s32(w[6], w[7], w[8])),
+                                          __vimin3_s32(__vimin3_s32(w[9], w[10], w[11]), __vimin3_s32(w[12], w[13], w[14]), w[15]));
+                        const int nb1 = -(b + 1);
+                        unsigned u[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) u[j] = (unsigned)(w[j] + nb1);
+                        const unsigned um = min(__vimin3_u32(__vimin3_u32(u[0], u[1], u[2]), __vimin3_u32(u[3], u[4], u[5]), __vimin3_u32(u[6], u[7], u[8])),
+                                                __vimin3_u32(__vimin3_u32(u[9], u[10], u[11]), __vimin3_u32(u[12], u[13], u[14]), u[15]));
+                        const int sec = (int)((unsigned)(b + 1) + um);
+                        if (info & (1u << 12)) {   // first block of a set
+                            best = b;
+                            second = sec;
+                            bcol = col;
+                        } else {
+                            if (b < best) bcol = col;   // (strict: an equal key of a later block never displaces an earlier one)
+                            second = __vimin3_s32(max(best, b), second, sec);
+                            best = min(best, b);
+                        }
+                        if (info & (1u << 13)) {   // the set is complete: its label, and whether the two best scores are safely apart
+                            const int q = (int)((info >> 8) & 15u);
+                            const float4 s0 = *reinterpret_cast<const float4*>(sets + q);   // col0, n_act, tk_a, tk_b
+                            const float tk = fmaf(s0.z, xx_tile, fmaf(s0.w, sq_xx, sets[q].tk_c));
+                            const int a = bcol - __float_as_int(s0.x) + (best & 15);
+                            labs |= (uint32_t)orig_s[__float_as_int(s0.x) + (a < __float_as_int(s0.y) ? a : 0)] << (8 * q);
+                            if (!((float)(second - best) > tk)) doubt |= 1u << q;
+                        }
+                    };
+                    uint32_t va[16], vb[16];
+                    if (nch > 0) tmem_ld16_raw(acc_base + (chunk_s[0].x & 255u), va);
+                    else release_acc();
+                    for (int c = 0; c < nch; c += 2) {
+                        tmem_wait_ld16(va);
+                        if (c + 1 < nch) tmem_ld16_raw(acc_base + (chunk_s[c + 1].x & 255u), vb);
+                        else release_acc();
+                        reduce(va, c);
+                        if (c + 1 < nch) {
+                            tmem_wait_ld16(vb);
+                            if (c + 2 < nch) tmem_ld16_raw(acc_base + (chunk_s[c + 2].x & 255u), va);
+                            else release_acc();
+                            reduce(vb, c + 1);
+                        }
                     }
-                    // the accumulator may take the products of tile seq + 3
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_free[grp]);
+                    SC_PROF(2);
                     // near ties: the whole warp re-decides the cell in fp64 with the reference's arithmetic (exact_label_warp)
                     if (__any_sync(0xffffffffu, doubt != 0 && live)) {
 #pragma unroll
@@ -390,39 +512,44 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
                             while (redo) {
                                 const int src = __ffs(redo) - 1;
                                 redo &= redo - 1;
-                                const int v = exact_label_warp(slot, wq * 32 + src, d, st->mu, d, orig_s + st->col0, st->n_act, lane);
-                                if (lane == src) lab[q] = v;
+                                const int v = exact_label_warp_inline(slot, wq * 32 + src, d, st->mu, d, orig_s + st->col0, st->n_act, lane);
+                                if (lane == src) labs = (labs & ~(255u << (8 * q))) | ((uint32_t)v << (8 * q));
                             }
                         }
                     }
+                    SC_PROF(3);
                     if (live) {
 #pragma unroll
                         for (int q = 0; q < kScMaxSets; ++q) {
                             if (q >= NS) break;
                             int32_t* out = sets[q].labels;
-                            if (out) out[mycell] = lab[q];
+                            if (out) out[mycell] = (int32_t)((labs >> (8 * q)) & 255u);
                         }
                         if (kPairs) {   // (ret1, ret2) of a penalty cell are neighbours in the bundle
-                            if (NS >= 2) atomicAdd(&pair_s[lab[0] * kk + lab[1]], 1u);
-                            if (NS >= 4) atomicAdd(&pair_s[kk2 + lab[2] * kk + lab[3]], 1u);
+                            if (NS >= 2) atomicAdd(&pair_s[(labs & 255u) * kk + ((labs >> 8) & 255u)], 1u);
+                            if (NS >= 4) atomicAdd(&pair_s[kk2 + ((labs >> 16) & 255u) * kk + (labs >> 24)], 1u);
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[s_idx]);
-                }
-                if (++s_idx == S) {
-                    s_idx = 0;
-                    ++s_use;
-                }
-                if (++r3 == kScAccs) {
-                    r3 = 0;
-                    ++u3;
+                    if (lane == 0) mbar_arrive(&empty[s_cur]);
+                    SC_PROF(4);
+                    SC_PROF_TILE;
                 }
             }
+            seq += (uint32_t)count;
+            r3 = seq % kScAccs;
+            s_idx = (int)((uint32_t)(s_idx + count) % (uint32_t)S);
+            tile = p_end;
         }
         tile = p_end;
         ++p;
     }
+#ifdef DPR_SC_PROFILE
+    if (blockIdx.x == 3 && lane == 0 && wq == 0 && pn_) {
+        if (splitter) printf("splitter tiles %lld: wait_full %lld wait_a_free %lld split %lld\n", pn_, pa_[1] / pn_, pa_[2] / pn_, pa_[3] / pn_);
+        else printf("reducer %d tiles %lld: wait_acc_full %lld ld+argmin(all sets) %lld release+recheck %lld store+pairs %lld\n", grp, pn_, pa_[1] / pn_, pa_[2] / pn_, pa_[3] / pn_, pa_[4] / pn_);
+    }
+#endif
     tc_fence_before();
     consumer_barrier<kScConsumerWarps * 32>();
     if (kPairs && prev_pairs > 0) {
@@ -434,6 +561,14 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+    }
+    };   // consumer
+    if (grp == kScAccs) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kScRegsSplit));
+        consumer(std::true_type{});
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kScRegsReduce));
+        consumer(std::false_type{});
     }
 }
 
@@ -452,7 +587,7 @@ int plan_score_pass(int d, int k_max, int sets_wanted, int fuse_kk, ScorePlan* p
     const int acols = 8 * k16;
     const size_t stage_bytes = (((size_t)(tile_groups(d) + (tile_groups(d) & 1)) * kGroupFloats * 4) + 127) & ~(size_t)127;
     const size_t bars = 512;
-    const size_t sets_bytes = 512;   // kScMaxSets x ScoreSet (64 B)
+    const size_t sets_bytes = 512;   // kScMaxSets x ScoreSet (56 B)
     const size_t cc_bytes = ((size_t)b_rows * 4 + 127) & ~(size_t)127;
     const size_t b_bytes = (size_t)2 * k16 * b_rows * 16;
     size_t pair_bytes = 0;

@@ -4,18 +4,24 @@
 // (ret1, ret2) pair taken inside the pass so that no label ever goes to HBM (cluster_distance's inputs, :376 and :267-305).
 //
 // Same arithmetic as tc_pass.cu (fp16-split operands, fp32 accumulation, exact fp64 re-decision of every near tie: labels are
-// bit-exact), different shape — the round-1 bundled instance of tc_pass_kernel ran at 29 % of its HBM roofline, bound by a chain
-// of latencies per (tile, set) inside a consumer group and by reading two accumulator halves per score:
+// bit-exact), different shape — the round-1 bundled instance of tc_pass_kernel ran at 29 % of its HBM roofline (0.237-0.245 ms per
+// set at 10M x 40, K = 30), bound by a chain of latencies per (tile, set) inside a consumer group:
 //   * the centre sets of a bundle (up to 4) are STACKED along N: one B operand of sum(n_q) rows, so one round of products per
-//     tile serves every set (one wait per tile instead of one per set);
+//     tile serves every set (one wait per tile instead of one per set); a set only occupies round16(active centres) columns;
 //   * the three partial products xh*ch, xh*cl, xl*ch accumulate into the SAME columns (3 tcgen05.mma per K = 16 step), so a
-//     score is one TMEM column, not the sum of two: tensor-memory reads (64 B/cycle/SM, the tightest resource of this pass at
-//     K = 30) are halved and the add disappears; a set only occupies round16(active centres) columns;
+//     score is one TMEM column, not the sum of two halves: half the tcgen05.ld traffic, and the add disappears;
 //   * roles: one group of four warps only SPLITS tiles (fp32 -> fp16 high/low parts into one of two A buffers in tensor memory),
 //     three groups of four warps only REDUCE (tcgen05.ld -> two smallest scores -> label), one accumulator each, so the products of
 //     tile t+1 and t+2 run while tile t is reduced; one warp issues the products, one keeps the ring of bulk copies in flight.
-//     512 TMEM columns = 3 accumulators x 128 + 2 x (xh + xl);
-//   * the two smallest scores come from a tournament over 16-column blocks (independent compare/selects) instead of a serial scan.
+//     512 TMEM columns = 3 accumulators x 128 + 2 x (xh + xl).  The roles run under different register limits (setmaxnreg:
+//     112 / 88 / 56 registers per thread for reduce / split / service, 480 per sub-partition), each with its own copy of the code;
+//   * the reduction is built for the ALU pipe (min / max / logic at half the FMA pipe's rate) and for instruction-level
+//     parallelism (three reducing warps per scheduler: dependent-issue latency, not a pipe, is what binds): scores become sortable
+//     integer keys with the column number inside on the FMA pipe (one fma + one shift-add), the smallest key of a block of 16 is a
+//     tree of 3-input mins, the second smallest comes from an unsigned-min trick (add + min fuse into VIADDMNMX), and two blocks
+//     are reduced side by side without a branch between them.
+// Measured (profiles/r02_summary.md): 0.154 ms per set (4 sets per tile) = 2.85 TB/s of the 176 B per cell and 4 sets = 44 % of the
+// HBM roofline; tensor-memory reads are NOT the limit (profiles/microbench/ldtm_probe.cu: 215-370 B/cycle/SM, the pass needs ~25).
 #include "common.cuh"
 #include "fused_pass.cuh"
 #include "pass_device.cuh"
@@ -439,12 +445,14 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_free[grp]);
                     };
-                    auto reduce = [&](const uint32_t (&v)[16], int c) {
-                        const uint2 ci = chunk_s[c];   // .x: column | set << 8 | first block of its set << 12 | last << 13; .y: the set's un-scaling factor
-                        const uint32_t info = ci.x;
+                    // one block of 16 keys -> (smallest, second smallest).  The smallest key b: a tree of 3-input mins (8 instructions).  The
+                    // second smallest: the keys are distinct (column number inside), so key - b - 1 as an UNSIGNED number is huge for the
+                    // smallest key and (key - b - 1) for every other one: second = b + 1 + unsigned-min of those (add + min fuse into one
+                    // instruction, VIADDMNMX).  No branch inside: two blocks are reduced side by side (independent instruction streams for
+                    // the scheduler — with three reducing warps per sub-partition the pass is bound by dependent-issue latency, not by a pipe).
+                    auto top2 = [&](const uint32_t (&v)[16], const uint2 ci, int& b, int& sec) {
                         const float unscale = __uint_as_float(ci.y);
-                        const int col = (int)(info & 255u);
-                        const float4* cc4 = reinterpret_cast<const float4*>(cc_s + col);
+                        const float4* cc4 = reinterpret_cast<const float4*>(cc_s + (ci.x & 255u));
                         int w[16];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -454,28 +462,26 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
                             w[4 * j + 2] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 2]), cq.z)) * 16u + (unsigned)(4 * j + 2));
                             w[4 * j + 3] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 3]), cq.w)) * 16u + (unsigned)(4 * j + 3));
                         }
-                        // the smallest key b: a tree of 3-input mins (8 instructions for 16 keys).  The second smallest: the keys are distinct
-                        // (column number inside), so key - b - 1 as an UNSIGNED number is huge for the smallest key and (key - b - 1) for
-                        // every other one: second = b + 1 + unsigned-min of those (16 adds that may run on the FMA pipe, 8 more 3-input mins)
-                        const int b = min(__vimin3_s32(__vimin3_s32(w[0], w[1], w[2]), __vimin3_s32(w[3], w[4], w[5]), __vimin3_s32(w[6], w[7], w[8])),
-                                          __vimin3_s32(__vimin3_s32(w[9], w[10], w[11]), __vimin3_s32(w[12], w[13], w[14]), w[15]));
+                        b = min(__vimin3_s32(__vimin3_s32(w[0], w[1], w[2]), __vimin3_s32(w[3], w[4], w[5]), __vimin3_s32(w[6], w[7], w[8])),
+                                __vimin3_s32(__vimin3_s32(w[9], w[10], w[11]), __vimin3_s32(w[12], w[13], w[14]), w[15]));
                         const int nb1 = -(b + 1);
                         unsigned u[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) u[j] = (unsigned)(w[j] + nb1);
                         const unsigned um = min(__vimin3_u32(__vimin3_u32(u[0], u[1], u[2]), __vimin3_u32(u[3], u[4], u[5]), __vimin3_u32(u[6], u[7], u[8])),
                                                 __vimin3_u32(__vimin3_u32(u[9], u[10], u[11]), __vimin3_u32(u[12], u[13], u[14]), u[15]));
-                        const int sec = (int)((unsigned)(b + 1) + um);
-                        if (info & (1u << 12)) {   // first block of a set
-                            best = b;
-                            second = sec;
-                            bcol = col;
-                        } else {
-                            if (b < best) bcol = col;   // (strict: an equal key of a later block never displaces an earlier one)
-                            second = __vimin3_s32(max(best, b), second, sec);
-                            best = min(best, b);
-                        }
-                        if (info & (1u << 13)) {   // the set is complete: its label, and whether the two best scores are safely apart
+                        sec = (int)((unsigned)(b + 1) + um);
+                    };
+                    // a block's result into the running (best, second) of its set; at the set's last block: the label, and whether the two
+                    // best scores are safely apart
+                    auto fold = [&](const uint2 ci, int b, int sec) {
+                        const uint32_t info = ci.x;   // column | set << 8 | first block of its set << 12 | last << 13
+                        const bool first = (info & (1u << 12)) != 0;
+                        const int col = (int)(info & 255u);
+                        if (first || b < best) bcol = col;   // (strict: an equal key of a later block never displaces an earlier one)
+                        second = first ? sec : __vimin3_s32(max(best, b), second, sec);
+                        best = first ? b : min(best, b);
+                        if (info & (1u << 13)) {
                             const int q = (int)((info >> 8) & 15u);
                             const float4 s0 = *reinterpret_cast<const float4*>(sets + q);   // col0, n_act, tk_a, tk_b
                             const float tk = fmaf(s0.z, xx_tile, fmaf(s0.w, sq_xx, sets[q].tk_c));
@@ -484,21 +490,23 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
                             if (!((float)(second - best) > tk)) doubt |= 1u << q;
                         }
                     };
+                    // blocks two at a time: both loads in flight, one wait, both tournaments in one straight-line stretch (three or four at
+                    // a time need more than the 112 registers of a reducing warp: measured 0.158-0.162 ms per set with their spills, 0.154 with two)
                     uint32_t va[16], vb[16];
-                    if (nch > 0) tmem_ld16_raw(acc_base + (chunk_s[0].x & 255u), va);
-                    else release_acc();
                     for (int c = 0; c < nch; c += 2) {
+                        const uint2 ca = chunk_s[c], cb = chunk_s[c + 1 < nch ? c + 1 : c];
+                        tmem_ld16_raw(acc_base + (ca.x & 255u), va);
+                        tmem_ld16_raw(acc_base + (cb.x & 255u), vb);
                         tmem_wait_ld16(va);
-                        if (c + 1 < nch) tmem_ld16_raw(acc_base + (chunk_s[c + 1].x & 255u), vb);
-                        else release_acc();
-                        reduce(va, c);
-                        if (c + 1 < nch) {
-                            tmem_wait_ld16(vb);
-                            if (c + 2 < nch) tmem_ld16_raw(acc_base + (chunk_s[c + 2].x & 255u), va);
-                            else release_acc();
-                            reduce(vb, c + 1);
-                        }
+                        tmem_wait_ld16(vb);
+                        if (c + 2 >= nch) release_acc();
+                        int ba, sa, bb, sb;
+                        top2(va, ca, ba, sa);
+                        top2(vb, cb, bb, sb);
+                        fold(ca, ba, sa);
+                        if (c + 1 < nch) fold(cb, bb, sb);
                     }
+                    if (nch == 0) release_acc();
                     SC_PROF(2);
                     // near ties: the whole warp re-decides the cell in fp64 with the reference's arithmetic (exact_label_warp)
                     if (__any_sync(0xffffffffu, doubt != 0 && live)) {

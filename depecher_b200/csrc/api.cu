@@ -1,6 +1,8 @@
 // api.cu — the C ABI (include/depecher_b200.h): context, resident datasets and the entry points that
 // replace the reference's four Rcpp exports (/root/reference/src/InterfaceUtils.cpp:66-161).
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -974,6 +976,15 @@ static int grid_search_range(dpr_dataset_t ds, const int32_t* k, int32_t nk, con
         if (k[j] < 2) return fail(DPR_ERR_INVALID, "grid_search: every k must be >= 2");
     if (c_lo < 0 || c_hi > (int)iterations * nk * nreg || c_lo >= c_hi) return fail(DPR_ERR_INVALID, "grid_search: bad problem range");
     DPR_TRY(ensure_ready());
+    static const bool timing = getenv("DPR_TIMING") != nullptr;   // diagnostics: host wall-clock per phase (each closed by a stream synchronize)
+    auto now = [&]() {
+        if (timing) cudaStreamSynchronize(ctx().stream);
+        return std::chrono::steady_clock::now();
+    };
+    auto ms_since = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const auto t_start = now();
     const int d = ds->d;
     const int cells = c_hi - c_lo;
     const int F = 2 * cells;
@@ -1003,6 +1014,7 @@ static int grid_search_range(dpr_dataset_t ds, const int32_t* k, int32_t nk, con
         specs[f] = ProblemSpec{xb.as<float>() + (size_t)f * fit_floats, xb_xx.as<float>() + (size_t)f * tiles_b, ds->tile_xx + ds->n_pad / kSlotCells, (int64_t)boot_n, k[j], reg[l], 1,
                                lab_b.as<int32_t>() + (size_t)f * ldb};
     }
+    const auto t_boot = now();
     Session fits;
     DPR_TRY(fits.init(specs, d, true));
     {
@@ -1019,9 +1031,11 @@ static int grid_search_range(dpr_dataset_t ds, const int32_t* k, int32_t nk, con
             if (!sub.empty()) DPR_TRY(run_seeding(sub, d, k[j], seed));
         }
     }
+    const auto t_seed = now();
     DPR_TRY(fits.prepare());
     DPR_TRY(fits.lloyd(1000));
     DPR_TRY(fits.fetch_state());
+    const auto t_fit = now();
     // distinct labels of each bootstrap fit (n_used_clusters, :379-380) = clusters with a non-zero count
     std::vector<long long> counts((size_t)F * fits.k_max());
     DPR_CUDA(cudaMemcpyAsync(counts.data(), fits.h_problems[0].counts, sizeof(long long) * counts.size(), cudaMemcpyDeviceToHost, ctx().stream));
@@ -1072,6 +1086,10 @@ static int grid_search_range(dpr_dataset_t ds, const int32_t* k, int32_t nk, con
         for (int c = 0; c < nc; ++c) pairs[c] = PairJob{sspecs[2 * c].labels, sspecs[2 * c + 1].labels, ds->n, (uint32_t)(c_lo + c0 + c)};
         DPR_TRY(run_ari(pairs, (uint32_t)kmax, seed, ari.data() + c0));
     }
+    const auto t_score = now();
+    if (timing)
+        fprintf(stderr, "[dpr] grid_search %d problems: bootstrap %.2f ms, seeding %.2f, fits %.2f, scoring + ARI %.2f\n", cells, ms_since(t_start, t_boot),
+                ms_since(t_boot, t_seed), ms_since(t_seed, t_fit), ms_since(t_fit, t_score));
     // 5. per-problem results: its ARI and the mean number of used clusters of its two fits
     size_t coff = 0;
     for (int c = 0; c < cells; ++c) {

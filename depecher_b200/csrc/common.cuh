@@ -32,7 +32,7 @@ constexpr int kGroupFloats = kSlotCells * 4 + 4;   // one 4-marker group of a ti
 constexpr int kMaxKC = 32;        // centres per register-tile chunk (4 cells x 32 centres = 128 accumulators)
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kMaxChunks = 8;     // => fast path handles up to 256 active centres
+constexpr int kMaxChunks = 16;    // => the FFMA pass handles up to 480 centres (depecheAllData fits K = 3k: depeche(k = 100) needs 300, R/depecheAllData.R:30-31)
 constexpr int kSmemBudget = 227 * 1024;
 
 // Resident layout of a cell matrix ("tile-major"): cells are grouped in tiles of 128 consecutive cells, a tile is

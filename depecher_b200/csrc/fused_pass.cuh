@@ -72,7 +72,7 @@ constexpr int kScMaxSets = 4;
 struct ScorePlan {
     int32_t d, k16;          // markers; K = 16 * k16 per product chain
     int32_t ncol_max;        // accumulator columns reserved per set (k_max rounded up to 16)
-    int32_t sets;            // centre sets per bundle: 4 (ncol_max <= 32) or 2
+    int32_t sets;            // centre sets per bundle: 4 (ncol_max <= 32) or 2; 1 for a plain assignment
     int32_t b_rows;          // rows of the stacked B operands = sets * ncol_max
     int32_t acols;           // TMEM columns of one fp16 A operand
     int32_t wait_hint;
@@ -81,7 +81,7 @@ struct ScorePlan {
     int32_t off_sets, off_cc, off_orig, off_bh, off_bl, off_pairs, off_stages;
     size_t smem_bytes;
 };
-// returns 1 when the shape fits (d <= 64, k_max <= 64, >= 2 sets share their cells); fuse_kk > 0 asks for the contingency tables
+// returns 1 when the shape fits (d <= 64, k_max <= 64); fuse_kk > 0 asks for the contingency tables
 // of the pairs in shared memory (plan->kk stays 0 when they do not fit)
 int plan_score_pass(int d, int k_max, int sets_wanted, int fuse_kk, ScorePlan* plan);
 int launch_score_pass(const ScorePlan& plan, const PassParams& P, int grid, cudaStream_t stream);

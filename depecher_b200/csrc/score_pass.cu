@@ -585,12 +585,12 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
 // ---------------------------------------------------------------------------------------------------
 int plan_score_pass(int d, int k_max, int sets_wanted, int fuse_kk, ScorePlan* plan) {
     static const bool off = getenv("DPR_SCORE_OLD") != nullptr;   // A/B aid: keep the bundled instance of tc_pass_kernel
-    if (off || d < 1 || k_max < 2 || sets_wanted < 2) return 0;
+    if (off || d < 1 || k_max < 2 || sets_wanted < 1) return 0;
     const int k16 = (d + 15) >> 4;
     if (k16 > 4) return 0;   // beside the 3 accumulators tensor memory holds 2 A buffers of 2 x 8 * k16 columns
     const int ncol = (k_max + 15) & ~15;
     if (ncol > 64) return 0;
-    const int sets = (kScAccCols / ncol >= 4 && sets_wanted >= 4) ? 4 : 2;
+    const int sets = sets_wanted < 2 ? 1 : (kScAccCols / ncol >= 4 && sets_wanted >= 4) ? 4 : 2;   // (one set: a plain assignment — the pass is then bound by the splitting group, i.e. close to HBM)
     const int b_rows = sets * ncol;
     const int acols = 8 * k16;
     const size_t stage_bytes = (((size_t)(tile_groups(d) + (tile_groups(d) & 1)) * kGroupFloats * 4) + 127) & ~(size_t)127;

@@ -240,8 +240,8 @@ def dAllocate(inDataFrame, depModel, engine=None, columns=None):
         Xr = np.asarray(X)[:, cols]
     if red.ndim == 1:
         red = red[None, :]
-    lab = eng.allocate_points(Xr, red, 1)["i"].astype(np.int64)
-    lab += 1                                                                     # :127-134 (in place: the vector has one entry per cell)
+    lab = eng.allocate_points(Xr, red, 1)["i"]                                   # R's integers are 32-bit too: no widening copy of a vector
+    lab += 1                                                                     # :127-134 (in place)                  with one entry per cell
     return lab
 
 

@@ -256,7 +256,7 @@ def test_unsupported_shapes_and_bad_arguments_fail_loudly(engine):
     rng = np.random.default_rng(0)
     X = rng.normal(size=(200, 4))
     with pytest.raises(dp.DepecherError, match="not supported"):
-        engine.allocate_points(X, rng.normal(size=(241, 4)), False)          # more than 240 centres
+        engine.allocate_points(X, rng.normal(size=(481, 4)), False)          # more than 480 centres
     with pytest.raises(dp.DepecherError, match="not supported"):
         engine.allocate_points(rng.normal(size=(10, 1000)), rng.normal(size=(3, 1000)), False)   # a slot would not fit in shared memory
     with pytest.raises(dp.DepecherError):
@@ -269,6 +269,29 @@ def test_unsupported_shapes_and_bad_arguments_fail_loudly(engine):
     same = np.ones((100, 3))
     mu, rows = engine.initialize_mu(same, 4, seed=1)
     assert np.array_equal(mu, np.ones((4, 3))) and (rows[1:] == 0).all()
+
+
+def test_many_centres_k300(engine, oracle):
+    """depecheAllData fits K = 3k centres (R/depecheAllData.R:30-31): depeche(k = 100) on fewer than 10 000 rows needs K = 300 —
+    beyond the tensor-core pass (K <= 128), on the FFMA pass with 10 chunks of centres (VERDICT r1 missing-6)"""
+    rng = np.random.default_rng(300)
+    n, d, k = 4000, 12, 300
+    X = blobs(rng, n, d, 9, amp=2.5)
+    mu = X[rng.choice(n, k, replace=False)].copy()
+    mu[[7, 150, 299]] = 0.0
+    for nz in (False, True):
+        assert np.array_equal(engine.allocate_points(X, mu, nz)["i"], oracle.allocate_points(X, mu, nz))
+    reg = 2.0 * n * np.sqrt(d) / 1450.0
+    a = engine.find_centers_from(X, mu, reg, True)
+    b = oracle.find_centers_from(X, mu, reg, True)
+    assert a["n_iter"] == b["n_iter"] and np.array_equal(a["i"], b["i"])
+    centres_close(a["c"], b["c"])
+    oracle.set_rng(RNG_PHILOX, 5)
+    want = oracle.sparse_k_means(X, k, reg, True, fit_id=0)
+    got = engine.sparse_k_means(X, k, reg, True, seed_off_set=5)
+    assert got["n_iter"] == want["n_iter"] and np.array_equal(got["i"], want["i"])
+    assert abs(got["n"] - want["n"]) <= 1e-9 * abs(want["n"])
+    assert engine.rand_index(got["i"] + 1, want["i"] + 1, k) == 1.0
 
 
 def test_random_shapes_fuzz(engine, oracle):

@@ -320,14 +320,15 @@ static int run_seeding(const std::vector<SeedJob>& jobs, int d, int k, uint64_t 
         w_total += j.n;
         b_total += (j.n + kSeedBlock - 1) / kSeedBlock;
     }
-    DevBuf w, bs, fits;
+    DevBuf w, bs, fits, done;
     DPR_TRY(w.alloc(sizeof(double) * w_total));
     DPR_TRY(bs.alloc(sizeof(double) * b_total));
     DPR_TRY(fits.alloc(sizeof(SeedFit) * F));
+    DPR_TRY(done.alloc(sizeof(int) * F, true));
     std::vector<SeedFit> h(F);
     int64_t wo = 0, bo = 0;
     for (int f = 0; f < F; ++f) {
-        h[f] = SeedFit{jobs[f].x, jobs[f].n, jobs[f].fit_id, 0, jobs[f].mu, w.as<double>() + wo, bs.as<double>() + bo, jobs[f].rows};
+        h[f] = SeedFit{jobs[f].x, jobs[f].n, jobs[f].fit_id, 0, jobs[f].mu, w.as<double>() + wo, bs.as<double>() + bo, jobs[f].rows, done.as<int>() + f};
         wo += jobs[f].n;
         bo += (jobs[f].n + kSeedBlock - 1) / kSeedBlock;
     }

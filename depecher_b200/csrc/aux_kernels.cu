@@ -121,7 +121,11 @@ __global__ void seed_first_kernel(SeedFit* fits, int d, uint64_t seed) {
     if (threadIdx.x == 0 && f.rows) f.rows[0] = row;
 }
 
-__global__ void seed_dist_kernel(const SeedFit* fits, int d, int c /* centre just chosen: c-1 >= 0 */, int first) {
+__device__ void seed_pick_body(const SeedFit& f, int d, int c, uint64_t seed);
+// Round c: distances to centre c - 1 (the running minimum, block sums), then — by the CTA of the fit that finishes last (a ticket
+// counter per fit) — the draw of centre c.  One launch per round instead of two: the rounds of a batch of small fits are
+// launch-latency-bound (28 launches fewer per seeding).
+__global__ void seed_dist_kernel(const SeedFit* fits, int d, int c /* centre just chosen: c-1 >= 0 */, int first, uint64_t seed) {
     extern __shared__ double s_mu[];
     const SeedFit f = fits[blockIdx.y];
     const int nb = (int)((f.n + kSeedBlock - 1) / kSeedBlock);
@@ -155,14 +159,22 @@ __global__ void seed_dist_kernel(const SeedFit* fits, int d, int c /* centre jus
         }
         __syncthreads();
     }
+    __shared__ int s_last;
+    __threadfence();   // this CTA's weights and block sums are visible before its ticket is
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(f.done, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) *f.done = 0;   // (for the next round)
+    __threadfence();
+    seed_pick_body(f, d, c, seed);
 }
 
-__global__ void seed_pick_kernel(SeedFit* fits, int d, int c, uint64_t seed) {
-    // One CTA per fit.  The cumulative sum the reference keeps in a std::map is evaluated hierarchically:
-    // thread segments of block sums -> the segment holding x -> its blocks -> the cells of one block.  Every level
-    // is summed in ascending order, so the pick only differs from a purely sequential cumsum when x falls within
-    // rounding distance (~1e-16 relative) of a boundary.
-    SeedFit f = fits[blockIdx.x];
+// One CTA per fit.  The cumulative sum the reference keeps in a std::map is evaluated hierarchically:
+// thread segments of block sums -> the segment holding x -> its blocks -> the cells of one block.  Every level
+// is summed in ascending order, so the pick only differs from a purely sequential cumsum when x falls within
+// rounding distance (~1e-16 relative) of a boundary.
+__device__ void seed_pick_body(const SeedFit& f, int d, int c, uint64_t seed) {
     const int nb = (int)((f.n + kSeedBlock - 1) / kSeedBlock);
     const int T = blockDim.x;
     const int seg = (nb + T - 1) / T;
@@ -513,9 +525,8 @@ int launch_seeding(SeedFit* d_fits, int n_fits, int64_t n_max, int d, int k, uin
     const int nb = (int)((n_max + kSeedBlock - 1) / kSeedBlock);
     const int gx = std::max(1, std::min(nb, (148 * 8 + n_fits - 1) / n_fits));
     for (int c = 1; c < k; ++c) {
-        seed_dist_kernel<<<dim3(gx, n_fits), kSeedBlock, sizeof(double) * d, st>>>(d_fits, d, c, c == 1);
-        seed_pick_kernel<<<n_fits, 256, 0, st>>>(d_fits, d, c, seed);
-        count_launch(2);
+        seed_dist_kernel<<<dim3(gx, n_fits), kSeedBlock, sizeof(double) * d, st>>>(d_fits, d, c, c == 1, seed);
+        count_launch();
     }
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;

@@ -17,6 +17,7 @@ struct SeedFit {            // one k-means++ seeding problem (device-resident ar
     double* w;              // n running min squared distances
     double* block_sums;     // ceil(n / kSeedBlock)
     long long* rows;        // nullable: chosen row numbers (k)
+    int* done;              // ticket counter of the round's CTAs (zero between rounds)
 };
 
 struct AriPair {

@@ -269,18 +269,21 @@ class Engine:
         return self.dataset(X), True
 
     # -- the four entry points (names and results as the reference's Rcpp exports) ----------------------
-    def allocate_points(self, X, mu, no_zero) -> dict:
-        """allocate_points(X, mu, no_zero) -> {'i': labels}   (src/InterfaceUtils.cpp:134-148)"""
+    def allocate_points(self, X, mu, no_zero, base: int = 0) -> dict:
+        """allocate_points(X, mu, no_zero) -> {'i': labels}   (src/InterfaceUtils.cpp:134-148); `base` is added to every label"""
         mu = _f64(mu)
         k = mu.shape[0]
         if isinstance(X, Dataset):
             idx = np.empty(X.n, np.int32)
-            self._chk(self.lib.dpr_dataset_allocate_points(X.handle, _ptr(mu, _dp), C.c_int32(k), C.c_int32(int(no_zero)), _ptr(idx, _ip)))
+            self._chk(self.lib.dpr_dataset_allocate_points_base(X.handle, _ptr(mu, _dp), C.c_int32(k), C.c_int32(int(no_zero)), C.c_int32(base),
+                                                                _ptr(idx, _ip)))
         else:
             Xf = _f64(X)
             idx = np.empty(Xf.shape[0], np.int32)
             self._chk(self.lib.dpr_allocate_points(_ptr(Xf, _dp), C.c_int64(Xf.shape[0]), C.c_int32(Xf.shape[1]), _ptr(mu, _dp), C.c_int32(k),
                                                    C.c_int32(int(no_zero)), _ptr(idx, _ip)))
+            if base:
+                idx += base
         return {"i": idx}
 
     def sparse_k_means(self, X, k, reg, no_zero, seed_off_set=0, want_labels=True) -> dict:

@@ -235,14 +235,40 @@ static int dataset_upload(dpr_dataset* ds, const T* X) {
 }
 
 // one Session over `ds` with a single problem
+// The cell-major copy that the delta iterations of a Lloyd fit gather moved cells from (delta_sums_kernel): built once per
+// dataset, on its first fit, when the matrix is large enough for the gathers to miss the L2 (the tile-major layout spreads
+// a row over tile_groups(d) sectors) and the device has the memory to spare.  A plan decision, not a requirement: without
+// it the gathers read the tile-major matrix.
+static int dataset_rows(dpr_dataset* ds) {
+    static const bool off = getenv("DPR_NO_ROWS_COPY") != nullptr;   // A/B aid
+    if (ds->rows || ds->rows_tried || off) return DPR_OK;
+    ds->rows_tried = true;
+    const size_t bytes = sizeof(float) * (size_t)ds->n_pad * 4 * tile_groups(ds->d);
+    if (bytes < ((size_t)64 << 20)) return DPR_OK;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < bytes + ((size_t)4 << 30)) {
+        cudaGetLastError();
+        return DPR_OK;
+    }
+    if (dev_alloc((void**)&ds->rows, bytes) != DPR_OK) {
+        ds->rows = nullptr;
+        cudaGetLastError();
+        return DPR_OK;
+    }
+    return launch_rows_from_tiles(ds->x, ds->n_pad / kSlotCells, ds->d, ds->rows, ctx().stream);
+}
+
 static int single_session(dpr_dataset* ds, int k, double reg, int no_zero, bool want_sums, Session& s) {
     DPR_TRY(dataset_labels(ds));
+    if (want_sums) DPR_TRY(dataset_rows(ds));
     std::vector<ProblemSpec> specs(1);
-    specs[0] = ProblemSpec{ds->x, ds->tile_xx, ds->tile_xx + ds->n_pad / kSlotCells, ds->n, k, reg, no_zero, ds->labels};
+    specs[0] = ProblemSpec{ds->x, ds->tile_xx, ds->tile_xx + ds->n_pad / kSlotCells, ds->n, k, reg, no_zero, ds->labels, ds->rows};
     return s.init(specs, ds->d, want_sums);
 }
 
-static int copy_labels_out(const int32_t* d_labels, int64_t n, int32_t* host) {
+// `base` is added to every label on the way out (R's clusters are 1-based: dAllocate.R:127-134 — adding it here saves the caller a
+// pass over a vector with one entry per cell)
+static int copy_labels_out(const int32_t* d_labels, int64_t n, int32_t* host, int32_t base = 0) {
     if (!host) return DPR_OK;
     if (n >= (1 << 19) && g_stage.cap > 0) {
         // the caller's vector is pageable: the driver would stage it at a few GB/s.  DMA into the pinned upload buffers instead
@@ -264,7 +290,9 @@ static int copy_labels_out(const int32_t* d_labels, int64_t n, int32_t* host) {
                 std::vector<std::thread> pool;
                 auto work = [=](int t) {
                     const int64_t a = prev_cnt * t / threads, z = prev_cnt * (t + 1) / threads;
-                    std::memcpy(host + prev0 + a, src + a, sizeof(int32_t) * (size_t)(z - a));
+                    if (base == 0) std::memcpy(host + prev0 + a, src + a, sizeof(int32_t) * (size_t)(z - a));
+                    else
+                        for (int64_t e = a; e < z; ++e) host[prev0 + e] = src[e] + base;
                 };
                 for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
                 work(0);
@@ -277,6 +305,8 @@ static int copy_labels_out(const int32_t* d_labels, int64_t n, int32_t* host) {
     }
     DPR_CUDA(cudaMemcpyAsync(host, d_labels, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx().stream));
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (base != 0)
+        for (int64_t e = 0; e < n; ++e) host[e] += base;
     return DPR_OK;
 }
 
@@ -772,6 +802,7 @@ int dpr_dataset_destroy(dpr_dataset_t ds) {
     dev_free(ds->x);
     dev_free(ds->tile_xx);
     dev_free(ds->labels);
+    dev_free(ds->rows);
     delete ds;
     return DPR_OK;
 }
@@ -810,6 +841,9 @@ int dpr_dataset_gather(dpr_dataset_t ds, const int64_t* rows, int64_t m, dpr_dat
 
 // ---- allocate_points -------------------------------------------------------------------------------
 int dpr_dataset_allocate_points(dpr_dataset_t ds, const double* mu, int32_t k, int32_t no_zero, int32_t* idx_out) {
+    return dpr_dataset_allocate_points_base(ds, mu, k, no_zero, 0, idx_out);
+}
+int dpr_dataset_allocate_points_base(dpr_dataset_t ds, const double* mu, int32_t k, int32_t no_zero, int32_t base, int32_t* idx_out) {
     if (!ds || !mu || k < 1) return fail(DPR_ERR_INVALID, "allocate_points: null argument or k < 1");
     Session s;
     DPR_TRY(single_session(ds, k, 0.0, no_zero, false, s));
@@ -818,7 +852,7 @@ int dpr_dataset_allocate_points(dpr_dataset_t ds, const double* mu, int32_t k, i
     DPR_TRY(s.set_centres(0, rm.data()));
     DPR_TRY(s.prepare());
     DPR_TRY(s.pass(kPassAssign, false));
-    return copy_labels_out(ds->labels, ds->n, idx_out);
+    return copy_labels_out(ds->labels, ds->n, idx_out, base);
 }
 int dpr_allocate_points(const double* X, int64_t n, int32_t d, const double* mu, int32_t k, int32_t no_zero, int32_t* idx_out) {
     if (!idx_out) return fail(DPR_ERR_INVALID, "null output");

@@ -500,6 +500,41 @@ int launch_max_finite(const float* v, int64_t n, float* out, cudaStream_t st) {
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
 }
+// One CTA per tile: the tile's float4s (a cell's 4 markers of one group) in through shared memory, out with consecutive
+// threads writing consecutive float4s of the rows (both sides coalesced).
+__global__ void __launch_bounds__(256) rows_from_tiles_kernel(const float* __restrict__ x, int64_t n_tiles, int d, float* __restrict__ rows) {
+    extern __shared__ float4 s_tile[];   // [groups][128]
+    const int groups = tile_groups(d);
+    const size_t tile_fl = tile_floats(d);
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const float* src = x + (size_t)t * tile_fl;
+        for (int i = threadIdx.x; i < groups * kSlotCells; i += blockDim.x) {
+            const int g = i >> 7, c = i & 127;
+            s_tile[i] = *reinterpret_cast<const float4*>(src + (size_t)g * kGroupFloats + 4 * c);
+        }
+        __syncthreads();
+        float4* dst = reinterpret_cast<float4*>(rows) + (size_t)t * kSlotCells * groups;
+        for (int i = threadIdx.x; i < groups * kSlotCells; i += blockDim.x) {
+            const int c = i / groups, g = i - c * groups;
+            dst[i] = s_tile[g * kSlotCells + c];
+        }
+        __syncthreads();
+    }
+}
+int launch_rows_from_tiles(const float* x, int64_t n_tiles, int d, float* rows, cudaStream_t st) {
+    const size_t shm = (size_t)tile_groups(d) * kSlotCells * sizeof(float4);
+    if (shm > 200 * 1024) return fail(DPR_ERR_INVALID, "rows_from_tiles: tile too large for shared memory");
+    static size_t configured = 48 * 1024;
+    if (shm > configured) {
+        DPR_CUDA(cudaFuncSetAttribute(rows_from_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    const int grid = (int)std::min<int64_t>(n_tiles, 148 * 8);
+    rows_from_tiles_kernel<<<grid, 256, shm, st>>>(x, n_tiles, d, rows);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
 int launch_tile_norms(const float* x, int64_t n_tiles, int d, float* out, cudaStream_t st) {
     tile_norms_kernel<<<blocks_for(n_tiles * 32), 256, 0, st>>>(x, n_tiles, d, out);
     count_launch();

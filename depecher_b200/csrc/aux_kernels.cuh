@@ -32,6 +32,8 @@ int launch_f64_to_cols(const double* src, int64_t e0, int64_t count, int64_t n, 
 int launch_f32_to_cols(const float* src, int64_t e0, int64_t count, int64_t n, int d, float* dst, cudaStream_t st);
 int launch_cols_to_f64(const float* x, int64_t row0, int64_t rows, int d, double* out, cudaStream_t st);
 int launch_max_finite(const float* v, int64_t n, float* out, cudaStream_t st);
+// cell-major copy of a tile-major matrix (row c at c * 4 * tile_groups(d) floats)
+int launch_rows_from_tiles(const float* x, int64_t n_tiles, int d, float* rows, cudaStream_t st);
 int launch_tile_norms(const float* x, int64_t n_tiles, int d, float* out, cudaStream_t st);
 int launch_gather(const float* x, int64_t n, int d, const int64_t* rows, uint64_t seed, uint32_t fit0, int64_t m, float* out, int n_fits,
                   int64_t fit_stride, cudaStream_t st);

@@ -76,6 +76,7 @@ struct Problem {
     const float* x;       // resident fp32 cells, tile-major (see x_index)
     const float* tile_xx; // per tile: an upper bound of ||x||^2 over its cells (enters the near-tie threshold)
     const float* xx_max;  // one float: the largest finite tile bound of the matrix the cells come from (fp16 scaling of the tensor-core pass)
+    const float* xrows;   // nullable: the same cells cell-major (row c at c * 4 * tile_groups(d) floats) — what delta_sums_kernel gathers moved cells from
     int64_t n;            // cells
     int32_t d;
     int32_t k;
@@ -138,4 +139,7 @@ struct dpr_dataset {
     float* x = nullptr;        // device, tile-major (dpr::x_index), (n_pad / 128) * tile_floats(d) floats
     float* tile_xx = nullptr;  // device, n_pad / 128 + 1 floats: max ||x||^2 of each tile (rounded up), then the largest finite one
     int32_t* labels = nullptr; // device, n_pad entries (lazily allocated)
+    float* rows = nullptr;     // device, n_pad x 4 * tile_groups(d) floats: a cell-major copy for row gathers, built on the first Lloyd fit of a
+                               //   large matrix (a moved cell's row is one contiguous 16 * tile_groups(d) bytes there, tile_groups(d) scattered sectors in x)
+    bool rows_tried = false;
 };

@@ -77,6 +77,8 @@ struct ScorePlan {
     int32_t acols;           // TMEM columns of one fp16 A operand
     int32_t wait_hint;
     int32_t kk;              // width of the fused contingency tables (k_max + 1); 0: not fused
+    uint32_t key_mul;        // 16, as a run-time value: ptxas turns a multiplication by a constant 16 into LEA (the half-rate ALU pipe, which
+                             //   the reduction saturates first); a register factor stays an IMAD on the FMA pipe
     int32_t stages, stage_floats;
     int32_t off_sets, off_cc, off_orig, off_bh, off_bl, off_pairs, off_stages;
     size_t smem_bytes;

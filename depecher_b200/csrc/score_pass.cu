@@ -55,6 +55,18 @@ struct ScoreSet {          // one centre set of the current bundle (shared memor
 
 static_assert(sizeof(ScoreSet) == 48, "the reducer reads a set's first 16 bytes as one float4");
 
+// A set of at most two 16-column blocks as the reducer's short path reads it (two 16-byte loads).  A set with one block gets a second
+// one made of padding: the same accumulator columns with factor 0 and the ||c||^2 of padding columns, so both blocks of every set go
+// through the same straight-line code.
+struct FastSet {
+    uint32_t cols;         // column of block A | column of block B << 8 | set number << 16 | first ||c||^2 entry of block B << 24
+    float unscale_a, unscale_b;
+    uint32_t col0_nact;    // the set's first column | active centres << 8
+    float tk_a, tk_b, tk_c;   // near-tie bound in key units (ScoreSet)
+    uint32_t pad_;
+};
+static_assert(sizeof(FastSet) == 32, "two float4 loads");
+
 // the two smallest of a sorted pair (a0 <= a1) and a sorted pair (b0 <= b1), sorted
 __device__ __forceinline__ void merge2(float a0, float a1, float b0, float b1, float& lo, float& hi) {
     lo = fminf(a0, b0);
@@ -105,6 +117,8 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
     int32_t* n_total_s = reinterpret_cast<int32_t*>(tmem_word + 1);   // accumulator columns the current bundle uses
     int32_t* n_chunks_s = n_total_s + 1;                               // blocks of 16 columns that hold scores (trivial sets have none)
     uint2* chunk_s = reinterpret_cast<uint2*>(n_chunks_s + 2);   // (8-byte aligned)   // [<= 8] .x: column | set << 8 | first of its set << 12 | last << 13; .y: its set's un-scaling factor
+    int32_t* n_fast_s = n_chunks_s + 1;                          // >= 0: every non-trivial set of the bundle has at most two blocks — that many FastSets; -1: the general walk
+    FastSet* fast_s = reinterpret_cast<FastSet*>(smem + 384);    // [kScMaxSets] (the chunk list ends at 328)
     ScoreSet* sets = reinterpret_cast<ScoreSet*>(smem + T.off_sets);
     float* cc_s = reinterpret_cast<float*>(smem + T.off_cc);          // [b_rows] ||c||^2 per accumulator column (padding: +huge)
     int32_t* orig_s = reinterpret_cast<int32_t*>(smem + T.off_orig);  // [b_rows] column -> row of its set's mu (padding: -1)
@@ -364,16 +378,37 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
                     sets[q] = st;
                 }
             }
+            if (tid < 16) cc_s[T.b_rows + tid] = big_m + 1048576.f * qq;   // a block of padding columns (second block of a one-block set)
             if (tid == 0) {
                 *n_total_s = col0[NS];
-                int nch = 0;
+                int nch = 0, nf = 0;
+                bool fast_ok = true;
                 for (int q = 0; q < NS; ++q) {
-                    if (P.problems[p + q].hdr->trivial) continue;
+                    const CentreHeader* h = P.problems[p + q].hdr;
+                    if (h->trivial) continue;
                     for (int c = col0[q]; c < col0[q + 1]; c += 16)
                         chunk_s[nch++] = make_uint2((uint32_t)c | ((uint32_t)q << 8) | (c == col0[q] ? 1u << 12 : 0u) | (c + 16 == col0[q + 1] ? 1u << 13 : 0u),
-                                                    __float_as_uint(P.problems[p + q].hdr->tc_unscale));
+                                                    __float_as_uint(h->tc_unscale));
+                    const int nq = col0[q + 1] - col0[q];
+                    if (nq > 32) {
+                        fast_ok = false;
+                        continue;
+                    }
+                    const bool two = nq == 32;
+                    const float cc2 = 2.0f * h->cc_max, iq16 = 16.f / qq;
+                    FastSet f;
+                    f.cols = (uint32_t)col0[q] | ((uint32_t)(two ? col0[q] + 16 : col0[q]) << 8) | ((uint32_t)q << 16) | ((uint32_t)(two ? col0[q] + 16 : T.b_rows) << 24);
+                    f.unscale_a = h->tc_unscale;
+                    f.unscale_b = two ? h->tc_unscale : 0.f;
+                    f.col0_nact = (uint32_t)col0[q] | ((uint32_t)h->k_act << 8);
+                    f.tk_a = (tau_a + tau_b) * iq16;      // (as in ScoreSet below)
+                    f.tk_b = h->tc_abs1 * iq16;
+                    f.tk_c = (h->force_exact || !q_ok) ? INFINITY : (tau_a * 0.5f * cc2 + tau_b * cc2 + h->tc_abs2 + 3.f * qq) * iq16;
+                    f.pad_ = 0u;
+                    fast_s[nf++] = f;
                 }
                 *n_chunks_s = nch;
+                *n_fast_s = fast_ok ? nf : -1;
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the B operands were written through the generic proxy
@@ -450,17 +485,17 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
                     // smallest key and (key - b - 1) for every other one: second = b + 1 + unsigned-min of those (add + min fuse into one
                     // instruction, VIADDMNMX).  No branch inside: two blocks are reduced side by side (independent instruction streams for
                     // the scheduler — with three reducing warps per sub-partition the pass is bound by dependent-issue latency, not by a pipe).
-                    auto top2 = [&](const uint32_t (&v)[16], const uint2 ci, int& b, int& sec) {
-                        const float unscale = __uint_as_float(ci.y);
-                        const float4* cc4 = reinterpret_cast<const float4*>(cc_s + (ci.x & 255u));
+                    auto top2 = [&](const uint32_t (&v)[16], const uint32_t cc_col, const float unscale, int& b, int& sec) {
+                        const uint32_t m16 = T.key_mul;
+                        const float4* cc4 = reinterpret_cast<const float4*>(cc_s + cc_col);
                         int w[16];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float4 cq = cc4[j];
-                            w[4 * j + 0] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 0]), cq.x)) * 16u + (unsigned)(4 * j + 0));
-                            w[4 * j + 1] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 1]), cq.y)) * 16u + (unsigned)(4 * j + 1));
-                            w[4 * j + 2] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 2]), cq.z)) * 16u + (unsigned)(4 * j + 2));
-                            w[4 * j + 3] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 3]), cq.w)) * 16u + (unsigned)(4 * j + 3));
+                            w[4 * j + 0] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 0]), cq.x)) * m16 + (unsigned)(4 * j + 0));
+                            w[4 * j + 1] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 1]), cq.y)) * m16 + (unsigned)(4 * j + 1));
+                            w[4 * j + 2] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 2]), cq.z)) * m16 + (unsigned)(4 * j + 2));
+                            w[4 * j + 3] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 3]), cq.w)) * m16 + (unsigned)(4 * j + 3));
                         }
                         b = min(__vimin3_s32(__vimin3_s32(w[0], w[1], w[2]), __vimin3_s32(w[3], w[4], w[5]), __vimin3_s32(w[6], w[7], w[8])),
                                 __vimin3_s32(__vimin3_s32(w[9], w[10], w[11]), __vimin3_s32(w[12], w[13], w[14]), w[15]));
@@ -493,20 +528,48 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
                     // blocks two at a time: both loads in flight, one wait, both tournaments in one straight-line stretch (three or four at
                     // a time need more than the 112 registers of a reducing warp: measured 0.158-0.162 ms per set with their spills, 0.154 with two)
                     uint32_t va[16], vb[16];
-                    for (int c = 0; c < nch; c += 2) {
-                        const uint2 ca = chunk_s[c], cb = chunk_s[c + 1 < nch ? c + 1 : c];
-                        tmem_ld16_raw(acc_base + (ca.x & 255u), va);
-                        tmem_ld16_raw(acc_base + (cb.x & 255u), vb);
-                        tmem_wait_ld16(va);
-                        tmem_wait_ld16(vb);
-                        if (c + 2 >= nch) release_acc();
-                        int ba, sa, bb, sb;
-                        top2(va, ca, ba, sa);
-                        top2(vb, cb, bb, sb);
-                        fold(ca, ba, sa);
-                        if (c + 1 < nch) fold(cb, bb, sb);
+                    const int nf = *n_fast_s;
+                    if (nf >= 0) {
+                        // the short path (every set of the bundle has at most 32 columns: the penalty search's K = 30): one set per round, its
+                        // two blocks reduced side by side and merged directly — no per-block bookkeeping
+                        for (int f = 0; f < nf; ++f) {
+                            const uint4 f0 = *reinterpret_cast<const uint4*>(fast_s + f);
+                            const float4 f1 = *(reinterpret_cast<const float4*>(fast_s + f) + 1);
+                            const uint32_t col_a = f0.x & 255u, col_b = (f0.x >> 8) & 255u;
+                            tmem_ld16_raw(acc_base + col_a, va);
+                            tmem_ld16_raw(acc_base + col_b, vb);
+                            tmem_wait_ld16(va);
+                            tmem_wait_ld16(vb);
+                            if (f + 1 == nf) release_acc();
+                            int ba, sa, bb, sb;
+                            top2(va, col_a, __uint_as_float(f0.y), ba, sa);
+                            top2(vb, f0.x >> 24, __uint_as_float(f0.z), bb, sb);
+                            const int bst = min(ba, bb);                       // (an equal key of block B never displaces block A's: strict below)
+                            const int sec = __vimin3_s32(max(ba, bb), sa, sb);
+                            const int col0_q = (int)(f0.w & 255u), n_act_q = (int)(f0.w >> 8);
+                            const int a = (int)(bb < ba ? col_b : col_a) - col0_q + (bst & 15);
+                            const uint32_t sh = (f0.x >> 13) & 0x18u;          // 8 * set number
+                            labs |= (uint32_t)orig_s[col0_q + (a < n_act_q ? a : 0)] << sh;
+                            const float tk = fmaf(f1.x, xx_tile, fmaf(f1.y, sq_xx, f1.z));
+                            if (!((float)(sec - bst) > tk)) doubt |= 1u << (sh >> 3);
+                        }
+                        if (nf == 0) release_acc();
+                    } else {
+                        for (int c = 0; c < nch; c += 2) {
+                            const uint2 ca = chunk_s[c], cb = chunk_s[c + 1 < nch ? c + 1 : c];
+                            tmem_ld16_raw(acc_base + (ca.x & 255u), va);
+                            tmem_ld16_raw(acc_base + (cb.x & 255u), vb);
+                            tmem_wait_ld16(va);
+                            tmem_wait_ld16(vb);
+                            if (c + 2 >= nch) release_acc();
+                            int ba, sa, bb, sb;
+                            top2(va, ca.x & 255u, __uint_as_float(ca.y), ba, sa);
+                            top2(vb, cb.x & 255u, __uint_as_float(cb.y), bb, sb);
+                            fold(ca, ba, sa);
+                            if (c + 1 < nch) fold(cb, bb, sb);
+                        }
+                        if (nch == 0) release_acc();
                     }
-                    if (nch == 0) release_acc();
                     SC_PROF(2);
                     // near ties: the whole warp re-decides the cell in fp64 with the reference's arithmetic (exact_label_warp)
                     if (__any_sync(0xffffffffu, doubt != 0 && live)) {
@@ -594,9 +657,9 @@ int plan_score_pass(int d, int k_max, int sets_wanted, int fuse_kk, ScorePlan* p
     const int b_rows = sets * ncol;
     const int acols = 8 * k16;
     const size_t stage_bytes = (((size_t)(tile_groups(d) + (tile_groups(d) & 1)) * kGroupFloats * 4) + 127) & ~(size_t)127;
-    const size_t bars = 512;
+    const size_t bars = 640;   // mbarriers, counters, the chunk list and the FastSets
     const size_t sets_bytes = 512;   // kScMaxSets x ScoreSet (56 B)
-    const size_t cc_bytes = ((size_t)b_rows * 4 + 127) & ~(size_t)127;
+    const size_t cc_bytes = ((size_t)(b_rows + 16) * 4 + 127) & ~(size_t)127;   // + one block of padding columns
     const size_t b_bytes = (size_t)2 * k16 * b_rows * 16;
     size_t pair_bytes = 0;
     int kk = 0;
@@ -615,6 +678,7 @@ int plan_score_pass(int d, int k_max, int sets_wanted, int fuse_kk, ScorePlan* p
     plan->b_rows = b_rows;
     plan->acols = acols;
     plan->wait_hint = 2000;
+    plan->key_mul = 16u;
     plan->kk = kk;
     plan->stages = S;
     plan->stage_floats = (int)(stage_bytes / 4);

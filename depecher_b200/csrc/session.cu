@@ -77,6 +77,7 @@ int Session::init(const std::vector<ProblemSpec>& specs, int d, bool want_sums, 
         pr.x = s.x;
         pr.tile_xx = s.tile_xx;
         pr.xx_max = s.xx_max;
+        pr.xrows = s.rows;
         pr.n = s.n;
         pr.d = d;
         pr.k = s.k;
@@ -249,11 +250,16 @@ int Session::zero_labels() {
 int Session::lloyd(int max_iter) {
     // The convergence rule needs i > 20 (Clusterer.cpp:247): iterations 0..20 run back to back without
     // touching the host; after that the host looks at the active-problem counter once per iteration.
+    // Batches of small fits (the bootstrap fits of a penalty search) are launch-latency-bound: an iteration is a few tens of
+    // microseconds, a host round trip costs as much, and a converged problem is skipped by every kernel — they look only every
+    // fourth iteration (at most three near-empty iterations at the end).  Large problems look every iteration: one more pass
+    // over 10M cells costs 20 round trips.
+    const int look_every = total_tiles_ >= 20000 ? 1 : 4;
     int last_active = n_problems();
     for (int i = 0; i < max_iter; ++i) {
         DPR_TRY(pass(kPassLloyd, true));
         DPR_TRY(reduce_and_finalize(i, max_iter));
-        if (i > 20) {
+        if (i > 20 && ((i - 21) % look_every == look_every - 1 || i + 1 == max_iter)) {
             DPR_CUDA(cudaMemcpyAsync(h_n_active_, d_n_active_ + last_active_slot_, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx().stream));
             DPR_CUDA(cudaStreamSynchronize(ctx().stream));
             if (*h_n_active_ == 0) break;

@@ -22,6 +22,7 @@ struct ProblemSpec {
     double reg;
     int32_t no_zero;
     int32_t* labels;   // device, >= n ints (nullable: session allocates when want_labels)
+    const float* rows = nullptr;   // nullable: cell-major copy of x (dpr_dataset::rows)
 };
 
 class Session {

@@ -657,6 +657,8 @@ __global__ void __launch_bounds__(512, 1) delta_sums_kernel(const PassParams P, 
                 double* tab = tabs + (size_t)warp * table_doubles;
                 long long* cnt = reinterpret_cast<long long*>(tab + stride);
                 const float* __restrict__ x = pr->x;
+                const float* __restrict__ xr = pr->xrows;   // cell-major copy (large matrices): a row is contiguous
+                const int d4 = 4 * tile_groups(d);
                 for (int l = warp; l < W; l += A) {
                     const int n_e = P.move_counts[(size_t)(blockIdx.x + p) * W + l];
                     const uint32_t pos_l = cursor[l];   // position of this range's first entry in list l
@@ -671,12 +673,13 @@ __global__ void __launch_bounds__(512, 1) delta_sums_kernel(const PassParams P, 
                             const int j0 = jb + lane, j1 = j0 + 32;
                             const bool on0 = j0 < d, on1 = j1 < d;
                             const int c0 = on0 ? j0 : 0, c1 = on1 ? j1 : 0;   // clamped: the gathers are unconditional (entries past the batch read cell 0)
-                            const size_t jo0 = (size_t)(c0 >> 2) * kGroupFloats + (c0 & 3), jo1 = (size_t)(c1 >> 2) * kGroupFloats + (c1 & 3);
+                            const size_t jo0 = xr ? (size_t)c0 : (size_t)(c0 >> 2) * kGroupFloats + (c0 & 3);
+                            const size_t jo1 = xr ? (size_t)c1 : (size_t)(c1 >> 2) * kGroupFloats + (c1 & 3);
                             float v0[kDeltaBatch], v1[kDeltaBatch];
 #pragma unroll
                             for (int q = 0; q < kDeltaBatch; ++q) {   // all gathers of the batch in flight
                                 const uint32_t cell = __shfl_sync(0xffffffffu, ent.x, q);
-                                const float* row = x + (size_t)(cell >> 7) * tile_fl + (size_t)(cell & 127u) * 4;
+                                const float* row = xr ? xr + (size_t)cell * d4 : x + (size_t)(cell >> 7) * tile_fl + (size_t)(cell & 127u) * 4;
                                 v0[q] = __ldg(row + jo0);
                                 v1[q] = __ldg(row + jo1);
                             }

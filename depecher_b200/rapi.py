@@ -240,6 +240,8 @@ def dAllocate(inDataFrame, depModel, engine=None, columns=None):
         Xr = np.asarray(X)[:, cols]
     if red.ndim == 1:
         red = red[None, :]
+    if hasattr(eng, "lib"):                                                      # the CUDA engine adds the 1 (:127-134) while it copies the labels out
+        return eng.allocate_points(Xr, red, 1, base=1)["i"]
     lab = eng.allocate_points(Xr, red, 1)["i"]                                   # R's integers are 32-bit too: no widening copy of a vector
     lab += 1                                                                     # :127-134 (in place)                  with one entry per cell
     return lab

@@ -120,6 +120,10 @@ int dpr_dataset_read(dpr_dataset_t ds, int64_t row0, int64_t rows, double* out);
 
 int dpr_dataset_allocate_points(dpr_dataset_t ds, const double* mu, int32_t k, int32_t no_zero,
                                 int32_t* idx_out /* host, nullable */);
+/* the same with `base` added to every label on the way out: base = 1 gives R's 1-based cluster numbers
+ * (R/dAllocate.R:127-134) without another pass over a vector with one entry per cell */
+int dpr_dataset_allocate_points_base(dpr_dataset_t ds, const double* mu, int32_t k, int32_t no_zero, int32_t base,
+                                     int32_t* idx_out /* host, nullable */);
 int dpr_dataset_sparse_k_means(dpr_dataset_t ds, uint32_t k, double reg, int32_t no_zero, uint64_t seed,
                                int32_t* idx_out /* nullable */, double* centers_out, double* norm_out,
                                int32_t* n_iter_out);

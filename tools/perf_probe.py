@@ -18,7 +18,8 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--modes", default="assign,lloyd")
     args = ap.parse_args()
-    eng = dp.Engine(device=0)
+    from depecher_b200 import _capi
+    eng = dp.Engine(device=0, path=os.environ.get("DPR_LIB", _capi.LIB_PATH))   # DPR_LIB=<path>: another build of the library (A/B on one box)
     for shp in args.shapes.split(","):
         d, k = (int(v) for v in shp.split("x"))
         ds = eng.synthetic(args.n, d, 24, 2.5, 7)

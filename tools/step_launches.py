@@ -8,7 +8,8 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import depecher_b200 as dp  # noqa: E402
 
-eng = dp.Engine(device=0)
+from depecher_b200 import _capi  # noqa: E402
+eng = dp.Engine(device=0, path=os.environ.get("DPR_LIB", _capi.LIB_PATH))
 n, d, k = 10_000_000, 40, 30
 ds = eng.synthetic(n, d, 24, 2.5, 20261021)
 reg = 1.0 * n * np.sqrt(d) / 1450.0

@@ -47,6 +47,7 @@ struct PassPlan {
 struct TcPlan {
     int32_t d, g8;          // markers; groups of 8 markers rounded up to whole K=16 steps
     int32_t wait_hint;      // suspend-time hint (ns) of the mbarrier waits
+    uint32_t key_mul;       // 16 as a run-time value (top2_block16)
     int32_t groups;         // consumer groups per CTA (2..4: as many as tensor memory holds)
     int32_t npad;           // columns reserved per centre set (k_max rounded up to 32)
     int32_t tmem_cols;      // allocation: groups x (accumulator 2*npad + xh 4*g8 + xl 4*g8 columns), power of two

@@ -73,21 +73,6 @@ __device__ __forceinline__ void merge2(float a0, float a1, float b0, float b1, f
     hi = fmin3(fmaxf(a0, b0), a1, b1);
 }
 
-// 16 accumulator columns of this warp's 32 lanes; the registers are valid after tmem_wait_ld16 (which names them, so that no use
-// can be scheduled above the wait)
-__device__ __forceinline__ void tmem_ld16_raw(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&v)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]),
-                   "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
-}
-
 #ifdef DPR_SC_PROFILE
 #define SC_PROF_DECL long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pa_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pn_ = 0
 #define SC_PROF(i) do { pt_[i] = clock64(); if (i > 0) pa_[i] += pt_[i] - pt_[i - 1]; } while (0)
@@ -327,20 +312,10 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
                 col0[q + 1] = col0[q] + (q < NS ? P.problems[p + q].hdr->tc_n : 0);
                 if (q < NS) ccm = fmaxf(ccm, P.problems[p + q].hdr->cc_max);
             }
-            // Sortable integer keys with the column number inside, built on the FMA pipe (min / max share the half-rate ALU pipe with
-            // all logic; the less of it the reduction needs, the better).  With q a power of two >= 2^-19 x (largest |score| of the
-            // matrix under any set of the bundle) and M = 1.5 * 2^23 * q,
-            //     w   = fma(unscale, D, cc + M)          the score rounded to a multiple of q, plus M: every w lies in the binade of M,
-            //                                            so its bit pattern is  const + score / q  (one rounding)
-            //     key = bits(w) * 16 + i                 i = the column's number in its block of 16 (IMAD); int32 arithmetic wraps, but
-            //                                            all keys of a cell lie within 2^25 of one another
-            // Signed integer min / max on the keys order the scores to within q and carry the winner's column; a difference of two keys
-            // times q / 16 is the difference of the scores up to 3 q (cc + M rounds cc: q / 2; the fma: q / 2; twice; the column numbers: < q).
-            const float smax = *pr.xx_max + 2.0f * ccm;
-            int e2 = 0;
-            frexpf(smax, &e2);                                   // smax < 2^e2
-            const bool q_ok = smax > 0.f && smax < 1e30f && e2 > -90;
-            const float qq = q_ok ? ldexpf(1.f, e2 - 19) : 1.f;
+            // sortable integer keys with the column number inside (tc_device.cuh: key_quantum, top2_block16); one scale for the bundle
+            const float qk = key_quantum(*pr.xx_max + 2.0f * ccm);   // (tc_device.cuh)
+            const bool q_ok = qk > 0.f;
+            const float qq = q_ok ? qk : 1.f;
             const float big_m = q_ok ? 12582912.f * qq : 0.f;     // 1.5 * 2^23 * q
 #pragma unroll
             for (int q = 0; q < kScMaxSets; ++q) {
@@ -355,8 +330,8 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
                     bl[(size_t)g * T.b_rows + col0[q] + r] = bsrc[(size_t)g * 2 * npad + npad + r];
                 }
                 for (int i = tid; i < nq; i += kScConsumerWarps * 32) {
-                    // (padding columns: M + 2^20 q, above every real score and still inside the binade of M)
-                    cc_s[col0[q] + i] = i < pq->hdr->k_act ? tab[i] + big_m : big_m + 1048576.f * qq;
+                    // (padding columns: above every real score and still inside the binade of M)
+                    cc_s[col0[q] + i] = i < pq->hdr->k_act ? tab[i] + big_m : big_m + kKeyPad * qq;
                     orig_s[col0[q] + i] = pq->tc_orig[i];
                 }
                 if (tid == 32 * q) {
@@ -378,7 +353,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
                     sets[q] = st;
                 }
             }
-            if (tid < 16) cc_s[T.b_rows + tid] = big_m + 1048576.f * qq;   // a block of padding columns (second block of a one-block set)
+            if (tid < 16) cc_s[T.b_rows + tid] = big_m + kKeyPad * qq;   // a block of padding columns (second block of a one-block set)
             if (tid == 0) {
                 *n_total_s = col0[NS];
                 int nch = 0, nf = 0;
@@ -486,26 +461,7 @@ __global__ void __launch_bounds__(kScThreads, 1) score_pass_kernel(const PassPar
                     // instruction, VIADDMNMX).  No branch inside: two blocks are reduced side by side (independent instruction streams for
                     // the scheduler — with three reducing warps per sub-partition the pass is bound by dependent-issue latency, not by a pipe).
                     auto top2 = [&](const uint32_t (&v)[16], const uint32_t cc_col, const float unscale, int& b, int& sec) {
-                        const uint32_t m16 = T.key_mul;
-                        const float4* cc4 = reinterpret_cast<const float4*>(cc_s + cc_col);
-                        int w[16];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 cq = cc4[j];
-                            w[4 * j + 0] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 0]), cq.x)) * m16 + (unsigned)(4 * j + 0));
-                            w[4 * j + 1] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 1]), cq.y)) * m16 + (unsigned)(4 * j + 1));
-                            w[4 * j + 2] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 2]), cq.z)) * m16 + (unsigned)(4 * j + 2));
-                            w[4 * j + 3] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 3]), cq.w)) * m16 + (unsigned)(4 * j + 3));
-                        }
-                        b = min(__vimin3_s32(__vimin3_s32(w[0], w[1], w[2]), __vimin3_s32(w[3], w[4], w[5]), __vimin3_s32(w[6], w[7], w[8])),
-                                __vimin3_s32(__vimin3_s32(w[9], w[10], w[11]), __vimin3_s32(w[12], w[13], w[14]), w[15]));
-                        const int nb1 = -(b + 1);
-                        unsigned u[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) u[j] = (unsigned)(w[j] + nb1);
-                        const unsigned um = min(__vimin3_u32(__vimin3_u32(u[0], u[1], u[2]), __vimin3_u32(u[3], u[4], u[5]), __vimin3_u32(u[6], u[7], u[8])),
-                                                __vimin3_u32(__vimin3_u32(u[9], u[10], u[11]), __vimin3_u32(u[12], u[13], u[14]), u[15]));
-                        sec = (int)((unsigned)(b + 1) + um);
+                        top2_block16(v, reinterpret_cast<const float4*>(cc_s + cc_col), unscale, T.key_mul, b, sec);
                     };
                     // a block's result into the running (best, second) of its set; at the set's last block: the label, and whether the two
                     // best scores are safely apart

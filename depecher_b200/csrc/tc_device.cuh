@@ -69,6 +69,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32], int
         : "r"(taddr)
         : "memory");
 }
+// 16 accumulator columns of this warp's 32 lanes; the registers are valid after tmem_wait_ld16 (which names them, so that no use
+// can be scheduled above the wait)
+__device__ __forceinline__ void tmem_ld16_raw(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]),
+                   "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
+}
+
 // one lane of a converged warp (the operands of the single-thread tcgen05 / bulk-copy instructions then stay
 // warp-uniform for the compiler: no per-lane waterfall loop around them)
 __device__ __forceinline__ bool elect_one() {
@@ -87,6 +102,49 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uin
     const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Sortable integer keys (tc_pass.cu, score_pass.cu).  With q a power of two in (2^-21, 2^-20] x (the largest |score| under the
+// centre set) and M = 1.5 * 2^23 * q,
+//     w   = fma(unscale, D, cc + M)     the score rounded to a multiple of q, plus M: every w lies in the binade of M, so its bit
+//                                       pattern is  const + score / q  (one rounding)
+//     key = bits(w) * 16 + i            i = the column's number in its block of 16; int32 arithmetic wraps, but the keys of one
+//                                       binade fill one 2^27-aligned block of the integers: they never straddle the sign change
+// Signed integer min / max on the keys order the scores to within q and carry the winner's column; a difference of two keys
+// times q / 16 is the difference of the scores up to 3 q (cc + M rounds cc: q / 2; the fma: q / 2; twice; the column numbers: < q).
+// key_scale: q for a set whose largest |score| is bounded by smax (0: no usable scale — decide every cell exactly)
+__device__ __forceinline__ float key_quantum(float smax) {
+    int e2 = 0;
+    frexpf(smax, &e2);                                   // smax < 2^e2
+    return (smax > 0.f && smax < 1e30f && e2 > -90) ? ldexpf(1.f, e2 - 21) : 0.f;   // |score| / q < 2^21: M +- 2^22 q is the binade of M
+}
+// ||c||^2 + M of a padding column, in units of q above M: above every real score (< 2^21), inside the binade (< 2^22)
+constexpr float kKeyPad = 4194240.f;   // 2^22 - 64
+// one block of 16 accumulator columns -> (smallest key, second smallest key).  cc4: the block's ||c||^2 + M (padding columns:
+// M + 2^20 q).  The smallest: a tree of 3-input mins.  The second smallest: the keys are distinct (column number inside), so
+// key - b - 1 as an UNSIGNED number is huge for the smallest key and (key - b - 1) for every other one: second = b + 1 +
+// unsigned-min of those (add + min fuse into one instruction, VIADDMNMX).  mul16 = 16 as a run-time value: a register factor stays
+// an IMAD on the FMA pipe, a constant 16 becomes LEA on the half-rate ALU pipe that the mins already load.
+__device__ __forceinline__ void top2_block16(const uint32_t (&v)[16], const float4* __restrict__ cc4, float unscale, uint32_t mul16, int& b, int& sec) {
+    int w[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 cq = cc4[j];
+        w[4 * j + 0] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 0]), cq.x)) * mul16 + (unsigned)(4 * j + 0));
+        w[4 * j + 1] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 1]), cq.y)) * mul16 + (unsigned)(4 * j + 1));
+        w[4 * j + 2] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 2]), cq.z)) * mul16 + (unsigned)(4 * j + 2));
+        w[4 * j + 3] = (int)(__float_as_uint(fmaf(unscale, __uint_as_float(v[4 * j + 3]), cq.w)) * mul16 + (unsigned)(4 * j + 3));
+    }
+    b = min(__vimin3_s32(__vimin3_s32(w[0], w[1], w[2]), __vimin3_s32(w[3], w[4], w[5]), __vimin3_s32(w[6], w[7], w[8])),
+            __vimin3_s32(__vimin3_s32(w[9], w[10], w[11]), __vimin3_s32(w[12], w[13], w[14]), w[15]));
+    const int nb1 = -(b + 1);
+    unsigned u[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) u[j] = (unsigned)(w[j] + nb1);
+    const unsigned um = min(__vimin3_u32(__vimin3_u32(u[0], u[1], u[2]), __vimin3_u32(u[3], u[4], u[5]), __vimin3_u32(u[6], u[7], u[8])),
+                            __vimin3_u32(__vimin3_u32(u[9], u[10], u[11]), __vimin3_u32(u[12], u[13], u[14]), u[15]));
+    sec = (int)((unsigned)(b + 1) + um);
 }
 
 // index of a column inside its 16-column block, in the 4 low mantissa bits of the score

@@ -112,6 +112,7 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
     uint64_t* acc_free = tables_ready + 1;                           // [G] bundles: the group has read its accumulator, the next set's products may overwrite it
     uint32_t* tmem_word = reinterpret_cast<uint32_t*>(acc_free + kTcMaxGroups);
     SetRef* set_ref = reinterpret_cast<SetRef*>(tmem_word + 2);      // [kTcMaxSets] label / exact-centre pointers of the bundle's problems
+    float4* keyc = reinterpret_cast<float4*>(smem + 304);            // [kTcMaxSets] per centre set: near-tie bound in key units tk_a, tk_b, tk_c (see below), un-scaling factor
     // kMulti: several centre sets per tile (bundles; assignment-only sessions).  A separate instance: the single-set pass keeps its registers
     CentreHeader* hdr = reinterpret_cast<CentreHeader*>(smem + T.off_hdr);
     float* bmat = reinterpret_cast<float*>(smem + T.off_b);
@@ -212,8 +213,8 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
             const uint32_t idesc0 = (1u << 4) | ((uint32_t)(128 >> 4) << 24);           // D fp32, A/B fp16, both K-major, M = 128
             if constexpr (!kMulti) {
                 const int N = reinterpret_cast<const CentreHeader*>(smem + T.off_hdr)->tc_n;
-                const uint32_t idesc_hi = idesc0 | ((uint32_t)((npad + N) >> 3) << 17);     // xh * [ch | cl] -> columns [0, npad + N)
-                const uint32_t idesc_lo = idesc0 | ((uint32_t)(N >> 3) << 17);              // xl * ch        -> columns [0, N)
+                const uint32_t idesc = idesc0 | ((uint32_t)(N >> 3) << 17);   // N columns: xh * ch, xh * cl and xl * ch all accumulate into [0, N)
+                const uint64_t desc_l0 = desc_b0 + (uint64_t)npad;            // the low parts: npad rows of 16 B further in every marker group
                 for (; tile < p_end; ++tile, ++it) {
                     const uint32_t g = it % kTcGroups;
                     mbar_wait_hint(&a_ready[g], (ar_phase >> g) & 1u, T.wait_hint);
@@ -222,8 +223,9 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                     if (elect_one()) {
                         const uint32_t acc = tmem + g * buf_cols, ah = acc + (uint32_t)(2 * npad), al = ah + (uint32_t)acols;
                         for (int s = 0; s < g16 / 2; ++s) {
-                            umma_f16_ts(acc, ah + 8 * s, desc_b0 + s * desc_step, idesc_hi, s > 0 ? 1u : 0u);
-                            umma_f16_ts(acc, al + 8 * s, desc_b0 + s * desc_step, idesc_lo, 1);
+                            umma_f16_ts(acc, ah + 8 * s, desc_b0 + s * desc_step, idesc, s > 0 ? 1u : 0u);   // xh * ch
+                            umma_f16_ts(acc, ah + 8 * s, desc_l0 + s * desc_step, idesc, 1);                  // xh * cl
+                            umma_f16_ts(acc, al + 8 * s, desc_b0 + s * desc_step, idesc, 1);                  // xl * ch
                         }
                         umma_commit(&mma_done[g]);
                     }
@@ -257,14 +259,14 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                         if (q == 0) ar_phase ^= 1u << g; else free_phase ^= 1u << g;
                         tc_fence_after();
                         const int N = reinterpret_cast<const CentreHeader*>(smem + T.off_hdr + q * T.set_bytes)->tc_n;
-                        const uint32_t idesc_hi = idesc0 | ((uint32_t)((npad + N) >> 3) << 17);
-                        const uint32_t idesc_lo = idesc0 | ((uint32_t)(N >> 3) << 17);
+                        const uint32_t idesc = idesc0 | ((uint32_t)(N >> 3) << 17);
                         if (elect_one()) {
                             const uint32_t acc = tmem + g * buf_cols, ah = acc + (uint32_t)(2 * npad), al = ah + (uint32_t)acols;
-                            const uint64_t db = desc_b0 + q * desc_set;
+                            const uint64_t db = desc_b0 + q * desc_set, dl = db + (uint64_t)npad;
                             for (int s = 0; s < g16 / 2; ++s) {
-                                umma_f16_ts(acc, ah + 8 * s, db + s * desc_step, idesc_hi, s > 0 ? 1u : 0u);
-                                umma_f16_ts(acc, al + 8 * s, db + s * desc_step, idesc_lo, 1);
+                                umma_f16_ts(acc, ah + 8 * s, db + s * desc_step, idesc, s > 0 ? 1u : 0u);
+                                umma_f16_ts(acc, ah + 8 * s, dl + s * desc_step, idesc, 1);
+                                umma_f16_ts(acc, al + 8 * s, db + s * desc_step, idesc, 1);
                             }
                             umma_commit(&mma_done[g]);
                         }
@@ -341,9 +343,33 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
             for (int i = threadIdx.x; i < 2 * g16 * npad; i += kTcWarps * 32) bdst[i] = bsrc[i];   // g16 groups x 2*npad rows x 16 B
             float* cq = reinterpret_cast<float*>(base + T.off_cc);
             int32_t* oq = reinterpret_cast<int32_t*>(base + T.off_orig);
+            const CentreHeader* hq = q ? pq->hdr : pr.hdr;
+            // sortable integer keys (tc_device.cuh): every score of the set is bounded by ||x||^2 + 2 ||c||^2
+            const float ccm = hq->cc_max;
+            const float qq = key_quantum(*pr.xx_max + 2.0f * ccm);
+            const float big_m = 12582912.f * qq;   // 1.5 * 2^23 * q  (0 without a usable scale: every cell is then decided exactly)
+            const int kact_q = hq->k_act;
             for (int i = threadIdx.x; i < npad; i += kTcWarps * 32) {
-                cq[i] = tab[i];
+                cq[i] = i < kact_q ? tab[i] + big_m : big_m + kKeyPad * qq;   // (padding columns: above every real score, inside the binade of M)
                 oq[i] = torig[i];
+            }
+            if (threadIdx.x == 32 * q) {
+                // near-tie bound of a pair of scores, in key units (q / 16): tau = tau_a (X + cc_max) + tau_b (X + 2 cc_max) + abs1 sqrt(X) + abs2 + 3 q,
+                // X = the tile's bound of ||x||^2.  tau_a: the fp16 splits leave at most 3 * 2^-22 (proved: |v - hi - lo| <= 2^-22 |v| for
+                // round-to-nearest parts, three cross terms); the fp32 accumulation inside the tensor core is allowed 2^-21 per product —
+                // measured on this part at <= 2^-24 per step, also for same-sign terms (profiles/microbench/tc_probe_f16.cu) — with 3 products
+                // per K = 16 step into one column; both relative to sum|x_j c_j| <= (||x||^2 + ||c||^2) / 2, doubled by the factor -2 and again
+                // for a difference of two scores.  tau_b: the un-scaling fma and cc + M (relative to |score| <= ||x||^2 + 2 ||c||^2).  abs1 /
+                // abs2: the absolute part of the split error (fp16 subnormals).  3 q: the keys' own resolution.
+                const float tau_a = 2.f * (3.f * 2.3841858e-7f + (float)(3 * (g16 / 2) + 1) * 4.7683716e-7f);
+                const float tau_b = 2.f * (4.f * 5.9604645e-8f);
+                const float cc2 = 2.0f * ccm, iq16 = qq > 0.f ? 16.f / qq : 0.f;
+                float4 kc;
+                kc.x = (tau_a + tau_b) * iq16;
+                kc.y = hq->tc_abs1 * iq16;
+                kc.z = (hq->force_exact || !(qq > 0.f)) ? INFINITY : (tau_a * 0.5f * cc2 + tau_b * cc2 + hq->tc_abs2 + 3.f * qq) * iq16;
+                kc.w = hq->tc_unscale;
+                keyc[q] = kc;
             }
             if (T.mu_in_smem) {
                 double* mq = reinterpret_cast<double*>(base + T.off_mu);
@@ -360,21 +386,9 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
         int N = hdr->tc_n, n_act = hdr->k_act;
         const double* mu_exact = T.mu_in_smem ? mu_s : pr.mu;
         const int mu_ld = T.mu_in_smem ? (d | 1) : d;
-        bool trivial = hdr->trivial != 0, force_exact = hdr->force_exact != 0;
-        // error bound of a score: the fp16 splits leave at most 3 * 2^-22 (proved: |v - hi - lo| <= 2^-22 |v| for round-to-nearest
-        // parts, three cross terms); the fp32 accumulation inside the tensor core is allowed 2^-21 per product step — measured on
-        // this part at <= 2^-24 per step, also for same-sign terms where a truncating adder's bias would add up
-        // (profiles/microbench/tc_probe_f16.cu: total error <= 8e-7, an fp32 FMA chain gives 5.7e-7).  Both are relative to
-        // sum|x_j c_j| <= (||x||^2 + ||c||^2) / 2 and doubled by the factor -2.  The sum of the two accumulator halves, the
-        // un-scaling fma and cc add 4 * 2^-24; twice all that for a difference of two scores, plus the 4 masked index bits
-        // (2 * 2^-19); the absolute part of the split error (fp16 subnormals) comes through tc_abs1 / tc_abs2.
-        // Per score k the first two parts are bounded by (||x||^2 + ||c_k||^2), the last part and the index bits by |score| <=
-        // ||x||^2 + 2 ||c_k||^2; for a pair of scores: tau = tau_a (X + cc_max) + tau_b (X + 2 cc_max).
-        const float tau_a = 2.f * (3.f * 2.3841858e-7f + (float)(g16 + 1) * 4.7683716e-7f);
-        const float tau_b = 2.f * (4.f * 5.9604645e-8f) + 3.8146973e-6f;
+        bool trivial = hdr->trivial != 0;
         const float scale_x = hdr->tc_scale_x;   // (the same for every set of a bundle: it depends on the cells only)
-        float unscale = hdr->tc_unscale, abs1 = hdr->tc_abs1, abs2 = hdr->tc_abs2;
-        float cc2 = 2.0f * hdr->cc_max;
+        float4 kc = keyc[0];                      // tk_a, tk_b, tk_c, un-scaling factor of the current set
         uint32_t set_off = 0;   // byte offset of the current set's tables (bundles)
         int32_t* labels_q = pr.labels;
         const bool delta = kLloyd && (kDeltaOnly || pr.delta);   // (a session that lets finalize set it has allocated the lists)
@@ -424,11 +438,7 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
                 N = h->tc_n;
                 n_act = h->k_act;
                 trivial = h->trivial != 0;
-                force_exact = h->force_exact != 0;
-                unscale = h->tc_unscale;
-                abs1 = h->tc_abs1;
-                abs2 = h->tc_abs2;
-                cc2 = 2.0f * h->cc_max;
+                kc = keyc[q];
                 set_off = (uint32_t)q * (uint32_t)T.set_bytes;
                 mu_exact = T.mu_in_smem ? reinterpret_cast<const double*>(base + T.off_mu) : set_ref[q].mu;
                 labels_q = set_ref[q].labels;
@@ -441,35 +451,21 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
             DPR_PROF(3);
             lab = 0;
             if (!trivial) {
-                float best = 3.3e38f, second = 3.3e38f;
-                int bchunk = 0;
+                int best = 0x7fffffff, second = 0x7fffffff, bchunk = 0;
                 for (int n0 = 0; n0 < N; n0 += 16) {   // N is a multiple of 16
-                    uint32_t v[32];
-                    tmem_ld16(lane_base + n0, v, 0);                        // x . ch (+ xl . ch)
-                    tmem_ld16(lane_base + (uint32_t)npad + n0, v, 16);     // xh . cl
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    uint32_t v[16];
+                    tmem_ld16_raw(lane_base + n0, v);
+                    tmem_wait_ld16(v);
                     DPR_PROF(4);
-                    const float prev = best;
-                    const float4* cc4 = reinterpret_cast<const float4*>(smem + set_off + T.off_cc) + (n0 >> 2);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 c = cc4[q];
-                        const float s0 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * q + 0]) + __uint_as_float(v[16 + 4 * q + 0]), c.x), 4 * q + 0);
-                        const float s1 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * q + 1]) + __uint_as_float(v[16 + 4 * q + 1]), c.y), 4 * q + 1);
-                        const float s2 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * q + 2]) + __uint_as_float(v[16 + 4 * q + 2]), c.z), 4 * q + 2);
-                        const float s3 = pack_idx4(fmaf(unscale, __uint_as_float(v[4 * q + 3]) + __uint_as_float(v[16 + 4 * q + 3]), c.w), 4 * q + 3);
-                        const float lo0 = fminf(s0, s1), hi0 = fmaxf(s0, s1);
-                        second = fmin3(fmaxf(best, lo0), second, hi0);
-                        best = fminf(best, lo0);
-                        const float lo1 = fminf(s2, s3), hi1 = fmaxf(s2, s3);
-                        second = fmin3(fmaxf(best, lo1), second, hi1);
-                        best = fminf(best, lo1);
-                    }
-                    if (best < prev) bchunk = n0;
+                    int b, sec;
+                    top2_block16(v, reinterpret_cast<const float4*>(smem + set_off + T.off_cc) + (n0 >> 2), kc.w, T.key_mul, b, sec);
+                    if (b < best) bchunk = n0;   // (strict: an equal key of a later block never displaces an earlier one)
+                    second = __vimin3_s32(max(best, b), second, sec);
+                    best = min(best, b);
                 }
-                const float tau = tau_a * (xx_tile + 0.5f * cc2) + tau_b * (xx_tile + cc2) + (abs1 * sqrtf(xx_tile) + abs2) + 1e-30f;
-                const int a = bchunk + (int)(__float_as_uint(best) & 15u);
-                const bool sure = (second - best > tau) && !force_exact;
+                const float tk = fmaf(kc.x, xx_tile, fmaf(kc.y, sqrtf(xx_tile), kc.z));
+                const int a = bchunk + (best & 15);
+                const bool sure = (float)(second - best) > tk;
                 const int32_t* orig_q = reinterpret_cast<const int32_t*>(smem + set_off + T.off_orig);
                 lab = orig_q[a < n_act ? a : 0];
                 DPR_PROF(5);
@@ -780,6 +776,7 @@ int plan_tc_pass(int d, int k_max, int sets_wanted, TcPlan* plan) {
     plan->groups = G;
     plan->g8 = g16;
     plan->wait_hint = 2000;
+    plan->key_mul = 16u;
     plan->npad = npad;
     plan->tmem_cols = tmem_cols;
     plan->stages = S;

@@ -13,6 +13,8 @@
 
 #include <cuda_fp16.h>
 
+#include <cstdio>
+
 namespace dpr {
 
 // Build header / chunk table / slot map of one problem from its fp64 centres.  One CTA; k, d are small.
@@ -101,10 +103,12 @@ __device__ void build_centre_table(const Problem& pr, const double* __restrict__
             cc[t] = row >= 0 ? (float)s_cc[row] : 3.0e38f;
             if (t < kc) pr.orig[h->chunk_base[q] + t] = row;
         }
-        for (int e = threadIdx.x; e < kcp * 4 * tile_groups(d); e += blockDim.x) {
-            const int j = e / kcp, t = e % kcp;
-            w[e] = (t < real && j < d) ? (float)(-2.0 * mu[(size_t)s_act[real_before + t] * d + j]) : 0.f;
-        }
+        // (a session of the tensor-core pass runs the FFMA kernel only to sum given labels, which reads no coefficients: skipped there)
+        if (!pr.tc_table)
+            for (int e = threadIdx.x; e < kcp * 4 * tile_groups(d); e += blockDim.x) {
+                const int j = e / kcp, t = e % kcp;
+                w[e] = (t < real && j < d) ? (float)(-2.0 * mu[(size_t)s_act[real_before + t] * d + j]) : 0.f;
+            }
         real_before += real;
     }
     // Tensor-core path (tc_pass.cu): the B operand of D = X * (-2 C)^T for tcgen05.mma kind::f16, K-major no-swizzle
@@ -215,14 +219,21 @@ __global__ void reduce_partials_kernel(const Problem* problems, const int32_t* c
 // ---------------------------------------------------------------------------------------------------
 // `in`: n_seg tables of this problem ([k_max*d sums][k_max counts][1 changed] each), summed in segment order; s_mu: shared memory
 // for the new centres when they fit (mu_in_smem): later phases read them there instead of through L2
+#ifdef DPR_RF_PROFILE
+#define RF_STAMP(i) do { if (threadIdx.x == 0) rf_t[i] = clock64(); } while (0)
+__device__ long long rf_t[16];
+#else
+#define RF_STAMP(i)
+#endif
 __device__ void finalize_body(Problem* problems, int p, const Problem& pr, const double* in, int n_seg, int k_max, int iter, int max_iter, int table_cap,
                               int allow_delta, int32_t* n_active_out, int mu_in_smem, double* s_mu) {
     const int k = pr.k, d = pr.d;
+    RF_STAMP(5);
     const int64_t stride = (int64_t)k_max * d;
     const int64_t entries = stride + k_max + 1;
     __shared__ long long s_changed;
-    // totals in fixed segment order
-    for (int64_t e = threadIdx.x; e < entries; e += blockDim.x) {
+    // totals in fixed segment order.  First the counts and the changed-label count (the update of every coefficient needs its row's count) ...
+    auto total = [&](int64_t e) {
         double acc = 0.0;
         for (int s0 = 0; s0 < n_seg; s0 += 16) {   // all loads in flight, then the fixed-order sum
             double v[16];
@@ -231,17 +242,20 @@ __device__ void finalize_body(Problem* problems, int p, const Problem& pr, const
 #pragma unroll
             for (int q = 0; q < 16; ++q) acc += v[q];
         }
-        if (e < stride) {
-            const int c = (int)(e / d), j = (int)(e % d);
-            if (c < k) pr.sums[(size_t)c * d + j] = (pr.delta ? pr.sums[(size_t)c * d + j] : 0.0) + acc;
-        } else if (e < stride + k_max) {
+        return acc;
+    };
+    for (int64_t e = stride + threadIdx.x; e < entries; e += blockDim.x) {
+        const double acc = total(e);
+        if (e < stride + k_max) {
             const int c = (int)(e - stride);
             if (c < k) pr.counts[c] = (pr.delta ? pr.counts[c] : 0LL) + (long long)acc;
         } else {
             s_changed = (long long)acc;
         }
     }
+    __threadfence_block();
     __syncthreads();
+    RF_STAMP(6);
     const long long changed = s_changed;
     const bool converged = (changed == 0 && iter > 20);
     if (threadIdx.x == 0) {
@@ -251,30 +265,42 @@ __device__ void finalize_body(Problem* problems, int p, const Problem& pr, const
         // valid from here on, and even a slot where every cell moves costs at most two contributions per cell
         problems[p].delta = allow_delta ? 1 : 0;
     }
-    if (converged || iter + 1 >= max_iter) {
-        // Clusterer.cpp:247-249: break BEFORE the update: centres stay those of the previous iteration.
-        // (at the iteration cap the reference has just run its last update, so apply it below first)
-        if (threadIdx.x == 0) problems[p].done = 1;
-        if (converged) return;
-    }
-    // reg_i = min(reg, reg * ((float)i / (float)20))   (Clusterer.cpp:251)
+    const bool last = iter + 1 >= max_iter;
+    if (threadIdx.x == 0 && (converged || last)) problems[p].done = 1;
+    // ... then the running sums and, unless the fit has just converged (Clusterer.cpp:247-249: break BEFORE the update, the centres
+    // stay those of the previous iteration; at the iteration cap the reference has just run its last update, so it is applied), the
+    // soft threshold in the same sweep.   reg_i = min(reg, reg * ((float)i / (float)20))   (Clusterer.cpp:251)
     const double ramp = pr.reg * (double)((float)iter / (float)20);
     const double reg_i = pr.reg < ramp ? pr.reg : ramp;
-    for (int e = threadIdx.x; e < k * d; e += blockDim.x) {
-        const int c = e / d;
-        const double S = pr.sums[e];
+    for (int64_t e = threadIdx.x; e < stride; e += blockDim.x) {
+        const double acc = total(e);
+        const int c = (int)(e / d), j = (int)(e % d);
+        if (c >= k) continue;
+        const size_t at = (size_t)c * d + j;
+        const double S = (pr.delta ? pr.sums[at] : 0.0) + acc;
+        pr.sums[at] = S;
+        if (converged) continue;
         const double nn = (double)pr.counts[c];
         const double lo = (S - reg_i / 2) / nn;
         const double hi = (S + reg_i / 2) / nn;
         const double m0 = lo > 0.0 ? lo : 0.0;  // _mm_max_pd(lo, 0): second operand when lo is NaN
         const double m = hi < m0 ? hi : m0;     // _mm_min_pd(hi, m0)
-        pr.mu[e] = m;
-        if (mu_in_smem) s_mu[e] = m;
+        pr.mu[at] = m;
+        if (mu_in_smem) s_mu[at] = m;
     }
+    if (converged) return;
     __threadfence_block();
     __syncthreads();
+    RF_STAMP(7);
     build_centre_table(pr, mu_in_smem ? s_mu : pr.mu, pr.no_zero, table_cap);
+    __syncthreads();
+    RF_STAMP(8);
     if (threadIdx.x == 0 && n_active_out && !(iter + 1 >= max_iter)) atomicAdd(n_active_out, 1);
+#ifdef DPR_RF_PROFILE
+    if (threadIdx.x == 0 && iter == 5)
+        printf("reduce_finalize (cycles): find ranges %lld, table sums %lld, cluster barrier %lld, dsmem sums %lld, barrier %lld | running sums %lld, soft threshold %lld, centre tables %lld\n",
+               rf_t[1] - rf_t[0], rf_t[2] - rf_t[1], rf_t[3] - rf_t[2], rf_t[4] - rf_t[3], rf_t[5] - rf_t[4], rf_t[6] - rf_t[5], rf_t[7] - rf_t[6], rf_t[8] - rf_t[7]);
+#endif
 }
 
 __global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_seg, int k_max, int iter, int max_iter, int table_cap,
@@ -306,6 +332,7 @@ __global__ void __cluster_dims__(kFuseCtas, 1, 1) reduce_finalize_kernel(Problem
     double* s_mu = s_dyn;
     double* s_part = s_dyn + (mu_in_smem ? (size_t)k_max * pr.d : 0);   // this CTA's partial table; in CTA 0 later the total
     if (p == 0 && r == 0 && threadIdx.x == 0) n_active2[(iter + 1) & 1] = 0;
+    if (r == 0) RF_STAMP(0);
     if (!pr.done) {
         const int t0 = pr.first_tile, t1 = pr.first_tile + pr.n_tiles;
         // the CTAs of the pass whose tile range touches the problem are consecutive: [ca, cb)
@@ -323,28 +350,49 @@ __global__ void __cluster_dims__(kFuseCtas, 1, 1) reduce_finalize_kernel(Problem
         }
         __syncthreads();
         const int ca = s_ca, cb = max(s_cb, s_ca);
+        if (r == 0) RF_STAMP(1);
         const int c0 = ca + (int)((int64_t)(cb - ca) * r / kFuseCtas), c1 = ca + (int)((int64_t)(cb - ca) * (r + 1) / kFuseCtas);
+        // which of this CTA's tables exist (the pass CTAs whose range touches the problem): one bit each, found once
+        constexpr int kInFlight = 24;
+        __shared__ unsigned s_use[8];   // up to 8 x 24 tables per CTA of the cluster
+        if (threadIdx.x < 8 * 32) {
+            const int chunk = threadIdx.x >> 5, cc = c0 + chunk * kInFlight + (threadIdx.x & 31);
+            bool use = (threadIdx.x & 31) < kInFlight && cc < c1;
+            if (use) {
+                const int a = cta_tile_start[cc], b = cta_tile_start[cc + 1];
+                use = !(a >= t1 || b <= t0 || a >= b);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, use);
+            if ((threadIdx.x & 31) == 0) s_use[chunk] = m;
+        }
+        __syncthreads();
         for (int64_t e = threadIdx.x; e < entries; e += blockDim.x) {
             double acc = 0.0;
-            for (int c = c0; c < c1; c += 8) {   // 8 loads in flight, then the fixed-order sum
-                double v[8];
+            for (int c = c0, chunk = 0; c < c1; c += kInFlight, ++chunk) {   // all loads of the chunk in flight, then the fixed-order sum
+                const unsigned m = chunk < 8 ? s_use[chunk] : 0u;
+                double v[kInFlight];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int cc = c + q;
-                    bool use = cc < c1;
-                    if (use) {
-                        const int a = cta_tile_start[cc], b = cta_tile_start[cc + 1];
-                        use = !(a >= t1 || b <= t0 || a >= b);
+                for (int q = 0; q < kInFlight; ++q) {
+                    bool use = (m >> q) & 1u;
+                    if (chunk >= 8) {   // (more than 192 tables per CTA: no pass grid is that large; kept correct all the same)
+                        const int cc = c + q;
+                        use = cc < c1;
+                        if (use) {
+                            const int a = cta_tile_start[cc], b = cta_tile_start[cc + 1];
+                            use = !(a >= t1 || b <= t0 || a >= b);
+                        }
                     }
-                    v[q] = use ? cta_tables[(size_t)(cc + p) * entries + e] : 0.0;
+                    v[q] = use ? __ldcg(cta_tables + (size_t)(c + q + p) * entries + e) : 0.0;
                 }
 #pragma unroll
-                for (int q = 0; q < 8; ++q) acc += v[q];
+                for (int q = 0; q < kInFlight; ++q) acc += v[q];
             }
             s_part[e] = acc;
         }
     }
+    if (r == 0) RF_STAMP(2);
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (r == 0) RF_STAMP(3);
     if (r == 0 && !pr.done) {
         const uint32_t mine = (uint32_t)__cvta_generic_to_shared(s_part);
         for (int64_t e = threadIdx.x; e < entries; e += blockDim.x) {
@@ -361,6 +409,7 @@ __global__ void __cluster_dims__(kFuseCtas, 1, 1) reduce_finalize_kernel(Problem
             s_part[e] = acc;   // (each thread overwrites only the entries it has just read from its own table)
         }
     }
+    if (r == 0) RF_STAMP(4);
     // the other CTAs' tables must stay alive until CTA 0 has read them
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     if (r != 0 || pr.done) return;

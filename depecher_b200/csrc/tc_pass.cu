@@ -53,35 +53,47 @@ __device__ __noinline__ void full_warp_sums(const float* __restrict__ slot, int 
 }
 
 // Lloyd full mode, one tile: warp w of the group takes the labels w, w + 4, ...; it finds a label's cells by ballot over the
-// labels the four warps published and adds their rows in cell order, lane = marker.  `lb` is double-buffered by the caller
-// (a warp can be one tile ahead of a slow neighbour at most).
+// labels the four warps published and adds their rows (lane = marker, fp64 registers, highest cell first: a fixed order) into the
+// group's table in shared memory.  `lb` is double-buffered by the caller (a warp can be one tile ahead of a slow neighbour at most).
+// The counts come from the warps' own cells (match.any: one shared-memory integer add per label and warp, which commutes).
+// The loop is bound by instruction issue (F2F + DADD per element, plus the bit scan): the address of a cell's second marker block
+// is the first one's plus a constant, and a set bit costs FLO + clear + LEA.
 __device__ __noinline__ void full_tile_sums(const float* __restrict__ slot, unsigned char* lb, double* gsum, long long* gcnt, int d, int k,
                                             int grp, int wq, int lane, int mycell_in_tile, int lab) {
     lb[mycell_in_tile] = (unsigned char)(lab >= 0 ? lab : 255);
+    {   // this warp's 32 cells: one add per label present among them
+        const unsigned peers = __match_any_sync(0xffffffffu, lab);
+        if (lab >= 0 && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(reinterpret_cast<unsigned long long*>(gcnt) + lab, (unsigned long long)__popc(peers));
+    }
     asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
     const int l0 = lb[lane], l1 = lb[32 + lane], l2 = lb[64 + lane], l3 = lb[96 + lane];
+    constexpr int kBlock1 = 8 * kGroupFloats;   // floats between a cell's marker j and marker j + 32 (8 marker groups)
     for (int jb = 0; jb < d; jb += 64) {
         const int j0 = jb + lane, j1 = jb + 32 + lane;
-        const float* r0 = slot + x_slot_index(0, j0 < d ? j0 : 0);
-        const float* r1 = slot + x_slot_index(0, j1 < d ? j1 : 0);
+        const bool on0 = j0 < d, on1 = j1 < d;
+        const float* r0 = slot + x_slot_index(0, on0 ? j0 : 0);   // marker j0 of cell 0 (clamped: the load is unconditional)
         for (int L = wq; L < k; L += 4) {
-            unsigned m[4] = {__ballot_sync(0xffffffffu, l0 == L), __ballot_sync(0xffffffffu, l1 == L), __ballot_sync(0xffffffffu, l2 == L),
-                             __ballot_sync(0xffffffffu, l3 == L)};
+            const unsigned m[4] = {__ballot_sync(0xffffffffu, l0 == L), __ballot_sync(0xffffffffu, l1 == L), __ballot_sync(0xffffffffu, l2 == L),
+                                   __ballot_sync(0xffffffffu, l3 == L)};
             if (!(m[0] | m[1] | m[2] | m[3])) continue;
             double a0 = 0.0, a1 = 0.0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 unsigned mm = m[q];
+                const uint32_t rq = smem_u32(r0 + 128 * q);   // cells 32 q .. (a shared-memory address: one LEA per cell)
                 while (mm) {
-                    const int c = 32 * q + __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    a0 += (double)r0[4 * c];
-                    a1 += (double)r1[4 * c];
+                    int c;   // the highest set bit (bfind: one FLO; 31 - __clz costs the compiler two more instructions)
+                    asm("bfind.u32 %0, %1;" : "=r"(c) : "r"(mm));
+                    mm ^= 1u << c;
+                    float x0, x1 = 0.f;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x0) : "r"(rq + 16u * (uint32_t)c));
+                    if (on1) asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(x1) : "r"(rq + 16u * (uint32_t)c), "n"(4 * kBlock1));
+                    a0 += (double)x0;
+                    a1 += (double)x1;   // (lanes without a second marker add 0)
                 }
             }
-            if (j0 < d) gsum[L * d + j0] += a0;
-            if (j1 < d) gsum[L * d + j1] += a1;
-            if (jb == 0 && lane == 0) gcnt[L] += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+            if (on0) gsum[L * d + j0] += a0;
+            if (on1) gsum[L * d + j1] += a1;
         }
     }
 }

@@ -270,6 +270,7 @@ static int single_session(dpr_dataset* ds, int k, double reg, int no_zero, bool 
 // pass over a vector with one entry per cell)
 static int copy_labels_out(const int32_t* d_labels, int64_t n, int32_t* host, int32_t base = 0) {
     if (!host) return DPR_OK;
+    if (n >= (1 << 19) && g_stage.cap == 0) DPR_TRY(upload_stage((int64_t)4 << 20));   // (a process that has not uploaded anything yet: the pinned buffers are made here)
     if (n >= (1 << 19) && g_stage.cap > 0) {
         // the caller's vector is pageable: the driver would stage it at a few GB/s.  DMA into the pinned upload buffers instead
         // and let host threads copy a piece out while the next one arrives.

@@ -137,7 +137,21 @@ __global__ void seed_dist_kernel(const SeedFit* fits, int d, int c /* centre jus
         double w = 0.0;
         if (i < f.n) {
             double s = 0.0;
-            for (int j = 0; j < d; ++j) {
+            // a cell's markers come four at a time (one 16-byte load per marker group); differences and squares of a group are independent,
+            // only the additions into s form the left-to-right chain of the reference
+            const float4* x4 = reinterpret_cast<const float4*>(f.x + x_index(i, 0, d));
+            int j = 0;
+            for (; j + 4 <= d; j += 4) {
+                const float4 xv = __ldg(x4 + (size_t)(j >> 2) * (kGroupFloats / 4));
+                const double d0 = __dadd_rn(-(double)xv.x, s_mu[j]), d1 = __dadd_rn(-(double)xv.y, s_mu[j + 1]);
+                const double d2 = __dadd_rn(-(double)xv.z, s_mu[j + 2]), d3 = __dadd_rn(-(double)xv.w, s_mu[j + 3]);
+                const double q0 = __dmul_rn(d0, d0), q1 = __dmul_rn(d1, d1), q2 = __dmul_rn(d2, d2), q3 = __dmul_rn(d3, d3);
+                s = __dadd_rn(s, q0);
+                s = __dadd_rn(s, q1);
+                s = __dadd_rn(s, q2);
+                s = __dadd_rn(s, q3);
+            }
+            for (; j < d; ++j) {
                 const double diff = __dadd_rn(-(double)f.x[x_index(i, j, d)], s_mu[j]);
                 s = __dadd_rn(s, __dmul_rn(diff, diff));
             }
@@ -175,11 +189,18 @@ __global__ void seed_dist_kernel(const SeedFit* fits, int d, int c /* centre jus
 // is summed in ascending order, so the pick only differs from a purely sequential cumsum when x falls within
 // rounding distance (~1e-16 relative) of a boundary.
 __device__ void seed_pick_body(const SeedFit& f, int d, int c, uint64_t seed) {
+    // The scans are sequential by definition (a running sum with an early exit), and one thread does them — but never on global
+    // memory: every stretch it walks (the block sums of a segment, the weights of a block) is first brought into shared memory by the
+    // whole CTA, and the thread reads it four values at a time.  (Walking global memory with a data-dependent exit costs a DRAM/L2 round
+    // trip per element: 40-80 us per round, which was most of a seeding round for batches of small fits and a third of it for 10M cells.)
     const int nb = (int)((f.n + kSeedBlock - 1) / kSeedBlock);
-    const int T = blockDim.x;
+    const int T = blockDim.x;   // == kSeedBlock == 256
     const int seg = (nb + T - 1) / T;
-    __shared__ double s_seg[256];
+    __shared__ __align__(16) double s_seg[256];
+    __shared__ __align__(16) double s_buf[256];
     __shared__ long long s_row;
+    __shared__ double s_x, s_cum;
+    __shared__ int s_sg, s_blk, s_last_blk, s_found;
     {
         double t = 0.0;
         const int b0 = threadIdx.x * seg, b1 = min(nb, b0 + seg);
@@ -187,50 +208,77 @@ __device__ void seed_pick_body(const SeedFit& f, int d, int c, uint64_t seed) {
         s_seg[threadIdx.x] = t;
     }
     __syncthreads();
+    // first element of v[0..n) at which the running sum (started at cum) exceeds x, skipping zero weights; cum is left at the sum before
+    // that element (or after all n); last_pos: the last positive element seen.  Same additions in the same order as a plain loop.
+    auto scan = [](const double* v, int n, double x, double& cum, int& last_pos) {
+        for (int t0 = 0; t0 < n; t0 += 4) {
+            const double2 a = *reinterpret_cast<const double2*>(v + t0), b = *reinterpret_cast<const double2*>(v + t0 + 2);
+            const double w[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (t0 + q >= n) return -1;
+                if (w[q] > 0) {
+                    last_pos = t0 + q;
+                    const double nxt = cum + w[q];
+                    if (nxt > x) return t0 + q;
+                    cum = nxt;
+                }
+            }
+        }
+        return -1;
+    };
     if (threadIdx.x == 0) {
         double total = 0.0;
         for (int t = 0; t < T; ++t) total += s_seg[t];
         const double u = dpr_rng_unit(dpr_rng_draw(seed, DPR_RNG_SEED, f.fit_id, (uint32_t)c, 0).w[0]);
         const double x = u * total;
         double cum = 0.0;
-        int sg = -1;
-        for (int t = 0; t < T; ++t) {
-            const double nxt = cum + s_seg[t];
-            if (nxt > x && s_seg[t] > 0) { sg = t; break; }
-            cum = nxt;
-        }
-        long long row = 0;
-        if (sg >= 0) {
-            int blk = -1;
-            const int b0 = sg * seg, b1 = min(nb, b0 + seg);
-            int last_blk = -1;
-            for (int b = b0; b < b1; ++b) {
-                const double bs = f.block_sums[b];
-                if (bs > 0) last_blk = b;
-                const double nxt = cum + bs;
-                if (nxt > x && bs > 0) { blk = b; break; }
-                cum = nxt;
-            }
-            if (blk < 0) blk = last_blk;   // rounding of the segment sums: take the segment's last non-empty block
-            double run = cum;
-            const int64_t i0 = (int64_t)blk * kSeedBlock, i1 = min(f.n, i0 + (int64_t)kSeedBlock);
-            long long last_pos = -1;
-            row = -1;
-            for (int64_t i = i0; i < i1; ++i) {
-                const double w = f.w[i];
-                if (w > 0) {
-                    run += w;
-                    last_pos = i;
-                    if (run > x) { row = i; break; }
-                }
-            }
-            if (row < 0) row = last_pos < 0 ? i0 : last_pos;
-        }
-        s_row = row;
-        if (f.rows) f.rows[c] = row;
+        int lp = -1;
+        s_sg = scan(s_seg, T, x, cum, lp);
+        s_x = x;
+        s_cum = cum;
+        s_blk = -1;
+        s_last_blk = -1;
+        s_found = 0;
+        s_row = 0;
     }
     __syncthreads();
+    const int sg = s_sg;
+    if (sg >= 0) {   // (uniform)
+        // the blocks of the segment, 256 at a time
+        const int b0 = sg * seg, b1 = min(nb, b0 + seg);
+        for (int base = b0; base < b1; base += T) {
+            s_buf[threadIdx.x] = base + (int)threadIdx.x < b1 ? f.block_sums[base + threadIdx.x] : 0.0;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double cum = s_cum;
+                int lp = -1;
+                const int at = scan(s_buf, min(T, b1 - base), s_x, cum, lp);
+                s_cum = cum;
+                if (lp >= 0) s_last_blk = base + lp;
+                if (at >= 0) {
+                    s_blk = base + at;
+                    s_found = 1;
+                }
+            }
+            __syncthreads();
+            if (s_found) break;
+        }
+        const int blk = s_blk >= 0 ? s_blk : s_last_blk;   // rounding of the segment sums: take the segment's last non-empty block
+        // the cells of the block
+        const int64_t i0 = (int64_t)blk * kSeedBlock, i1 = min(f.n, i0 + (int64_t)kSeedBlock);
+        s_buf[threadIdx.x] = i0 + threadIdx.x < i1 ? f.w[i0 + threadIdx.x] : 0.0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double run = s_cum;
+            int lp = -1;
+            const int at = scan(s_buf, (int)(i1 - i0), s_x, run, lp);
+            s_row = at >= 0 ? i0 + at : (lp < 0 ? i0 : i0 + lp);
+        }
+        __syncthreads();
+    }
     const long long row = s_row;
+    if (threadIdx.x == 0 && f.rows) f.rows[c] = row;
     for (int j = threadIdx.x; j < d; j += blockDim.x) f.mu[(size_t)c * d + j] = (double)f.x[x_index(row, j, d)];
 }
 

@@ -121,6 +121,17 @@ def test_device_prescaling_matches_host(engine, testdata):
     assert np.allclose(info[1], winfo[1], atol=1e-9) and np.allclose(got, want, rtol=3e-6, atol=1e-6)
 
 
+def test_device_prescaling_pinned_by_stored_depeche_result(engine, testdata):
+    """the same pin as tests/test_host_logic.py::test_prescaling_pinned_by_stored_depeche_result through the device path: the matrix
+    scaled by dpr_dataset_create_scaled (peak centres and sd found on the GPU), allocated onto the stored centres by the tensor-core
+    pass — every one of the 20 000 labels of the stored R result"""
+    X, cc, stored = testdata["X"], testdata["stored_clusterCenters"], testdata["stored_clusterVector"]
+    ds, info = engine.dataset_scaled(X)
+    lab = engine.allocate_points(ds, cc / info[2], True, base=1)["i"]
+    ds.close()
+    assert np.array_equal(lab, stored)
+
+
 def test_peer_mailbox_setup_and_error_paths(engine):
     """dpr_comm_peer_*: a rank can always make its mailbox and hand out the 64-byte CUDA IPC handle; attaching needs a communicator of
     2..8 ranks and one handle per rank — anything else fails loudly and leaves the library on the NCCL / single-GPU path"""

@@ -116,6 +116,31 @@ def test_testdata_scaling_matches_stored_fixture(testdata):
     assert abs(10000 * np.sqrt(14) / 1450 - 25.80) < 0.01
 
 
+def test_prescaling_pinned_by_stored_depeche_result(testdata):
+    """f-3 pin: R itself is not in the image, so pretty() / hist() / the peak centres cannot be regenerated here — but the
+    stored depeche(testData) result carries them implicitly.  The stored cluster vector is dAllocate() of the data scaled with R's own
+    peak centres and sd onto the stored centres (which that package version keeps centred: scaled centre x sd).  Scaling with OUR
+    restatement's centres and allocating with the reference's arithmetic must reproduce all 20 000 stored labels; moving any single
+    marker's centre to a neighbouring histogram bin (0.5 units) changes at least one label (checked below), so equality pins the peak
+    bin of every marker.  (R/depecheLogCenterSd.R:49-63, R/dScaleCoFunction.R:74-88, R/depeche.R:228-232.)"""
+    from oracle.oracle import Oracle
+    orc = Oracle()
+    X, cc, stored = testdata["X"], testdata["stored_clusterCenters"], testdata["stored_clusterVector"]
+    _, info = rapi.depecheLogCenterSd(X)
+    c, sd = np.asarray(info[1], float), float(info[2])
+
+    def labels(centres):
+        return orc.allocate_points(np.ascontiguousarray((X - centres) / sd), cc / sd, True) + 1
+
+    assert info[0] is False
+    assert np.array_equal(labels(c), stored)
+    for j in range(X.shape[1]):          # the pin has power for every marker, in both directions
+        for shift in (0.5, -0.5):
+            moved = c.copy()
+            moved[j] += shift
+            assert not np.array_equal(labels(moved), stored), (j, shift)
+
+
 def test_renumber_by_size_matches_sort_based_definition():
     """depeche() renumbers the clusters by decreasing size (R/depeche.R:236-252); the counting implementation must equal the definition
     through np.unique + one comparison per cluster, including ties in size (old number decides) and unused cluster numbers"""

@@ -286,6 +286,16 @@ class Engine:
                 idx += base
         return {"i": idx}
 
+    def allocate_points_ranked(self, ds: "Dataset", mu, no_zero):
+        """depeche()'s final step on a resident matrix: labels renumbered 1, 2, ... by decreasing cluster size, and the old 0-based labels in
+        rank order (R/depeche.R:228-252)"""
+        mu = _f64(mu)
+        k = mu.shape[0]
+        idx = np.empty(ds.n, np.int32)
+        order = np.empty(k, np.int32)
+        self._chk(self.lib.dpr_dataset_allocate_points_ranked(ds.handle, _ptr(mu, _dp), C.c_int32(k), C.c_int32(int(no_zero)), _ptr(idx, _ip), _ptr(order, _ip)))
+        return idx, order[order >= 0]
+
     def sparse_k_means(self, X, k, reg, no_zero, seed_off_set=0, want_labels=True) -> dict:
         """sparse_k_means(X, k, reg, no_zero, seed) -> {'i','o','c','v','n','m'}   (src/InterfaceUtils.cpp:66-94)"""
         nit, norm = C.c_int32(), C.c_double()

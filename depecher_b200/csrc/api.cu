@@ -1,5 +1,7 @@
 // api.cu — the C ABI (include/depecher_b200.h): context, resident datasets and the entry points that
 // replace the reference's four Rcpp exports (/root/reference/src/InterfaceUtils.cpp:66-161).
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -178,6 +180,43 @@ static void copy_piece(const double* src, double* dst, int64_t count) {
 #endif
     std::memcpy(dst, src, sizeof(double) * (size_t)count);
 }
+// double -> float, reporting whether every value survived the trip unchanged (a NaN counts as changed: the caller then ships doubles)
+#if defined(__x86_64__)
+__attribute__((target("avx"))) static bool narrow_check_avx(const double* src, float* dst, int64_t a, int64_t b) {
+    int64_t i = a;
+    bool ok = true;
+    for (; i < b && (reinterpret_cast<uintptr_t>(dst + i) & 31); ++i) {
+        dst[i] = (float)src[i];
+        ok &= (double)dst[i] == src[i];
+    }
+    __m256d all = _mm256_castsi256_pd(_mm256_set1_epi64x(-1));
+    for (; i + 8 <= b; i += 8) {
+        const __m256d x0 = _mm256_loadu_pd(src + i), x1 = _mm256_loadu_pd(src + i + 4);
+        const __m128 lo = _mm256_cvtpd_ps(x0), hi = _mm256_cvtpd_ps(x1);
+        all = _mm256_and_pd(all, _mm256_and_pd(_mm256_cmp_pd(_mm256_cvtps_pd(lo), x0, _CMP_EQ_OQ), _mm256_cmp_pd(_mm256_cvtps_pd(hi), x1, _CMP_EQ_OQ)));
+        _mm256_stream_ps(dst + i, _mm256_set_m128(hi, lo));
+    }
+    ok &= _mm256_movemask_pd(all) == 0xf;
+    for (; i < b; ++i) {
+        dst[i] = (float)src[i];
+        ok &= (double)dst[i] == src[i];
+    }
+    _mm_sfence();
+    return ok;
+}
+#endif
+static bool narrow_check(const double* src, float* dst, int64_t a, int64_t b) {
+#if defined(__x86_64__)
+    static const bool avx = __builtin_cpu_supports("avx");
+    if (avx) return narrow_check_avx(src, dst, a, b);
+#endif
+    bool ok = true;
+    for (int64_t i = a; i < b; ++i) {
+        dst[i] = (float)src[i];
+        ok &= (double)dst[i] == src[i];
+    }
+    return ok;
+}
 template <typename T>
 static void narrow_piece(const T* src, float* dst, int64_t a, int64_t b) {
     for (int64_t i = a; i < b; ++i) dst[i] = (float)src[i];
@@ -268,7 +307,7 @@ static int single_session(dpr_dataset* ds, int k, double reg, int no_zero, bool 
 
 // `base` is added to every label on the way out (R's clusters are 1-based: dAllocate.R:127-134 — adding it here saves the caller a
 // pass over a vector with one entry per cell)
-static int copy_labels_out(const int32_t* d_labels, int64_t n, int32_t* host, int32_t base = 0) {
+static int copy_labels_out(const int32_t* d_labels, int64_t n, int32_t* host, int32_t base = 0, const int32_t* lut = nullptr) {   // lut (host, nullable): label l goes out as lut[l]
     if (!host) return DPR_OK;
     if (n >= (1 << 19) && g_stage.cap == 0) DPR_TRY(upload_stage((int64_t)4 << 20));   // (a process that has not uploaded anything yet: the pinned buffers are made here)
     if (n >= (1 << 19) && g_stage.cap > 0) {
@@ -291,7 +330,9 @@ static int copy_labels_out(const int32_t* d_labels, int64_t n, int32_t* host, in
                 std::vector<std::thread> pool;
                 auto work = [=](int t) {
                     const int64_t a = prev_cnt * t / threads, z = prev_cnt * (t + 1) / threads;
-                    if (base == 0) std::memcpy(host + prev0 + a, src + a, sizeof(int32_t) * (size_t)(z - a));
+                    if (lut)
+                        for (int64_t e = a; e < z; ++e) host[prev0 + e] = lut[src[e]];
+                    else if (base == 0) std::memcpy(host + prev0 + a, src + a, sizeof(int32_t) * (size_t)(z - a));
                     else
                         for (int64_t e = a; e < z; ++e) host[prev0 + e] = src[e] + base;
                 };
@@ -306,7 +347,9 @@ static int copy_labels_out(const int32_t* d_labels, int64_t n, int32_t* host, in
     }
     DPR_CUDA(cudaMemcpyAsync(host, d_labels, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx().stream));
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));
-    if (base != 0)
+    if (lut)
+        for (int64_t e = 0; e < n; ++e) host[e] = lut[host[e]];
+    else if (base != 0)
         for (int64_t e = 0; e < n; ++e) host[e] += base;
     return DPR_OK;
 }
@@ -640,10 +683,13 @@ std::vector<double> r_pretty_breaks(double lo, double hi, int ndiv) {
         if (std::fabs(v) < 1e-14 * delta) v = 0.0;
     return b;
 }
-double median_of(std::vector<double> v) {
-    std::sort(v.begin(), v.end());
+double median_of(std::vector<double> v) {   // (selection, not a sort: hist() of 10M cells has 200 000 breaks per marker)
     const size_t m = v.size();
-    return m % 2 ? v[m / 2] : 0.5 * (v[m / 2 - 1] + v[m / 2]);
+    std::nth_element(v.begin(), v.begin() + m / 2, v.end());
+    const double hi = v[m / 2];
+    if (m % 2) return hi;
+    const double lo = *std::max_element(v.begin(), v.begin() + m / 2);
+    return 0.5 * (lo + hi);
 }
 }  // namespace
 
@@ -652,6 +698,15 @@ int dpr_dataset_create_scaled(const double* X, int64_t n, int32_t d, int32_t log
     if (!X || n < 2 || d < 1 || !out) return fail(DPR_ERR_INVALID, "create_scaled: null argument or too few rows");
     if (center_mode < 0 || center_mode > 3 || scale_mode < 0 || scale_mode > 2) return fail(DPR_ERR_INVALID, "create_scaled: unknown mode");
     if ((center_mode == 3 && !centers_inout) || (scale_mode == 2 && !scale_inout)) return fail(DPR_ERR_INVALID, "create_scaled: missing values");
+    static const bool timing = getenv("DPR_TIMING") != nullptr;   // diagnostics: host wall-clock per phase (each closed by a stream synchronize)
+    auto t_prev = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(ctx().stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[dpr] create_scaled: %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     dpr_dataset* ds = nullptr;
     DPR_TRY(dataset_alloc(n, d, &ds));
     std::unique_ptr<dpr_dataset, int (*)(dpr_dataset*)> guard(ds, dpr_dataset_destroy);
@@ -661,8 +716,40 @@ int dpr_dataset_create_scaled(const double* X, int64_t n, int32_t d, int32_t log
     DPR_TRY(raw.alloc(sizeof(double) * total));
     DPR_TRY(part.alloc(sizeof(double) * 3 * B * d));
     DPR_TRY(dvec.alloc(sizeof(double) * 2 * d));
-    // raw doubles to the device through the pinned staging area (as bytes)
+    // The raw values to the device.  Cytometry matrices are usually fp32 values stored as R doubles: host threads narrow each chunk and
+    // check that every value survives the trip unchanged; while that holds, half the bytes cross PCIe and a kernel widens them back
+    // (exactly).  The first value that does not survive sends the whole matrix as doubles instead.
+    bool compact = true;
     {
+        const int64_t chunk = std::min<int64_t>(total, (int64_t)32 << 20);
+        DPR_TRY(upload_stage(chunk));
+        const int threads = host_copy_threads();
+        int b = 0;
+        for (int64_t e0 = 0; e0 < total && compact; e0 += chunk, b ^= 1) {
+            const int64_t cnt = std::min(chunk, total - e0);
+            DPR_CUDA(cudaEventSynchronize(g_stage.done[b]));
+            std::atomic<int> bad{0};
+            float* pin = g_stage.pinned[b];
+            auto work = [&, pin](int t) {
+                const int64_t a0 = cnt * t / threads, a1 = cnt * (t + 1) / threads;
+                if (!narrow_check(X + e0, pin, a0, a1)) bad.store(1);
+            };
+            std::vector<std::thread> pool;
+            for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+            work(0);
+            for (auto& th : pool) th.join();
+            if (bad.load()) {
+                compact = false;
+                break;
+            }
+            DPR_CUDA(cudaMemcpyAsync(g_stage.dev[b], pin, sizeof(float) * cnt, cudaMemcpyHostToDevice, ctx().stream));
+            DPR_CUDA(cudaEventRecord(g_stage.done[b], ctx().stream));
+            DPR_TRY(launch_widen(g_stage.dev[b], raw.as<double>() + e0, cnt, ctx().stream));
+        }
+        if (!compact) DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
+    // raw doubles to the device through the pinned staging area (as bytes)
+    if (!compact) {
         const int64_t chunk = std::min<int64_t>(total, (int64_t)16 << 20);
         DPR_TRY(upload_stage(2 * chunk));
         const int threads = host_copy_threads();
@@ -679,6 +766,7 @@ int dpr_dataset_create_scaled(const double* X, int64_t n, int32_t d, int32_t log
             DPR_CUDA(cudaEventRecord(g_stage.done[b], ctx().stream));
         }
     }
+    mark("allocations + upload");
     std::vector<double> hp((size_t)3 * B * d), colsum(d), colmin(d), colmax(d);
     auto col_stats = [&]() -> int {
         double* p = part.as<double>();
@@ -732,44 +820,76 @@ int dpr_dataset_create_scaled(const double* X, int64_t n, int32_t d, int32_t log
             DPR_TRY(col_stats());
         }
     }
+    mark("column statistics + kurtosis");
     // 2. centres (:49-98)
     std::vector<double> centre(d, 0.0);
     if (center_mode == 1) {   // peak of hist(x, breaks = n / 50 | 10)   (dScaleCoFunction.R:74-88)
         const int n_breaks = n < 500 ? 10 : (int)((double)n / 50.0);
-        DevBuf fb, counts, amax;
-        size_t cap = 0;
-        DPR_TRY(amax.alloc(sizeof(int)));
-        for (int j = 0; j < d; ++j) {
-            std::vector<double> br = r_pretty_breaks(colmin[j], colmax[j], n_breaks);
-            const int nb = (int)br.size() - 1;
-            if (nb < 1) return fail(DPR_ERR_INVALID, "create_scaled: degenerate histogram");
-            std::vector<double> diffs(nb);
-            for (int i = 0; i < nb; ++i) diffs[i] = br[i + 1] - br[i];
-            const double range = colmax[j] - colmin[j];
-            const double diddle = 1e-7 * (nb + 1 > 5 ? median_of(diffs) : (nb + 1 <= 3 ? range : std::max(range, median_of(diffs))));
-            std::vector<double> fz(br);
-            fz[0] -= diddle;
-            for (int i = 1; i <= nb; ++i) fz[i] += diddle;
-            if ((size_t)nb + 1 > cap) {
-                cap = (size_t)nb + 1;
-                if (fb.p) { dev_free(fb.p); fb.p = nullptr; }
-                if (counts.p) { dev_free(counts.p); counts.p = nullptr; }
-                DPR_TRY(fb.alloc(sizeof(double) * cap));
-                DPR_TRY(counts.alloc(sizeof(unsigned int) * cap));
-            }
-            DPR_CUDA(cudaMemcpyAsync(fb.p, fz.data(), sizeof(double) * (nb + 1), cudaMemcpyHostToDevice, ctx().stream));
-            DPR_TRY(launch_hist(raw.as<double>() + (int64_t)j * n, n, fb.as<double>(), nb, br[0], 1.0 / diffs[nb / 2], counts.as<unsigned int>(),
-                                amax.as<int>(), ctx().stream));
-            int best = 0;
-            DPR_CUDA(cudaMemcpyAsync(&best, amax.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
-            DPR_CUDA(cudaStreamSynchronize(ctx().stream));   // also keeps `fz` alive until the copy is done
-            centre[j] = 0.5 * (br[best] + br[best + 1]);
+        // the breaks of every marker on the host (threads: one marker each; only their parameters go to the device, which recomputes a
+        // break where it needs one), ONE histogram launch over all markers, one read of the d winners
+        std::vector<std::vector<double>> br(d);
+        std::vector<HistCol> hc(d);
+        std::vector<int> bad(d, 0);
+        {
+            auto prep = [&](int j) {
+                br[j] = r_pretty_breaks(colmin[j], colmax[j], n_breaks);
+                const int nb = (int)br[j].size() - 1;
+                if (nb < 1) {
+                    bad[j] = 1;
+                    return;
+                }
+                std::vector<double> diffs(nb);
+                for (int i = 0; i < nb; ++i) diffs[i] = br[j][i + 1] - br[j][i];
+                const double range = colmax[j] - colmin[j];
+                HistCol c{};
+                c.col = raw.as<double>() + (int64_t)j * n;
+                c.nb = nb;
+                c.diddle = 1e-7 * (nb + 1 > 5 ? median_of(diffs) : (nb + 1 <= 3 ? range : std::max(range, median_of(diffs))));
+                c.inv_by = 1.0 / diffs[nb / 2];
+                // what r_pretty_breaks built the sequence from (its interior values are l + i * by)
+                c.l = br[j][0];
+                c.u = br[j][nb];
+                c.by = (c.u - c.l) / nb;
+                // (a break that was snapped to exactly zero has |l + i * by| < 1e-14 * by; the device applies the same rule.  The first and
+                // last break are exact ends, never snapped: check that this holds, otherwise the table path would be needed)
+                if (std::fabs(c.l) < 1e-14 * c.by && c.l != 0.0) bad[j] = 2;
+                hc[j] = c;
+            };
+            const int threads = std::max(1, std::min(host_copy_threads(), (int)d));
+            std::vector<std::thread> pool;
+            for (int t = 0; t < threads; ++t)
+                pool.emplace_back([&, t] {
+                    for (int j = t; j < d; j += threads) prep(j);
+                });
+            for (auto& th : pool) th.join();
         }
+        mark("  breaks on the host");
+        size_t tot_bins = 0;
+        for (int j = 0; j < d; ++j) {
+            if (bad[j]) return fail(DPR_ERR_INVALID, "create_scaled: degenerate histogram");
+            tot_bins += (size_t)hc[j].nb;
+        }
+        DevBuf cols_dev, counts, amax;
+        DPR_TRY(cols_dev.alloc(sizeof(HistCol) * d));
+        DPR_TRY(counts.alloc(sizeof(unsigned int) * tot_bins));
+        DPR_TRY(amax.alloc(sizeof(int) * d));
+        size_t at = 0;
+        for (int j = 0; j < d; ++j) {
+            hc[j].counts = counts.as<unsigned int>() + at;
+            at += (size_t)hc[j].nb;
+        }
+        DPR_CUDA(cudaMemcpyAsync(cols_dev.p, hc.data(), sizeof(HistCol) * d, cudaMemcpyHostToDevice, ctx().stream));
+        DPR_TRY(launch_hist_cols(cols_dev.as<HistCol>(), d, n, counts.as<unsigned int>(), tot_bins, amax.as<int>(), ctx().stream));
+        std::vector<int> best(d, 0);
+        DPR_CUDA(cudaMemcpyAsync(best.data(), amax.p, sizeof(int) * d, cudaMemcpyDeviceToHost, ctx().stream));
+        DPR_CUDA(cudaStreamSynchronize(ctx().stream));   // (also keeps hc alive until its copy is done)
+        for (int j = 0; j < d; ++j) centre[j] = 0.5 * (br[j][best[j]] + br[j][best[j] + 1]);
     } else if (center_mode == 2) {
         for (int j = 0; j < d; ++j) centre[j] = colsum[j] / (double)n;
     } else if (center_mode == 3) {
         for (int j = 0; j < d; ++j) centre[j] = centers_inout[j];
     }
+    mark("centres");
     // 3. one sd over all centred values (:102-106)
     double sd = 1.0;
     if (scale_mode == 1) {
@@ -789,6 +909,7 @@ int dpr_dataset_create_scaled(const double* X, int64_t n, int32_t d, int32_t log
     DPR_TRY(launch_scale_to_tiles(raw.as<double>(), n, d, dvec.as<double>(), sd, ds->x, ctx().stream));
     DPR_TRY(dataset_finish(ds));
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    mark("sd + scaling into tiles");
     if (centers_inout && center_mode != 0)
         for (int j = 0; j < d; ++j) centers_inout[j] = centre[j];
     if (scale_inout) *scale_inout = sd;
@@ -843,6 +964,37 @@ int dpr_dataset_gather(dpr_dataset_t ds, const int64_t* rows, int64_t m, dpr_dat
 // ---- allocate_points -------------------------------------------------------------------------------
 int dpr_dataset_allocate_points(dpr_dataset_t ds, const double* mu, int32_t k, int32_t no_zero, int32_t* idx_out) {
     return dpr_dataset_allocate_points_base(ds, mu, k, no_zero, 0, idx_out);
+}
+// depeche()'s final step (R/depeche.R:228-252): allocate, then renumber the clusters 1, 2, ... by decreasing size, ties in the order of
+// the old numbers (`sort(table(.), decreasing = TRUE)`).  The sizes are counted on the device, the new numbers go through a lookup
+// table while the labels are copied out: no pass over the host vector.  order_out (k entries): the old 0-based label of rank 1, 2, ...
+// (-1 beyond the clusters that own cells).
+int dpr_dataset_allocate_points_ranked(dpr_dataset_t ds, const double* mu, int32_t k, int32_t no_zero, int32_t* idx_out, int32_t* order_out) {
+    if (!ds || !mu || k < 1 || !idx_out || !order_out) return fail(DPR_ERR_INVALID, "allocate_points_ranked: null argument or k < 1");
+    Session s;
+    DPR_TRY(single_session(ds, k, 0.0, no_zero, false, s));
+    std::vector<double> rm;
+    colmajor_to_rowmajor(mu, k, ds->d, rm);
+    DPR_TRY(s.set_centres(0, rm.data()));
+    DPR_TRY(s.prepare());
+    DPR_TRY(s.pass(kPassAssign, false));
+    DevBuf cnt;
+    DPR_TRY(cnt.alloc(sizeof(unsigned long long) * k));
+    DPR_TRY(launch_label_counts(ds->labels, ds->n, k, cnt.as<unsigned long long>(), ctx().stream));
+    std::vector<unsigned long long> h((size_t)k);
+    DPR_CUDA(cudaMemcpyAsync(h.data(), cnt.p, sizeof(unsigned long long) * k, cudaMemcpyDeviceToHost, ctx().stream));
+    DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    std::vector<int32_t> order;
+    for (int l = 0; l < k; ++l)
+        if (h[l]) order.push_back(l);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h[a] > h[b]; });
+    std::vector<int32_t> lut((size_t)k, 0);
+    for (int l = 0; l < k; ++l) order_out[l] = -1;
+    for (size_t r = 0; r < order.size(); ++r) {
+        lut[order[r]] = (int32_t)r + 1;
+        order_out[r] = order[r];
+    }
+    return copy_labels_out(ds->labels, ds->n, idx_out, 0, lut.data());
 }
 int dpr_dataset_allocate_points_base(dpr_dataset_t ds, const double* mu, int32_t k, int32_t no_zero, int32_t base, int32_t* idx_out) {
     if (!ds || !mu || k < 1) return fail(DPR_ERR_INVALID, "allocate_points: null argument or k < 1");

@@ -473,6 +473,20 @@ __global__ void label_presence_kernel(const int32_t* labels, int64_t n, int kk, 
     }
 }
 
+// cluster sizes: counts[l] = number of cells with label l (0 <= l < kk; kk small: per-CTA counts in shared memory first)
+__global__ void label_counts_kernel(const int32_t* __restrict__ labels, int64_t n, int kk, unsigned long long* counts) {
+    extern __shared__ unsigned int s_cnt[];
+    for (int i = threadIdx.x; i < kk; i += blockDim.x) s_cnt[i] = 0u;
+    __syncthreads();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = labels[i];
+        if (l >= 0 && l < kk) atomicAdd(&s_cnt[l], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kk; i += blockDim.x)
+        if (s_cnt[i]) atomicAdd(&counts[i], (unsigned long long)s_cnt[i]);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // synthetic cells (bench): group g = Philox % G, x = centre[g][j] + N(0,1)  (generateSparseData shape,
 // R/simulateData.R:47-80, generalised), then / global sd (depecheLogCenterSd.R:102-106) by scale_kernel.
@@ -662,6 +676,13 @@ int launch_ari_from_tables(int n_pairs, int64_t n, int kk, const unsigned long l
 }
 int launch_label_presence(const int32_t* labels, int64_t n, int kk, int32_t* present, int32_t* bad, cudaStream_t st) {
     label_presence_kernel<<<blocks_for(n), 256, 0, st>>>(labels, n, kk, present, bad);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_label_counts(const int32_t* labels, int64_t n, int kk, unsigned long long* counts, cudaStream_t st) {
+    DPR_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * kk, st));
+    label_counts_kernel<<<std::min(blocks_for(n), 148 * 8), 256, sizeof(unsigned int) * kk, st>>>(labels, n, kk, counts);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;

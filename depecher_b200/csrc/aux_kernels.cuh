@@ -45,6 +45,7 @@ int launch_ari(const AriPair* d_pairs, int n_pairs, int64_t n_max, int kk, int m
                unsigned int* d_stab, int32_t* d_bad, double* d_out, cudaStream_t st);
 // exact ARI of n_pairs contingency tables (kk x kk, u64) that were each filled from the same n cells
 int launch_ari_from_tables(int n_pairs, int64_t n, int kk, const unsigned long long* d_tables, double* d_out, cudaStream_t st);
+int launch_label_counts(const int32_t* labels, int64_t n, int kk, unsigned long long* counts, cudaStream_t st);   // counts[l] = cells with label l
 int launch_label_presence(const int32_t* labels, int64_t n, int kk, int32_t* present, int32_t* bad, cudaStream_t st);
 int launch_synth(float* x, int64_t n, int d, const float* centres, int groups, uint64_t seed, int64_t row0, double* sum, double* sumsq,
                  cudaStream_t st);

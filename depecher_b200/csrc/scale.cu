@@ -7,8 +7,9 @@
 //   3. division by ONE standard deviation taken over all centred values (sd(as.matrix(.)), n-1 denominator);
 // and writes the result as the resident fp32 tile-major dataset.  All statistics are fp64 with fixed-order reductions;
 // (x - c)/sd is evaluated in fp64 and rounded to fp32 once, exactly like R's doubles handed to the fp32 upload.
-// The histogram breakpoints come from the host (R's pretty(), api side) and are searched with the fuzz R applies
-// (hist.default: breaks + 1e-7 * median(diff(breaks)), right-closed bins, lowest value included).
+// The histogram breakpoints are R's pretty() sequence, found on the host (api side); the device recomputes a break from the
+// sequence's parameters where it needs one and applies the fuzz R applies (hist.default: breaks + 1e-7 * median(diff(breaks)),
+// right-closed bins, lowest value included).
 #include "scale.cuh"
 
 namespace dpr {
@@ -92,42 +93,6 @@ __global__ void log2_kernel(double* raw, int64_t n, int d, const double* __restr
     }
 }
 
-// hist.default + C_BinCount for one column: fb = fuzzy breaks (nb+1 values), counts[nb]
-__global__ void hist_kernel(const double* __restrict__ col, int64_t n, const double* __restrict__ fb, int nb, double lo, double inv_by,
-                            unsigned int* counts) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double x = col[i];
-        if (!(fb[0] <= x && x <= fb[nb])) continue;        // outside the (fuzzy) range: not counted, like BinCount
-        int b = (int)((x - lo) * inv_by);
-        b = b < 0 ? 0 : (b > nb - 1 ? nb - 1 : b);
-        while (b < nb - 1 && x > fb[b + 1]) ++b;            // right-closed bins: fb[b] < x <= fb[b+1]
-        while (b > 0 && !(x > fb[b])) --b;
-        atomicAdd(&counts[b], 1u);                          // integer counts: order-independent
-    }
-}
-__global__ void argmax_first_kernel(const unsigned int* __restrict__ counts, int nb, int* out) {
-    __shared__ unsigned int sv[256];
-    __shared__ int si[256];
-    unsigned int bv = 0;
-    int bi = 0x7fffffff;
-    for (int i = threadIdx.x; i < nb; i += blockDim.x)
-        if (counts[i] > bv || (counts[i] == bv && i < bi)) {
-            bv = counts[i];
-            bi = i;
-        }
-    sv[threadIdx.x] = bv;
-    si[threadIdx.x] = bi;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int t = 1; t < (int)blockDim.x; ++t)
-            if (sv[t] > bv || (sv[t] == bv && si[t] < bi)) {
-                bv = sv[t];
-                bi = si[t];
-            }
-        *out = bi;   // match(max(counts), counts): first maximum
-    }
-}
-
 // (x - c_j) / sd in fp64 -> fp32, into the tile-major resident layout
 __global__ void scale_to_tiles_kernel(const double* __restrict__ raw, int64_t n, int d, const double* __restrict__ centre, double sd,
                                       float* __restrict__ out) {
@@ -140,6 +105,16 @@ __global__ void scale_to_tiles_kernel(const double* __restrict__ raw, int64_t n,
 
 static inline int grid_for(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(148 * 8, (n + 255) / 256)); }
 
+// fp32 values that are the exact images of the caller's doubles (checked on the host) back to doubles
+__global__ void widen_kernel(const float* __restrict__ src, double* __restrict__ dst, int64_t count) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) dst[i] = (double)src[i];
+}
+int launch_widen(const float* src, double* dst, int64_t count, cudaStream_t st) {
+    widen_kernel<<<(int)std::min<int64_t>((count + 255) / 256, 148 * 16), 256, 0, st>>>(src, dst, count);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
 int launch_col_sum_minmax(const double* raw, int64_t n, int d, double* psum, double* pmin, double* pmax, cudaStream_t st) {
     col_sum_minmax_kernel<<<dim3(kStatBlocks, d), 256, 0, st>>>(raw, n, psum, pmin, pmax);
     count_launch();
@@ -158,11 +133,59 @@ int launch_log2(double* raw, int64_t n, int d, const double* colmin, int per_col
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
 }
-int launch_hist(const double* col, int64_t n, const double* fb, int nb, double lo, double inv_by, unsigned int* counts, int* argmax_out,
-                cudaStream_t st) {
-    DPR_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned int) * nb, st));
-    hist_kernel<<<grid_for(n), 256, 0, st>>>(col, n, fb, nb, lo, inv_by, counts);
-    argmax_first_kernel<<<1, 256, 0, st>>>(counts, nb, argmax_out);
+// hist.default + C_BinCount (right-closed bins, lowest value included, hist.default's fuzz) for every marker
+__device__ __forceinline__ double hist_fuzzy_break(const HistCol& c, int i) {
+    double v = i == 0 ? c.l : (i == c.nb ? c.u : __dadd_rn(c.l, __dmul_rn((double)i, c.by)));   // (separate multiply and add: what the host computes)
+    if (fabs(v) < 1e-14 * c.by) v = 0.0;
+    return i == 0 ? v - c.diddle : v + c.diddle;
+}
+__global__ void hist_cols_kernel(const HistCol* __restrict__ cols, int64_t n) {
+    const HistCol c = cols[blockIdx.y];
+    const double f0 = hist_fuzzy_break(c, 0), f1 = hist_fuzzy_break(c, c.nb);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = c.col[i];
+        if (!(f0 <= x && x <= f1)) continue;                 // outside the (fuzzy) range: not counted, like BinCount
+        int b = (int)((x - c.l) * c.inv_by);
+        b = b < 0 ? 0 : (b > c.nb - 1 ? c.nb - 1 : b);
+        while (b < c.nb - 1 && x > hist_fuzzy_break(c, b + 1)) ++b;   // right-closed bins: fb[b] < x <= fb[b+1]
+        while (b > 0 && !(x > hist_fuzzy_break(c, b))) --b;
+        atomicAdd(&c.counts[b], 1u);                           // integer counts: order-independent
+    }
+}
+__global__ void argmax_cols_kernel(const HistCol* __restrict__ cols, int* out) {   // match(max(counts), counts): first maximum; one CTA per marker
+    const HistCol c = cols[blockIdx.x];
+    __shared__ unsigned int sv[1024];
+    __shared__ int si[1024];
+    unsigned int bv = 0;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < c.nb; i += blockDim.x) {
+        const unsigned int v = c.counts[i];
+        if (v > bv || (v == bv && i < bi)) {
+            bv = v;
+            bi = i;
+        }
+    }
+    sv[threadIdx.x] = bv;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            const unsigned int ov = sv[threadIdx.x + o];
+            const int oi = si[threadIdx.x + o];
+            if (ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) {
+                sv[threadIdx.x] = ov;
+                si[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = si[0];
+}
+int launch_hist_cols(const HistCol* d_cols, int d, int64_t n, unsigned int* counts_all, size_t counts_total, int* argmax_out, cudaStream_t st) {
+    DPR_CUDA(cudaMemsetAsync(counts_all, 0, sizeof(unsigned int) * counts_total, st));
+    const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((148 * 16 + d - 1) / d, (n + 255) / 256));
+    hist_cols_kernel<<<dim3(gx, d), 256, 0, st>>>(d_cols, n);
+    argmax_cols_kernel<<<d, 1024, 0, st>>>(d_cols, argmax_out);
     count_launch(2);
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;

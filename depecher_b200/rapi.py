@@ -423,6 +423,7 @@ def depeche(inDataFrame, samplingSubset=None, penalties=None, sampleSize="defaul
     if nCores == "default":
         nCores = default_ncores()                                                               # :169-174
     use_ds = hasattr(eng, "dataset")
+    ranked = None
     ds_used = ds_scaled if device_scaled else (eng.dataset(used) if use_ds else used)           # resident for the whole search (SURVEY f-2)
     try:
         opt = depechePenaltyOpt(ds_used, k=k, maxIter=maxIter, sampleSize=sampleSize, penalties=penalties, createOutput=createOutput,
@@ -451,14 +452,25 @@ def depeche(inDataFrame, samplingSubset=None, penalties=None, sampleSize="defaul
             full_cc = np.zeros((reduced.shape[0], X.shape[1]))
             full_cc[:, cols] = reduced
             model_cc = full_cc if ds_all is ds_used else reduced
-            clusterVector = dAllocate(ds_all, {"clusterCenters": model_cc, "logCenterSd": False}, engine=eng)   # :228-232
+            if hasattr(eng, "allocate_points_ranked") and hasattr(ds_all, "handle"):
+                # allocation (:228-232) and renumbering by size (:236-252) in one call: sizes counted on the device, the new numbers
+                # applied while the labels are copied out (no pass over a host vector with one entry per cell)
+                rows_kept, cols_kept = _reduce_centres(model_cc)
+                cc = model_cc[rows_kept].copy()
+                drop = np.ones(cc.shape[1], bool)
+                drop[cols_kept] = False
+                cc[:, drop] = 0.0                                                               # (as dAllocate does for a resident matrix)
+                newVec, order0 = eng.allocate_points_ranked(ds_all, cc, 1)
+                ranked = (newVec, order0 + 1, {int(l) + 1: i for i, l in enumerate(order0, start=1)})
+            else:
+                clusterVector = dAllocate(ds_all, {"clusterCenters": model_cc, "logCenterSd": False}, engine=eng)   # :228-232
             if use_ds and ds_all is not ds_used:
                 ds_all.close()
     finally:
         if use_ds:
             ds_used.close()
     # clusters renumbered by size (:236-252)
-    newVec, order, rank_of_label = _renumber_by_size(clusterVector, int(reduced.shape[0]))
+    newVec, order, rank_of_label = ranked if ranked is not None else _renumber_by_size(clusterVector, int(reduced.shape[0]))
     sortedLabels = np.sort(order)
     if len(sortedLabels) == reduced.shape[0]:
         reduced = reduced[np.argsort([rank_of_label[l] for l in sortedLabels])]

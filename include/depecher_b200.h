@@ -124,6 +124,10 @@ int dpr_dataset_allocate_points(dpr_dataset_t ds, const double* mu, int32_t k, i
  * (R/dAllocate.R:127-134) without another pass over a vector with one entry per cell */
 int dpr_dataset_allocate_points_base(dpr_dataset_t ds, const double* mu, int32_t k, int32_t no_zero, int32_t base,
                                      int32_t* idx_out /* host, nullable */);
+/* depeche()'s final step (R/depeche.R:228-252): allocate and renumber the clusters 1, 2, ... by decreasing size (ties in the order
+ * of the old numbers).  order_out[k]: the old 0-based label that became 1, 2, ...; -1 beyond the clusters that own cells. */
+int dpr_dataset_allocate_points_ranked(dpr_dataset_t ds, const double* mu, int32_t k, int32_t no_zero,
+                                       int32_t* idx_out /* host */, int32_t* order_out /* host, k */);
 int dpr_dataset_sparse_k_means(dpr_dataset_t ds, uint32_t k, double reg, int32_t no_zero, uint64_t seed,
                                int32_t* idx_out /* nullable */, double* centers_out, double* norm_out,
                                int32_t* n_iter_out);

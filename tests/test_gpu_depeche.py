@@ -92,6 +92,25 @@ def test_depeche_full_length_sampling_subset_keeps_row_order(engine):
     assert (table.max(axis=1) == table.sum(axis=1)).all()
 
 
+def test_ranked_allocation_equals_allocation_then_renumbering(engine):
+    """dpr_dataset_allocate_points_ranked (allocation + R/depeche.R:236-252 in one call) against dAllocate followed by the host renumbering,
+    on sizes on both sides of the chunked copy-out, with equal-sized clusters (ties keep the order of the old numbers) and an empty one"""
+    from depecher_b200.rapi import _renumber_by_size
+    rng = np.random.default_rng(11)
+    for n in (3000, 700_000):
+        cent = rng.normal(size=(7, 9)) * 3
+        lab = np.repeat(np.arange(6), n // 6)            # six clusters of the same size: all ties
+        lab[: n // 12] = 3                               # ... then one larger, one smaller
+        X = cent[lab] + 0.05 * rng.normal(size=(len(lab), 9))
+        mu = np.vstack([cent, np.full((1, 9), 100.0)])   # the last centre owns nothing
+        ds = engine.dataset(X)
+        got, order = engine.allocate_points_ranked(ds, mu, 1)
+        plain = engine.allocate_points(ds, mu, 1, base=1)["i"]
+        ds.close()
+        want, worder, _ = _renumber_by_size(plain, mu.shape[0])
+        assert np.array_equal(got, want) and np.array_equal(order + 1, worder)
+
+
 def test_device_prescaling_matches_host(engine, testdata):
     """depecheLogCenterSd on the device (dpr_dataset_create_scaled) against the numpy restatement: same peak centres,
     same sd, scaled cells equal up to the last fp32 bit; also the mean / given-centre / log2 paths."""
@@ -105,6 +124,23 @@ def test_device_prescaling_matches_host(engine, testdata):
     w32 = want.astype(np.float32).astype(np.float64)
     assert np.max(np.abs(got - w32)) <= 2.5e-7 * np.max(np.abs(w32))
     assert (got == w32).mean() > 0.999
+    # a matrix whose doubles are all fp32 values crosses PCIe as floats and is widened on the device (exactly): same result
+    Xf = X.astype(np.float32).astype(np.float64)
+    want, winfo = rapi.depecheLogCenterSd(Xf)
+    ds, info = engine.dataset_scaled(Xf)
+    got = engine.read(ds, 0, len(Xf))
+    ds.close()
+    assert np.allclose(info[1], winfo[1], rtol=0, atol=1e-12) and abs(info[2] - winfo[2]) <= 1e-12 * winfo[2]
+    w32 = want.astype(np.float32).astype(np.float64)
+    assert np.max(np.abs(got - w32)) <= 2.5e-7 * np.max(np.abs(w32)) and (got == w32).mean() > 0.999
+    Xm = Xf.copy()
+    Xm[12345, 3] += 1e-9          # one value that is not an fp32 value, late in the matrix: the upload starts over with doubles
+    want, winfo = rapi.depecheLogCenterSd(Xm)
+    ds, info = engine.dataset_scaled(Xm)
+    got = engine.read(ds, 0, len(Xm))
+    ds.close()
+    assert np.allclose(info[1], winfo[1], rtol=0, atol=1e-12) and abs(info[2] - winfo[2]) <= 1e-12 * winfo[2]
+    assert np.allclose(got, want, rtol=3e-7, atol=1e-7)
     for center in ("mean", False, list(np.arange(14.0))):
         want, winfo = rapi.depecheLogCenterSd(X, True, center, True)
         ds, info = engine.dataset_scaled(X, True, center, True)

@@ -127,14 +127,16 @@ def test_find_centers_from_same_trajectory(engine, oracle, n, d, k, pen):
 
 
 def test_kmeanspp_seeding_matches_oracle(engine, oracle):
+    """identical rows and centres, from a fit of two 256-cell blocks to one of 274 (several block sums per scanning thread)"""
     rng = np.random.default_rng(3)
-    X = blobs(rng, 7000, 14, 8)
-    oracle.set_rng(RNG_PHILOX, 77)
-    for fit in (0, 5):
-        want_mu, want_rows = oracle.initialize_mu(X, 30, fit_id=fit)
-        got_mu, got_rows = engine.initialize_mu(X, 30, seed=77, fit_id=fit)
-        assert np.array_equal(got_rows, want_rows)
-        assert np.array_equal(got_mu, want_mu)
+    for n, d, k in ((7000, 14, 30), (300, 5, 12), (65536, 9, 20), (70000, 14, 30)):
+        X = blobs(rng, n, d, 8)
+        oracle.set_rng(RNG_PHILOX, 77)
+        for fit in (0, 5):
+            want_mu, want_rows = oracle.initialize_mu(X, k, fit_id=fit)
+            got_mu, got_rows = engine.initialize_mu(X, k, seed=77, fit_id=fit)
+            assert np.array_equal(got_rows, want_rows), (n, d, k, fit)
+            assert np.array_equal(got_mu, want_mu)
 
 
 def test_bootstrap_rows_match_oracle(engine, oracle):

@@ -40,3 +40,11 @@ for rep in range(3):
     eng.synchronize()
     print(f"dataset_scaled (upload of doubles + device pre-scaling): {time.perf_counter()-t0:.4f} s", flush=True)
     hs.close()
+h = eng.dataset(Xh)
+eng.synchronize()
+for want in (True, False, True, False):
+    t0 = time.perf_counter()
+    res = eng.sparse_k_means(h, k, reg, True, seed_off_set=1, want_labels=want)
+    eng.synchronize()
+    print(f"sparse_k_means on the resident matrix (labels to the host: {want}): {time.perf_counter()-t0:.4f} s, {res['n_iter']} iterations", flush=True)
+h.close()

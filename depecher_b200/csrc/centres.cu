@@ -314,6 +314,63 @@ __global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_s
 }
 
 // ---------------------------------------------------------------------------------------------------
+// reduce + finalize in one launch for batches of MANY problems (the bootstrap fits of a penalty search: 220 problems of 10 000 cells, each
+// touched by one to three CTAs of the pass): one CTA per problem adds the (CTA, problem) tables of those CTAs in ascending order into its
+// shared memory and carries on as finalize_kernel does.  (The two-kernel path spends a launch of 8-16 us per iteration on
+// reduce_partials_kernel, whose 16 segment tables per problem are almost all empty for such batches.)
+// n_active: two counters, as in reduce_finalize_kernel below.
+// ---------------------------------------------------------------------------------------------------
+__global__ void finalize_direct_kernel(Problem* problems, const int32_t* cta_tile_start, int grid_ctas, const double* cta_tables, int k_max, int iter,
+                                       int max_iter, int table_cap, int allow_delta, int32_t* n_active2, int mu_in_smem) {
+    const int p = blockIdx.x;
+    if (p == 0 && threadIdx.x == 0) n_active2[(iter + 1) & 1] = 0;
+    const Problem pr = problems[p];
+    if (pr.done) return;
+    extern __shared__ double s_dyn[];
+    const int64_t entries = (int64_t)k_max * pr.d + k_max + 1;
+    double* s_mu = s_dyn;
+    double* s_part = s_dyn + (mu_in_smem ? (size_t)k_max * pr.d : 0);
+    const int t0 = pr.first_tile, t1 = pr.first_tile + pr.n_tiles;
+    // the CTAs of the pass whose tile range touches the problem are consecutive: [ca, cb).  Ranges are sorted: the first CTA whose
+    // range ends beyond t0, the first one whose range starts at or beyond t1 (binary searches by one thread: a few dependent loads)
+    __shared__ int s_ca, s_cb;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = grid_ctas;
+        while (lo < hi) {   // first c with cta_tile_start[c + 1] > t0
+            const int mid = (lo + hi) >> 1;
+            if (cta_tile_start[mid + 1] > t0) hi = mid; else lo = mid + 1;
+        }
+        s_ca = lo;
+        hi = grid_ctas;
+        while (lo < hi) {   // first c >= ca with cta_tile_start[c] >= t1
+            const int mid = (lo + hi) >> 1;
+            if (cta_tile_start[mid] >= t1) hi = mid; else lo = mid + 1;
+        }
+        s_cb = lo;
+    }
+    __syncthreads();
+    const int ca = s_ca, cb = s_cb;
+    for (int64_t e = threadIdx.x; e < entries; e += blockDim.x) {
+        double acc = 0.0;
+        for (int c = ca; c < cb; c += 8) {   // 8 loads in flight, then the fixed-order sum
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int cc = c + q;
+                bool use = cc < cb;
+                if (use) use = cta_tile_start[cc] < cta_tile_start[cc + 1];   // (a CTA without tiles wrote nothing)
+                v[q] = use ? __ldcg(cta_tables + (size_t)(cc + p) * entries + e) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc += v[q];
+        }
+        s_part[e] = acc;
+    }
+    __syncthreads();
+    finalize_body(problems, p, pr, s_part, 1, k_max, iter, max_iter, table_cap, allow_delta, n_active2 + (iter & 1), mu_in_smem, s_mu);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // reduce + finalize in one launch (single GPU: nothing to exchange between the two).  A cluster of kFuseCtas CTAs per problem:
 // CTA r adds up the r-th eighth of the (CTA, problem) tables the pass wrote, in ascending CTA order, into its shared memory;
 // after the cluster barrier CTA 0 adds the eight partial tables in rank order through distributed shared memory and carries on
@@ -550,6 +607,22 @@ int launch_reduce_finalize(Problem* d_problems, int n_problems, const int32_t* c
     }
     dim3 g(kFuseCtas, n_problems);
     reduce_finalize_kernel<<<g, 512, smem, st>>>(d_problems, cta_tile_start, grid_ctas, cta_tables, k_max, iter, max_iter, table_cap, allow_delta, n_active2, mu_in_smem, px);
+    count_launch();
+    DPR_CUDA(cudaGetLastError());
+    return DPR_OK;
+}
+int launch_finalize_direct(Problem* d_problems, int n_problems, const int32_t* cta_tile_start, int grid_ctas, const double* cta_tables, int k_max, int d,
+                           int iter, int max_iter, int table_cap, int allow_delta, int32_t* n_active2, cudaStream_t st) {
+    const size_t mu_bytes = (size_t)k_max * d * sizeof(double);
+    const int mu_in_smem = mu_bytes <= 64 * 1024;
+    const size_t smem = (mu_in_smem ? mu_bytes : 0) + ((size_t)k_max * d + k_max + 1) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        DPR_CUDA(cudaFuncSetAttribute(finalize_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = true;
+    }
+    finalize_direct_kernel<<<n_problems, 512, smem, st>>>(d_problems, cta_tile_start, grid_ctas, cta_tables, k_max, iter, max_iter, table_cap, allow_delta,
+                                                          n_active2, mu_in_smem);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;

@@ -224,6 +224,12 @@ int Session::reduce_and_finalize(int iter, int max_iter) {
         return launch_reduce_finalize(d_problems, n_problems(), d_cta_start_, grid, cta_tables_, k_max_, d_, iter, max_iter, plan.table_floats_cap,
                                       allow_delta ? 1 : 0, d_n_active_, exchanges(), ctx().stream);
     }
+    static const bool two_kernels = getenv("DPR_TWO_KERNEL_FINALIZE") != nullptr;   // A/B aid
+    if (!two_kernels && !exchanges() && reduce_finalize_fits(k_max_, d_)) {   // many problems, one GPU: one CTA per problem reduces and finalizes
+        last_active_slot_ = iter & 1;
+        return launch_finalize_direct(d_problems, n_problems(), d_cta_start_, grid, cta_tables_, k_max_, d_, iter, max_iter, plan.table_floats_cap,
+                                      allow_delta ? 1 : 0, d_n_active_, ctx().stream);
+    }
     last_active_slot_ = 0;
     DPR_TRY(launch_reduce_partials(d_problems, n_problems(), d_cta_start_, grid, k_max_, d_, cta_tables_, seg, n_seg, d_n_active_, ctx().stream));
     if (exchanges()) DPR_TRY(comm_allreduce_sum_f64(seg, (size_t)n_problems() * n_seg * seg_entries));

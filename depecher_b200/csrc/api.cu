@@ -502,6 +502,15 @@ static int find_centers_dev(dpr_dataset* ds, const double* init_mu_colmajor, uin
     if (!ds) return fail(DPR_ERR_INVALID, "null dataset");
     if (k < 2) return fail(DPR_ERR_INVALID, "k must be >= 2 (initialize_mu writes two rows, Clusterer.cpp:157-162)");
     if (max_iter < 1) return fail(DPR_ERR_INVALID, "max_iter must be >= 1");
+    static const bool timing = getenv("DPR_TIMING") != nullptr;   // diagnostics: host wall-clock per phase (each closed by a stream synchronize)
+    auto t_prev = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(ctx().stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[dpr] find_centers: %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     Session s;
     // several ranks: a fit from GIVEN centres is the row-sharded one (every rank holds a shard and the same initial centres, the tables
     // are summed over the ranks each iteration); a fit that seeds itself (sparse_k_means) draws its centres from the local cells and
@@ -515,15 +524,19 @@ static int find_centers_dev(dpr_dataset* ds, const double* init_mu_colmajor, uin
     } else {
         std::vector<SeedJob> jobs(1);
         jobs[0] = SeedJob{ds->x, ds->n, fit_id, s.h_problems[0].mu, nullptr};
+        mark("session (+ cell-major copy)");
         DPR_TRY(run_seeding(jobs, ds->d, (int)k, seed));
+        mark("k-means++");
     }
     DPR_TRY(s.prepare());
     DPR_TRY(s.zero_labels());
     DPR_TRY(s.lloyd(max_iter));
     DPR_TRY(s.fetch_state());
+    mark("Lloyd loop");
     const Problem& pr = s.h_problems[0];
     if (n_iter_out) *n_iter_out = pr.n_assign;
     DPR_TRY(copy_labels_out(pr.labels, ds->n, idx_out));
+    mark("labels to the host");
     if (centers_out) {
         std::vector<double> rm((size_t)k * ds->d);
         DPR_TRY(s.get_centres(0, rm.data()));
@@ -1056,7 +1069,9 @@ int dpr_dataset_sparse_k_means(dpr_dataset_t ds, uint32_t k, double reg, int32_t
 int dpr_sparse_k_means(const double* X, int64_t n, int32_t d, uint32_t k, double reg, int32_t no_zero, uint64_t seed,
                        int32_t* idx_out, double* centers_out, double* norm_out, int32_t* n_iter_out) {
     dpr_dataset_t ds = nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     DPR_TRY(dpr_dataset_create(X, n, d, &ds));
+    if (getenv("DPR_TIMING")) fprintf(stderr, "[dpr] sparse_k_means: upload %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     const int rc = dpr_dataset_sparse_k_means(ds, k, reg, no_zero, seed, idx_out, centers_out, norm_out, n_iter_out);
     dpr_dataset_destroy(ds);
     return rc;

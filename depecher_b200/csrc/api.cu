@@ -359,39 +359,69 @@ static int copy_labels_out(const int32_t* d_labels, int64_t n, int32_t* host, in
     if (!host) return DPR_OK;
     if (n >= (1 << 19) && g_stage.cap == 0) DPR_TRY(upload_stage((int64_t)4 << 20));   // (a process that has not uploaded anything yet: the pinned buffers are made here)
     if (n >= (1 << 19) && g_stage.cap > 0) {
-        // the caller's vector is pageable: the driver would stage it at a few GB/s.  DMA into the pinned upload buffers instead
-        // and let host threads copy a piece out while the next one arrives.
-        const int64_t piece = std::min<int64_t>(g_stage.cap, (int64_t)4 << 20);
-        const int threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
-        DPR_CUDA(cudaStreamSynchronize(ctx().stream));
-        int b = 0;
-        int64_t prev0 = -1, prev_cnt = 0;
-        for (int64_t e0 = 0; e0 < n || prev0 >= 0; e0 += piece, b ^= 1) {
-            const int64_t cnt = e0 < n ? std::min(piece, n - e0) : 0;
-            if (cnt > 0) {
-                DPR_CUDA(cudaMemcpyAsync(g_stage.pinned[b], d_labels + e0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ctx().stream));
-                DPR_CUDA(cudaEventRecord(g_stage.done[b], ctx().stream));
+        // The caller's vector is pageable (and usually untouched: every page of it faults on its first write), the driver would stage
+        // the copy at a few GB/s.  The upload pipeline in reverse: the labels arrive by DMA in the ring of pinned buffers, 4 MB at a
+        // time; worker threads started once per call draw pieces of landed chunks from one counter and write them out (with the offset
+        // or the lookup table applied), the calling thread issues a copy whenever a buffer has been emptied.
+        const int64_t chunk = std::min<int64_t>(g_stage.cap, (int64_t)1 << 20);
+        const int64_t nchunks = (n + chunk - 1) / chunk;
+        const int threads = host_copy_threads();
+        const int P = std::max(1, threads);
+        DPR_CUDA(cudaStreamSynchronize(ctx().stream));   // (the labels are final; whatever used the ring before has left it)
+        std::unique_ptr<std::atomic<int>[]> pieces_done(new std::atomic<int>[(size_t)nchunks]);
+        for (int64_t c = 0; c < nchunks; ++c) pieces_done[c].store(0, std::memory_order_relaxed);
+        std::atomic<int64_t> next{0}, landed{0};
+        std::atomic<int> stop{0};
+        auto worker = [&] {
+            for (;;) {
+                const int64_t t = next.fetch_add(1, std::memory_order_relaxed);
+                if (t >= nchunks * P) return;
+                const int64_t c = t / P;
+                const int piece = (int)(t % P);
+                while (landed.load(std::memory_order_acquire) <= c) {
+                    if (stop.load(std::memory_order_relaxed)) return;
+                    std::this_thread::yield();
+                }
+                const int64_t e0 = c * chunk, cnt = std::min(chunk, n - e0);
+                const int64_t a = cnt * piece / P, z = cnt * (piece + 1) / P;
+                const int32_t* src = reinterpret_cast<const int32_t*>(g_stage.pinned[c % kStageBufs]);
+                if (lut)
+                    for (int64_t e = a; e < z; ++e) host[e0 + e] = lut[src[e]];
+                else if (base == 0) std::memcpy(host + e0 + a, src + a, sizeof(int32_t) * (size_t)(z - a));
+                else
+                    for (int64_t e = a; e < z; ++e) host[e0 + e] = src[e] + base;
+                pieces_done[c].fetch_add(1, std::memory_order_release);
             }
-            if (prev0 >= 0) {   // the previous piece has landed in the other buffer: out to the caller
-                DPR_CUDA(cudaEventSynchronize(g_stage.done[b ^ 1]));
-                const int32_t* src = reinterpret_cast<const int32_t*>(g_stage.pinned[b ^ 1]);
-                std::vector<std::thread> pool;
-                auto work = [=](int t) {
-                    const int64_t a = prev_cnt * t / threads, z = prev_cnt * (t + 1) / threads;
-                    if (lut)
-                        for (int64_t e = a; e < z; ++e) host[prev0 + e] = lut[src[e]];
-                    else if (base == 0) std::memcpy(host + prev0 + a, src + a, sizeof(int32_t) * (size_t)(z - a));
-                    else
-                        for (int64_t e = a; e < z; ++e) host[prev0 + e] = src[e] + base;
-                };
-                for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
-                work(0);
-                for (auto& th : pool) th.join();
+        };
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back(worker);
+        int rc = DPR_OK;
+        int64_t issued = 0, arrived = 0, freed = 0;
+        while (arrived < nchunks && rc == DPR_OK) {
+            bool progress = false;
+            while (issued < nchunks && issued < freed + kStageBufs && rc == DPR_OK) {
+                const int bb = (int)(issued % kStageBufs);
+                const int64_t e0 = issued * chunk, cnt = std::min(chunk, n - e0);
+                if (cudaMemcpyAsync(g_stage.pinned[bb], d_labels + e0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, ctx().stream) != cudaSuccess ||
+                    cudaEventRecord(g_stage.done[bb], ctx().stream) != cudaSuccess)
+                    rc = fail(DPR_ERR_CUDA, "labels to the host: copy failed");
+                ++issued;
+                progress = true;
             }
-            prev0 = cnt > 0 ? e0 : -1;
-            prev_cnt = cnt;
+            while (arrived < issued && cudaEventQuery(g_stage.done[arrived % kStageBufs]) == cudaSuccess) {
+                ++arrived;
+                landed.store(arrived, std::memory_order_release);
+                progress = true;
+            }
+            while (freed < arrived && pieces_done[freed].load(std::memory_order_acquire) == P) {
+                ++freed;
+                progress = true;
+            }
+            if (!progress) std::this_thread::yield();
         }
-        return DPR_OK;
+        if (rc != DPR_OK) stop.store(1);
+        for (auto& th : pool) th.join();
+        return rc;
     }
     DPR_CUDA(cudaMemcpyAsync(host, d_labels, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx().stream));
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));

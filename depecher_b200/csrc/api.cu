@@ -485,8 +485,16 @@ static int run_seeding(const std::vector<SeedJob>& jobs, int d, int k, uint64_t 
         bo += (jobs[f].n + kSeedBlock - 1) / kSeedBlock;
     }
     DPR_CUDA(cudaMemcpyAsync(fits.p, h.data(), sizeof(SeedFit) * F, cudaMemcpyHostToDevice, ctx().stream));
+    static const bool timing = getenv("DPR_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0;
+    if (timing) {
+        cudaStreamSynchronize(ctx().stream);
+        t0 = std::chrono::steady_clock::now();
+    }
     DPR_TRY(launch_seeding(fits.as<SeedFit>(), F, n_max, d, k, seed, ctx().stream));
     DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (timing)
+        fprintf(stderr, "[dpr] seeding: %d rounds of %d fits %.2f ms\n", k - 1, F, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     return DPR_OK;
 }
 

@@ -125,51 +125,76 @@ __device__ void seed_pick_body(const SeedFit& f, int d, int c, uint64_t seed);
 // Round c: distances to centre c - 1 (the running minimum, block sums), then — by the CTA of the fit that finishes last (a ticket
 // counter per fit) — the draw of centre c.  One launch per round instead of two: the rounds of a batch of small fits are
 // launch-latency-bound (28 launches fewer per seeding).
+template <int U>   // blocks of 256 cells per trip of a CTA
 __global__ void seed_dist_kernel(const SeedFit* fits, int d, int c /* centre just chosen: c-1 >= 0 */, int first, uint64_t seed) {
     extern __shared__ double s_mu[];
     const SeedFit f = fits[blockIdx.y];
     const int nb = (int)((f.n + kSeedBlock - 1) / kSeedBlock);
     for (int j = threadIdx.x; j < d; j += blockDim.x) s_mu[j] = f.mu[(size_t)(c - 1) * d + j];
     __syncthreads();
-    __shared__ double s_red[kSeedBlock / 32];
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        const int64_t i = (int64_t)b * kSeedBlock + threadIdx.x;
-        double w = 0.0;
-        if (i < f.n) {
-            double s = 0.0;
-            // a cell's markers come four at a time (one 16-byte load per marker group); differences and squares of a group are independent,
-            // only the additions into s form the left-to-right chain of the reference
-            const float4* x4 = reinterpret_cast<const float4*>(f.x + x_index(i, 0, d));
-            int j = 0;
-            for (; j + 4 <= d; j += 4) {
-                const float4 xv = __ldg(x4 + (size_t)(j >> 2) * (kGroupFloats / 4));
-                const double d0 = __dadd_rn(-(double)xv.x, s_mu[j]), d1 = __dadd_rn(-(double)xv.y, s_mu[j + 1]);
-                const double d2 = __dadd_rn(-(double)xv.z, s_mu[j + 2]), d3 = __dadd_rn(-(double)xv.w, s_mu[j + 3]);
-                const double q0 = __dmul_rn(d0, d0), q1 = __dmul_rn(d1, d1), q2 = __dmul_rn(d2, d2), q3 = __dmul_rn(d3, d3);
-                s = __dadd_rn(s, q0);
-                s = __dadd_rn(s, q1);
-                s = __dadd_rn(s, q2);
-                s = __dadd_rn(s, q3);
-            }
-            for (; j < d; ++j) {
-                const double diff = __dadd_rn(-(double)f.x[x_index(i, j, d)], s_mu[j]);
-                s = __dadd_rn(s, __dmul_rn(diff, diff));
-            }
-            if (!first) {
-                const double old = f.w[i];
-                if (!(s < old)) s = old;   // if (temp_dists(j) < dists(j)) dists(j) = temp_dists(j)   (:167-169)
-            }
-            f.w[i] = s;
-            w = s > 0 ? s : 0.0;
+    // U blocks of 256 cells per trip: a thread holds one cell of each, the marker groups of the U cells are requested together and their
+    // sums advance side by side (U independent fp64 chains), and the CTA meets once per U blocks instead of once per block.  Per cell the
+    // operations and their order are unchanged, and a block's sum is still its eight warp sums added in warp order.  (U = 4 for large
+    // matrices: a round over 10M x 40 cells 0.38 -> 0.35 ms; batches of small fits keep U = 1: they need the CTAs more than the overlap.)
+    __shared__ double s_red[U][kSeedBlock / 32];
+    for (int b0 = blockIdx.x * U; b0 < nb; b0 += gridDim.x * U) {
+        int64_t i[U];
+        bool on[U];
+        double s[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            i[u] = (int64_t)(b0 + u) * kSeedBlock + threadIdx.x;
+            on[u] = b0 + u < nb && i[u] < f.n;
+            if (!on[u]) i[u] = 0;   // (loads stay unconditional: cell 0 exists)
+            s[u] = 0.0;
         }
-        // deterministic block sum
-        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = w;
+        double old[U];
+        if (!first) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) old[u] = on[u] ? f.w[i[u]] : 0.0;
+        }
+        // a cell's markers come four at a time (one 16-byte load per marker group); differences and squares of a group are independent,
+        // only the additions into s form the left-to-right chain of the reference
+        int j = 0;
+        for (; j + 4 <= d; j += 4) {
+            float4 xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = __ldg(reinterpret_cast<const float4*>(f.x + x_index(i[u], 0, d)) + (size_t)(j >> 2) * (kGroupFloats / 4));
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double d0 = __dadd_rn(-(double)xv[u].x, s_mu[j]), d1 = __dadd_rn(-(double)xv[u].y, s_mu[j + 1]);
+                const double d2 = __dadd_rn(-(double)xv[u].z, s_mu[j + 2]), d3 = __dadd_rn(-(double)xv[u].w, s_mu[j + 3]);
+                const double q0 = __dmul_rn(d0, d0), q1 = __dmul_rn(d1, d1), q2 = __dmul_rn(d2, d2), q3 = __dmul_rn(d3, d3);
+                s[u] = __dadd_rn(s[u], q0);
+                s[u] = __dadd_rn(s[u], q1);
+                s[u] = __dadd_rn(s[u], q2);
+                s[u] = __dadd_rn(s[u], q3);
+            }
+        }
+        for (; j < d; ++j) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double diff = __dadd_rn(-(double)f.x[x_index(i[u], j, d)], s_mu[j]);
+                s[u] = __dadd_rn(s[u], __dmul_rn(diff, diff));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            double w = 0.0;
+            if (on[u]) {
+                if (!first && !(s[u] < old[u])) s[u] = old[u];   // if (temp_dists(j) < dists(j)) dists(j) = temp_dists(j)   (:167-169)
+                f.w[i[u]] = s[u];
+                w = s[u] > 0 ? s[u] : 0.0;
+            }
+            // deterministic block sum
+            for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+            if ((threadIdx.x & 31) == 0) s_red[u][threadIdx.x >> 5] = w;
+        }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < U && b0 + (int)threadIdx.x < nb) {
             double t = 0.0;
-            for (int q = 0; q < kSeedBlock / 32; ++q) t += s_red[q];
-            f.block_sums[b] = t;
+            for (int q = 0; q < kSeedBlock / 32; ++q) t += s_red[threadIdx.x][q];
+            f.block_sums[b0 + threadIdx.x] = t;
         }
         __syncthreads();
     }
@@ -204,7 +229,13 @@ __device__ void seed_pick_body(const SeedFit& f, int d, int c, uint64_t seed) {
     {
         double t = 0.0;
         const int b0 = threadIdx.x * seg, b1 = min(nb, b0 + seg);
-        for (int b = b0; b < b1; ++b) t += f.block_sums[b];
+        for (int b = b0; b < b1; b += 16) {   // sixteen block sums requested at once, added in ascending order (a missing one adds +0)
+            double v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = b + q < b1 ? __ldcg(f.block_sums + b + q) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) t += v[q];
+        }
         s_seg[threadIdx.x] = t;
     }
     __syncthreads();
@@ -620,9 +651,11 @@ int launch_seeding(SeedFit* d_fits, int n_fits, int64_t n_max, int d, int k, uin
     seed_first_kernel<<<n_fits, 64, 0, st>>>(d_fits, d, seed);
     count_launch();
     const int nb = (int)((n_max + kSeedBlock - 1) / kSeedBlock);
-    const int gx = std::max(1, std::min(nb, (148 * 8 + n_fits - 1) / n_fits));
+    const bool wide = n_max >= (1 << 20);   // four blocks per trip of a CTA
+    const int gx = std::max(1, std::min(wide ? (nb + 3) / 4 : nb, (148 * 8 + n_fits - 1) / n_fits));
     for (int c = 1; c < k; ++c) {
-        seed_dist_kernel<<<dim3(gx, n_fits), kSeedBlock, sizeof(double) * d, st>>>(d_fits, d, c, c == 1, seed);
+        if (wide) seed_dist_kernel<4><<<dim3(gx, n_fits), kSeedBlock, sizeof(double) * d, st>>>(d_fits, d, c, c == 1, seed);
+        else seed_dist_kernel<1><<<dim3(gx, n_fits), kSeedBlock, sizeof(double) * d, st>>>(d_fits, d, c, c == 1, seed);
         count_launch();
     }
     DPR_CUDA(cudaGetLastError());

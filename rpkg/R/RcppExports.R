@@ -30,6 +30,14 @@ dataset_destroy <- function(handle) {
     invisible(.Call('_DepecheR_dataset_destroy', PACKAGE = 'DepecheR', handle))
 }
 
+dataset_create_scaled <- function(X, log2Off, centerMode, centers, scaleMode, scaleValue) {
+    .Call('_DepecheR_dataset_create_scaled', PACKAGE = 'DepecheR', X, log2Off, centerMode, centers, scaleMode, scaleValue)
+}
+
+dataset_allocate_points_ranked <- function(handle, mu, no_zero) {
+    .Call('_DepecheR_dataset_allocate_points_ranked', PACKAGE = 'DepecheR', handle, mu, no_zero)
+}
+
 dataset_gather <- function(handle, rows) {
     .Call('_DepecheR_dataset_gather', PACKAGE = 'DepecheR', handle, rows)
 }

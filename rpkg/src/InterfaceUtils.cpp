@@ -8,6 +8,8 @@
 // to regenerate src/RcppExports.cpp — rpkg/R/RcppExports.R shows the R side it produces):
 //   dataset_create / dataset_destroy / dataset_gather / dataset_allocate_points   the matrix stays in HBM across calls
 //                                                         (external pointer; the finalizer frees the device memory)
+//   dataset_create_scaled            depecheLogCenterSd on the device while uploading (the scaled matrix never exists in R)
+//   dataset_allocate_points_ranked   depeche()'s final dAllocate + renumbering by cluster size in one call
 //   grid_search_each     one set of the penalty search = all former SOCK workers' grid_search calls as one batch
 //   penalty_opt          depechePenaltyOpt's whole adaptive loop in one call (dpr_dataset_penalty_opt)
 //   select_solution      depecheClusterCenterSelection's allocation + all-pairs ARI (dpr_dataset_select_solution)
@@ -180,6 +182,30 @@ SEXP dataset_create(NumericMatrix X) {
     return wrap_dataset(ds);
 }
 
+// depecheLogCenterSd on the device (R/depecheLogCenterSd.R:6-115) + the upload in one call: the scaled matrix never exists in R.
+// centerMode: 0 none, 1 histogram peak (R/dScaleCoFunction.R:74-88), 2 mean, 3 the values in `centers`; scaleMode: 0 none, 1 the sd of all
+// centred values, 2 `scaleValue` (the R wrapper maps depeche()'s center = "default" / "peak" / "mean" / FALSE / numeric and scale = TRUE /
+// FALSE / numeric onto these, R/depeche.R:131-141).  Returns list(handle = <external pointer>, log2Applied, center, scale) — the
+// logCenterSd record depeche() stores for dAllocate (R/dAllocate.R:81-90).
+// [[Rcpp::export]]
+List dataset_create_scaled(NumericMatrix X, const bool log2Off, const int centerMode, NumericVector centers, const int scaleMode,
+                           const double scaleValue) {
+    const int d = X.ncol();
+    if (centerMode == 3 && centers.size() != d) stop("dataset_create_scaled: one centre per column is needed");
+    NumericVector used((long)d);
+    for (int j = 0; j < d; ++j) used[j] = centerMode == 3 ? centers[j] : 0.0;
+    double sd = scaleMode == 2 ? scaleValue : 1.0;
+    int32_t log2_applied = 0;
+    dpr_dataset_t ds = NULL;
+    check(dpr_dataset_create_scaled(REAL(X), X.nrow(), d, log2Off ? 1 : 0, centerMode, REAL(used), scaleMode, &sd, &log2_applied, &ds));
+    List ret;
+    ret["handle"] = wrap_dataset(ds);
+    ret["log2Applied"] = log2_applied != 0;
+    ret["center"] = used;
+    ret["scale"] = sd;
+    return ret;
+}
+
 // [[Rcpp::export]]
 void dataset_destroy(SEXP handle) { dataset_finalizer(handle); }
 
@@ -204,6 +230,26 @@ List dataset_allocate_points(SEXP handle, NumericMatrix mu, const bool no_zero) 
     check(dpr_dataset_allocate_points(ds, REAL(mu), mu.nrow(), no_zero ? 1 : 0, INTEGER(inds)));
     List ret;
     ret["i"] = inds;
+    return ret;
+}
+
+// depeche()'s final step (R/depeche.R:228-252) in one call: dAllocate of the resident matrix and the renumbering of the clusters by
+// decreasing size (sizes counted on the device, the new numbers applied while the labels are copied out).  Returns list(i = the new
+// cluster numbers 1, 2, ..., order = the rows of mu (1-based) in rank order, 0 beyond the clusters that own cells).
+// [[Rcpp::export]]
+List dataset_allocate_points_ranked(SEXP handle, NumericMatrix mu, const bool no_zero) {
+    dpr_dataset_t ds = dataset_of(handle);
+    int64_t n = 0;
+    int32_t d = 0;
+    check(dpr_dataset_shape(ds, &n, &d));
+    if (mu.ncol() != d) stop("dataset_allocate_points_ranked: the dataset and mu differ in the number of columns");
+    IntegerVector inds((long)n);
+    IntegerVector order((long)mu.nrow());   // the rows of mu (1-based) in rank order; 0 beyond the clusters that own cells
+    check(dpr_dataset_allocate_points_ranked(ds, REAL(mu), mu.nrow(), no_zero ? 1 : 0, INTEGER(inds), INTEGER(order)));
+    for (long r = 0; r < order.size(); ++r) order[r] += 1;
+    List ret;
+    ret["i"] = inds;
+    ret["order"] = order;
     return ret;
 }
 

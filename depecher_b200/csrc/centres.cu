@@ -323,6 +323,7 @@ __global__ void finalize_kernel(Problem* problems, const double* seg_in, int n_s
 __global__ void finalize_direct_kernel(Problem* problems, const int32_t* cta_tile_start, int grid_ctas, const double* cta_tables, int k_max, int iter,
                                        int max_iter, int table_cap, int allow_delta, int32_t* n_active2, int mu_in_smem) {
     const int p = blockIdx.x;
+    DPR_GRID_DEPENDENCY();
     if (p == 0 && threadIdx.x == 0) n_active2[(iter + 1) & 1] = 0;
     const Problem pr = problems[p];
     if (pr.done) return;
@@ -383,6 +384,7 @@ __global__ void __cluster_dims__(kFuseCtas, 1, 1) reduce_finalize_kernel(Problem
                                                                         int32_t* n_active2, int mu_in_smem, const PeerExchange px) {
     const int p = blockIdx.y;
     const unsigned r = blockIdx.x;   // rank in the cluster
+    DPR_GRID_DEPENDENCY();
     const Problem pr = problems[p];
     extern __shared__ double s_dyn[];
     const int64_t entries = (int64_t)k_max * pr.d + k_max + 1;
@@ -606,7 +608,8 @@ int launch_reduce_finalize(Problem* d_problems, int n_problems, const int32_t* c
         configured = true;
     }
     dim3 g(kFuseCtas, n_problems);
-    reduce_finalize_kernel<<<g, 512, smem, st>>>(d_problems, cta_tile_start, grid_ctas, cta_tables, k_max, iter, max_iter, table_cap, allow_delta, n_active2, mu_in_smem, px);
+    DPR_CUDA(launch_dependent(reduce_finalize_kernel, g, dim3(512), smem, st, d_problems, cta_tile_start, grid_ctas, cta_tables, k_max, iter, max_iter, table_cap,
+                              allow_delta, n_active2, mu_in_smem, px));
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;
@@ -621,8 +624,8 @@ int launch_finalize_direct(Problem* d_problems, int n_problems, const int32_t* c
         DPR_CUDA(cudaFuncSetAttribute(finalize_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         configured = true;
     }
-    finalize_direct_kernel<<<n_problems, 512, smem, st>>>(d_problems, cta_tile_start, grid_ctas, cta_tables, k_max, iter, max_iter, table_cap, allow_delta,
-                                                          n_active2, mu_in_smem);
+    DPR_CUDA(launch_dependent(finalize_direct_kernel, dim3(n_problems), dim3(512), smem, st, d_problems, cta_tile_start, grid_ctas, cta_tables, k_max, iter, max_iter,
+                              table_cap, allow_delta, n_active2, mu_in_smem));
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;

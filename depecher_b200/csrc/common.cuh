@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <string>
 #include <utility>
 #include <vector>
@@ -129,6 +130,30 @@ int dev_alloc(void** p, size_t bytes);   // stream-ordered, pooled (api.cu)
 void dev_free(void* p);   // picks the device, checks sm_100, creates the stream
 
 inline void count_launch(int n = 1) { ctx().launches += n; }
+
+// Launch with programmatic stream serialization: the kernels of a Lloyd step (pass -> sums of the moved cells -> reduce + finalize -> next
+// pass) each begin with griddepcontrol.launch_dependents + griddepcontrol.wait, so the next kernel's CTAs are placed on the SMs as the
+// previous kernel's CTAs leave them and only wait for its completion (and the visibility of its writes) there: the launch latency between
+// dependent kernels is hidden.  DPR_NO_PDL=1: plain launches (A/B aid).
+inline bool pdl_enabled() {
+    static const bool on = getenv("DPR_NO_PDL") == nullptr;
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define DPR_GRID_DEPENDENCY() asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory")
 
 }  // namespace dpr
 

@@ -112,6 +112,7 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
     constexpr bool kDeltaOnly = MODE == kPassLloydDelta;   // no problem of the launch needs full sums: that code is not in this instance
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    DPR_GRID_DEPENDENCY();   // (everything below reads what the previous kernel of the step wrote)
     const int t_begin = P.cta_tile_start[blockIdx.x], t_end = P.cta_tile_start[blockIdx.x + 1];
     if (t_begin >= t_end) return;
 
@@ -634,6 +635,7 @@ __global__ void __launch_bounds__(512, 1) delta_sums_kernel(const PassParams P, 
     double* tabs = reinterpret_cast<double*>(dsm);
     __shared__ uint32_t cursor[4 * kTcMaxGroups];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    DPR_GRID_DEPENDENCY();
     const int t_begin = P.cta_tile_start[blockIdx.x], t_end = P.cta_tile_start[blockIdx.x + 1];
     if (t_begin >= t_end) return;
     if (threadIdx.x < 4 * kTcMaxGroups) cursor[threadIdx.x] = 0;
@@ -837,8 +839,8 @@ int launch_tc_pass(const TcPlan& plan, const PassParams& P, int grid, cudaStream
     if (plan.groups == G) {                                                                                                       \
         if (P.mode == kPassAssign && P.bundles) tc_pass_kernel<kPassAssign, G, true><<<grid, threads, plan.smem_bytes, stream>>>(P, plan); \
         else if (P.mode == kPassAssign) tc_pass_kernel<kPassAssign, G, false><<<grid, threads, plan.smem_bytes, stream>>>(P, plan);       \
-        else if (P.all_delta) tc_pass_kernel<kPassLloydDelta, G, false><<<grid, threads, plan.smem_bytes, stream>>>(P, plan);                \
-        else tc_pass_kernel<kPassLloyd, G, false><<<grid, threads, plan.smem_bytes, stream>>>(P, plan);                               \
+        else if (P.all_delta) DPR_CUDA(launch_dependent(tc_pass_kernel<kPassLloydDelta, G, false>, dim3(grid), dim3(threads), plan.smem_bytes, stream, P, plan)); \
+        else DPR_CUDA(launch_dependent(tc_pass_kernel<kPassLloyd, G, false>, dim3(grid), dim3(threads), plan.smem_bytes, stream, P, plan));   \
     }
     DPR_TC_LAUNCH(2) DPR_TC_LAUNCH(3) DPR_TC_LAUNCH(4)
 #undef DPR_TC_LAUNCH
@@ -862,7 +864,7 @@ int launch_delta_sums(const TcPlan& plan, const PassParams& P, int grid, cudaStr
     const size_t budget = (size_t)kSmemBudget - 1024;
     int A = (int)std::min<size_t>((size_t)W, budget / table_bytes);
     if (A < 1) return fail(DPR_ERR_INVALID, "delta sums: one k x d table does not fit in shared memory");
-    delta_sums_kernel<<<grid, 512, (size_t)A * table_bytes, stream>>>(P, plan.d, W, A, (int)(table_bytes / 8));
+    DPR_CUDA(launch_dependent(delta_sums_kernel, dim3(grid), dim3(512), (size_t)A * table_bytes, stream, P, plan.d, W, A, (int)(table_bytes / 8)));
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;

@@ -112,8 +112,10 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
     constexpr bool kDeltaOnly = MODE == kPassLloydDelta;   // no problem of the launch needs full sums: that code is not in this instance
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    DPR_GRID_DEPENDENCY();   // (everything below reads what the previous kernel of the step wrote)
-    const int t_begin = P.cta_tile_start[blockIdx.x], t_end = P.cta_tile_start[blockIdx.x + 1];
+    asm volatile("griddepcontrol.launch_dependents;");
+    // (the tile ranges are not written by the kernels of a step — only by the host and by partition_kernel, a plain launch that has completed
+    // before this grid is placed: safe to read before the wait, through L2)
+    const int t_begin = __ldcg(P.cta_tile_start + blockIdx.x), t_end = __ldcg(P.cta_tile_start + blockIdx.x + 1);
     if (t_begin >= t_end) return;
 
     const int S = T.stages;
@@ -164,6 +166,9 @@ __global__ void __launch_bounds__((4 * kTcGroups + 2) * 32, 1) tc_pass_kernel(co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_word;
+    // the set-up above (barriers, tensor-memory allocation, zero padding) runs while the previous kernel of the step is still finishing
+    // on other SMs; everything below reads what it wrote
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     int p = 0;
     {

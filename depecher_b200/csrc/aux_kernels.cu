@@ -128,6 +128,7 @@ __device__ void seed_pick_body(const SeedFit& f, int d, int c, uint64_t seed);
 template <int U>   // blocks of 256 cells per trip of a CTA
 __global__ void seed_dist_kernel(const SeedFit* fits, int d, int c /* centre just chosen: c-1 >= 0 */, int first, uint64_t seed) {
     extern __shared__ double s_mu[];
+    DPR_GRID_DEPENDENCY();   // (a round reads the centre the previous round's launch drew: the rounds are launched as dependent kernels)
     const SeedFit f = fits[blockIdx.y];
     const int nb = (int)((f.n + kSeedBlock - 1) / kSeedBlock);
     for (int j = threadIdx.x; j < d; j += blockDim.x) s_mu[j] = f.mu[(size_t)(c - 1) * d + j];
@@ -654,8 +655,9 @@ int launch_seeding(SeedFit* d_fits, int n_fits, int64_t n_max, int d, int k, uin
     const bool wide = n_max >= (1 << 20);   // four blocks per trip of a CTA
     const int gx = std::max(1, std::min(wide ? (nb + 3) / 4 : nb, (148 * 8 + n_fits - 1) / n_fits));
     for (int c = 1; c < k; ++c) {
-        if (wide) seed_dist_kernel<4><<<dim3(gx, n_fits), kSeedBlock, sizeof(double) * d, st>>>(d_fits, d, c, c == 1, seed);
-        else seed_dist_kernel<1><<<dim3(gx, n_fits), kSeedBlock, sizeof(double) * d, st>>>(d_fits, d, c, c == 1, seed);
+        const SeedFit* cf = d_fits;
+        if (wide) DPR_CUDA(launch_dependent(seed_dist_kernel<4>, dim3(gx, n_fits), dim3(kSeedBlock), sizeof(double) * d, st, cf, d, c, (int)(c == 1), seed));
+        else DPR_CUDA(launch_dependent(seed_dist_kernel<1>, dim3(gx, n_fits), dim3(kSeedBlock), sizeof(double) * d, st, cf, d, c, (int)(c == 1), seed));
         count_launch();
     }
     DPR_CUDA(cudaGetLastError());

@@ -27,8 +27,12 @@ __device__ void build_centre_table(const Problem& pr, const double* __restrict__
     __shared__ double s_cc[kMaxRows];
     __shared__ unsigned char s_zero[kMaxRows];
     __shared__ int s_nact, s_bad;
+    // The header is assembled in shared memory and copied to the problem's header in global memory once, at the end: the phases below
+    // read what thread 0 has just written (chunk sizes and offsets, cc_max), and through global memory every such read was an L2 round trip
+    __shared__ CentreHeader s_h;
     const int k = pr.k, d = pr.d;
-    CentreHeader* h = pr.hdr;
+    CentreHeader* h = &s_h;
+    for (int i = threadIdx.x; i < (int)(sizeof(CentreHeader) / 4); i += blockDim.x) reinterpret_cast<int*>(&s_h)[i] = 0;
     if (threadIdx.x == 0) s_bad = 0;
     __syncthreads();
     // one thread per row: all-zero flag, non-finite flag, ||c||^2 in fp64
@@ -163,6 +167,8 @@ __device__ void build_centre_table(const Problem& pr, const double* __restrict__
             b[at + (size_t)npad * 8] = lo;
         }
     }
+    __syncthreads();   // (the header is complete: tc_n and the scales were the last fields)
+    for (int i = threadIdx.x; i < (int)(sizeof(CentreHeader) / 4); i += blockDim.x) reinterpret_cast<int*>(pr.hdr)[i] = reinterpret_cast<const int*>(&s_h)[i];
 }
 
 __global__ void prepare_centres_kernel(Problem* problems, int table_cap) {

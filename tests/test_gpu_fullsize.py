@@ -75,3 +75,41 @@ def test_c4_dallocate_100m_x_40(engine, oracle):
             assert np.array_equal(oracle.allocate_points(Xs, mu, True), lab[r0:r0 + 4096])
         counts = np.bincount(lab, minlength=k)
         assert counts.sum() == n and (counts[[0, 1, 3, 4]] > 0).all()
+
+
+def test_host_pipelines_over_several_chunks(engine):
+    """The host <-> device pipelines (api.cu: staged_pipeline, copy_labels_out) at sizes that take several 32 MB / 4 MB chunks of the ring
+    of pinned buffers: what comes back is exactly what went in — fp32(X) for an upload, the same labels through the chunked copy-out as
+    through a plain read of a slice, and the device pre-scaling on the fp32 route and on the doubles route (one value that is not an fp32
+    value, in the LAST chunk: the upload starts over) agree with the host restatement."""
+    from depecher_b200 import rapi
+    rng = np.random.default_rng(17)
+    n, d = 1_300_000, 20                                          # 26M values: four chunks of 8M
+    X = rng.normal(size=(n, d)) * 3.0 + rng.integers(-2, 3, size=(n, 1)) * 4.0
+    ds = engine.dataset(X)
+    for r0 in (0, 419_999, n - 1000):                             # rows whose values sit in different chunks of the column-major matrix
+        got = engine.read(ds, r0, 1000)
+        assert np.array_equal(got, X[r0:r0 + 1000].astype(np.float32).astype(np.float64))
+    mu = rng.normal(size=(9, d)) * 3.0
+    lab = engine.allocate_points(ds, mu, True)["i"]               # 1.3M labels = 5.2 MB: two chunks of the copy-out
+    lab1 = engine.allocate_points(ds, mu, True, base=1)["i"]
+    assert np.array_equal(lab + 1, lab1)
+    with engine.gather(ds, np.arange(n - 3000, n)) as tail:       # the same cells through the small (unchunked) copy-out
+        assert np.array_equal(engine.allocate_points(tail, mu, True)["i"], lab[n - 3000:])
+    ds.close()
+    Xf = X.astype(np.float32).astype(np.float64)
+    for M in (Xf, X):                                             # fp32 route; doubles route (nearly every value fails the check: first chunk)
+        want, winfo = rapi.depecheLogCenterSd(M)
+        dss, info = engine.dataset_scaled(M)
+        got = engine.read(dss, n - 2000, 2000)
+        dss.close()
+        assert np.allclose(info[1], winfo[1], rtol=0, atol=1e-12) and abs(info[2] - winfo[2]) <= 1e-12 * winfo[2]
+        assert np.allclose(got, want[n - 2000:], rtol=3e-7, atol=1e-7)
+    Xm = Xf.copy()
+    Xm[n - 5, d - 1] += 1e-9                                      # the very last chunk holds the one value that is not an fp32 value
+    want, winfo = rapi.depecheLogCenterSd(Xm)
+    dss, info = engine.dataset_scaled(Xm)
+    got = engine.read(dss, n - 2000, 2000)
+    dss.close()
+    assert np.allclose(info[1], winfo[1], rtol=0, atol=1e-12) and abs(info[2] - winfo[2]) <= 1e-12 * winfo[2]
+    assert np.allclose(got, want[n - 2000:], rtol=3e-7, atol=1e-7)

@@ -25,6 +25,7 @@ __device__ void build_centre_table(const Problem& pr, const double* __restrict__
     constexpr int kMaxRows = kMaxKC * kMaxChunks;
     __shared__ int s_act[kMaxRows];
     __shared__ double s_cc[kMaxRows];
+    __shared__ float s_ccf[kMaxRows];
     __shared__ unsigned char s_zero[kMaxRows];
     __shared__ int s_nact, s_bad;
     // The header is assembled in shared memory and copied to the problem's header in global memory once, at the end: the phases below
@@ -33,6 +34,7 @@ __device__ void build_centre_table(const Problem& pr, const double* __restrict__
     const int k = pr.k, d = pr.d;
     CentreHeader* h = &s_h;
     for (int i = threadIdx.x; i < (int)(sizeof(CentreHeader) / 4); i += blockDim.x) reinterpret_cast<int*>(&s_h)[i] = 0;
+    const float xx_max_early = (threadIdx.x == 0 && pr.tc_table) ? *pr.xx_max : 0.f;   // (requested now, needed by thread 0 four phases later)
     if (threadIdx.x == 0) s_bad = 0;
     __syncthreads();
     // one thread per row: all-zero flag, non-finite flag, ||c||^2 in fp64
@@ -47,11 +49,13 @@ __device__ void build_centre_table(const Problem& pr, const double* __restrict__
         }
         s_zero[c] = zero;
         s_cc[c] = s;
+        s_ccf[c] = (float)s;
         if (bad) s_bad = 1;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         int n = 0, ref_active = 0, seen_zero = 0;
+        float ccmax = 0.f;
         for (int c = 0; c < k && c < kMaxRows; ++c) {
             const bool zero = s_zero[c];
             bool use;
@@ -63,7 +67,10 @@ __device__ void build_centre_table(const Problem& pr, const double* __restrict__
                 use = !(zero && seen_zero);
                 if (zero) seen_zero = 1;
             }
-            if (use) s_act[n++] = c;
+            if (use) {
+                s_act[n++] = c;
+                ccmax = fmaxf(ccmax, s_ccf[c]);   // (the largest ||c||^2 of the active rows, taken in the same sweep)
+            }
         }
         s_nact = n;
         const bool trivial = ref_active < 2 || n < 2;
@@ -74,8 +81,6 @@ __device__ void build_centre_table(const Problem& pr, const double* __restrict__
         h->trivial = trivial;
         h->force_exact = s_bad;
         int off = 0, base = 0;
-        float ccmax = 0.f;
-        for (int a = 0; a < n; ++a) ccmax = fmaxf(ccmax, (float)s_cc[s_act[a]]);
         h->cc_max = ccmax * 1.0000002f;
         for (int q = 0; q < n_chunks; ++q) {
             const int real = n / n_chunks + (q < n % n_chunks ? 1 : 0);
@@ -140,7 +145,7 @@ __device__ void build_centre_table(const Problem& pr, const double* __restrict__
                 if (vmax >= 0.015625f && vmax <= 8192.f) return 0;
                 return pow2_to_2p13(vmax);
             };
-            const int ex = scale_exp(sqrtf(*pr.xx_max) * 1.0001f);
+            const int ex = scale_exp(sqrtf(xx_max_early) * 1.0001f);
             const int ec = scale_exp(2.f * sqrtf(h->cc_max) * 1.0001f);
             h->tc_scale_x = ldexpf(1.f, ex);
             h->tc_unscale = ldexpf(1.f, -(ex + ec));

@@ -536,7 +536,7 @@ static int run_ari(const std::vector<PairJob>& jobs, uint32_t k, uint64_t seed, 
 // ------------------------------------------------------------------------------------------------
 static int find_centers_dev(dpr_dataset* ds, const double* init_mu_colmajor, uint32_t k, double reg, int no_zero, int max_iter,
                             uint64_t seed, uint32_t fit_id, int32_t* idx_out, double* centers_out, double* norm_out,
-                            int32_t* n_iter_out) {
+                            int32_t* n_iter_out, Session* ready = nullptr) {   // ready: a session already set up over `ds` (dpr_sparse_k_means on a host matrix)
     if (!ds) return fail(DPR_ERR_INVALID, "null dataset");
     if (k < 2) return fail(DPR_ERR_INVALID, "k must be >= 2 (initialize_mu writes two rows, Clusterer.cpp:157-162)");
     if (max_iter < 1) return fail(DPR_ERR_INVALID, "max_iter must be >= 1");
@@ -549,12 +549,15 @@ static int find_centers_dev(dpr_dataset* ds, const double* init_mu_colmajor, uin
         fprintf(stderr, "[dpr] find_centers: %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
         t_prev = now;
     };
-    Session s;
+    Session own;
+    Session& s = ready ? *ready : own;
     // several ranks: a fit from GIVEN centres is the row-sharded one (every rank holds a shard and the same initial centres, the tables
     // are summed over the ranks each iteration); a fit that seeds itself (sparse_k_means) draws its centres from the local cells and
     // stays local
-    s.row_sharded = init_mu_colmajor != nullptr;
-    DPR_TRY(single_session(ds, (int)k, reg, no_zero, true, s));
+    if (!ready) {
+        s.row_sharded = init_mu_colmajor != nullptr;
+        DPR_TRY(single_session(ds, (int)k, reg, no_zero, true, s));
+    }
     if (init_mu_colmajor) {
         std::vector<double> rm;
         colmajor_to_rowmajor(init_mu_colmajor, (int)k, ds->d, rm);
@@ -1106,16 +1109,22 @@ int dpr_dataset_sparse_k_means(dpr_dataset_t ds, uint32_t k, double reg, int32_t
 }
 int dpr_sparse_k_means(const double* X, int64_t n, int32_t d, uint32_t k, double reg, int32_t no_zero, uint64_t seed,
                        int32_t* idx_out, double* centers_out, double* norm_out, int32_t* n_iter_out) {
-    dpr_dataset_t ds = nullptr;
-    const auto t0 = std::chrono::steady_clock::now();
-    DPR_TRY(dpr_dataset_create(X, n, d, &ds));
-    if (getenv("DPR_TIMING")) fprintf(stderr, "[dpr] sparse_k_means: upload %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    if (!X) return fail(DPR_ERR_INVALID, "null X");
+    if (k < 2) return fail(DPR_ERR_INVALID, "k must be >= 2 (initialize_mu writes two rows, Clusterer.cpp:157-162)");
+    dpr_dataset* ds = nullptr;
+    DPR_TRY(dataset_alloc(n, d, &ds));
+    std::unique_ptr<dpr_dataset, int (*)(dpr_dataset*)> guard(ds, dpr_dataset_destroy);
     // (a matrix that lives for this one fit: the cell-major copy the delta iterations would gather from costs more to make — 1.6 GB of pool
     // memory and a pass over the cells — than it saves in twenty-odd iterations: 0.062-0.070 -> 0.059 s for 10M x 40)
     ds->rows_tried = true;
-    const int rc = dpr_dataset_sparse_k_means(ds, k, reg, no_zero, seed, idx_out, centers_out, norm_out, n_iter_out);
-    dpr_dataset_destroy(ds);
-    return rc;
+    // the session's tables are allocated, cleared and described to the device BEFORE the upload: that work (and its synchronisation) then
+    // overlaps with the first chunks the host threads narrow instead of standing between the upload and the seeding
+    Session s;
+    DPR_TRY(single_session(ds, (int)k, reg, no_zero, true, s));
+    const auto t0 = std::chrono::steady_clock::now();
+    DPR_TRY(dataset_upload(ds, X));
+    if (getenv("DPR_TIMING")) fprintf(stderr, "[dpr] sparse_k_means: upload %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    return find_centers_dev(ds, nullptr, k, reg, no_zero, 1000, seed, 0, idx_out, centers_out, norm_out, n_iter_out, &s);
 }
 int dpr_dataset_find_centers_from(dpr_dataset_t ds, const double* init_mu, uint32_t k, double reg, int32_t no_zero, int32_t max_iter,
                                   int32_t* idx_out, double* centers_out, double* norm_out, int32_t* n_iter_out) {

@@ -549,6 +549,17 @@ static int find_centers_dev(dpr_dataset* ds, const double* init_mu_colmajor, uin
         fprintf(stderr, "[dpr] find_centers: %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
         t_prev = now;
     };
+    // The caller's label vector is usually untouched memory: every page of it faults on its first write.  A helper thread writes it once
+    // while the device seeds and iterates (the host has nothing else to do), so that the copy-out at the end finds the pages mapped.
+    struct Joiner {
+        std::thread t;
+        ~Joiner() { if (t.joinable()) t.join(); }
+    } prefault;
+    if (idx_out && ds->n >= (1 << 19)) {
+        int32_t* dst = idx_out;
+        const int64_t cells = ds->n;
+        prefault.t = std::thread([dst, cells] { std::memset(dst, 0, sizeof(int32_t) * (size_t)cells); });
+    }
     Session own;
     Session& s = ready ? *ready : own;
     // several ranks: a fit from GIVEN centres is the row-sharded one (every rank holds a shard and the same initial centres, the tables
@@ -576,6 +587,7 @@ static int find_centers_dev(dpr_dataset* ds, const double* init_mu_colmajor, uin
     mark("Lloyd loop");
     const Problem& pr = s.h_problems[0];
     if (n_iter_out) *n_iter_out = pr.n_assign;
+    if (prefault.t.joinable()) prefault.t.join();
     DPR_TRY(copy_labels_out(pr.labels, ds->n, idx_out));
     mark("labels to the host");
     if (centers_out) {

@@ -286,12 +286,13 @@ class Engine:
                 idx += base
         return {"i": idx}
 
-    def allocate_points_ranked(self, ds: "Dataset", mu, no_zero):
+    def allocate_points_ranked(self, ds: "Dataset", mu, no_zero, out=None):
         """depeche()'s final step on a resident matrix: labels renumbered 1, 2, ... by decreasing cluster size, and the old 0-based labels in
-        rank order (R/depeche.R:228-252)"""
+        rank order (R/depeche.R:228-252).  out: an int32 vector of ds.n entries to write the labels into (depeche() hands over one whose
+        pages it has touched while the search ran)"""
         mu = _f64(mu)
         k = mu.shape[0]
-        idx = np.empty(ds.n, np.int32)
+        idx = out if (out is not None and out.dtype == np.int32 and out.shape == (ds.n,) and out.flags.c_contiguous) else np.empty(ds.n, np.int32)
         order = np.empty(k, np.int32)
         self._chk(self.lib.dpr_dataset_allocate_points_ranked(ds.handle, _ptr(mu, _dp), C.c_int32(k), C.c_int32(int(no_zero)), _ptr(idx, _ip), _ptr(order, _ip)))
         return idx, order[order >= 0]

@@ -424,6 +424,14 @@ def depeche(inDataFrame, samplingSubset=None, penalties=None, sampleSize="defaul
         nCores = default_ncores()                                                               # :169-174
     use_ds = hasattr(eng, "dataset")
     ranked = None
+    out_labels, toucher = None, None
+    if device_scaled and n_rows >= 10000 and hasattr(eng, "allocate_points_ranked"):
+        # the cluster vector of the result: allocated now and written once by a helper thread while the device searches (every page of a fresh
+        # vector faults on its first write: 40 MB at 10M cells), so that the final allocation copies its labels into mapped memory
+        import threading
+        out_labels = np.empty(n_rows, np.int32)
+        toucher = threading.Thread(target=out_labels.fill, args=(0,))
+        toucher.start()
     ds_used = ds_scaled if device_scaled else (eng.dataset(used) if use_ds else used)           # resident for the whole search (SURVEY f-2)
     try:
         opt = depechePenaltyOpt(ds_used, k=k, maxIter=maxIter, sampleSize=sampleSize, penalties=penalties, createOutput=createOutput,
@@ -460,13 +468,18 @@ def depeche(inDataFrame, samplingSubset=None, penalties=None, sampleSize="defaul
                 drop = np.ones(cc.shape[1], bool)
                 drop[cols_kept] = False
                 cc[:, drop] = 0.0                                                               # (as dAllocate does for a resident matrix)
-                newVec, order0 = eng.allocate_points_ranked(ds_all, cc, 1)
+                if toucher is not None:
+                    toucher.join()
+                    toucher = None
+                newVec, order0 = eng.allocate_points_ranked(ds_all, cc, 1, out=out_labels if ds_all is ds_used else None)
                 ranked = (newVec, order0 + 1, {int(l) + 1: i for i, l in enumerate(order0, start=1)})
             else:
                 clusterVector = dAllocate(ds_all, {"clusterCenters": model_cc, "logCenterSd": False}, engine=eng)   # :228-232
             if use_ds and ds_all is not ds_used:
                 ds_all.close()
     finally:
+        if toucher is not None:
+            toucher.join()
         if use_ds:
             ds_used.close()
     # clusters renumbered by size (:236-252)

@@ -805,6 +805,45 @@ double median_of(std::vector<double> v) {   // (selection, not a sort: hist() of
     const double lo = *std::max_element(v.begin(), v.begin() + m / 2);
     return 0.5 * (lo + hi);
 }
+// median(diff(b)) — the same value median_of gives for the vector of differences, without building it: the breaks are l + i * by in
+// floating point, so their differences take a handful of distinct values (by and its neighbours); they are tallied in one sweep and the
+// middle element(s) read off the sorted tally.  More than 32 distinct values: the general route.
+double median_of_diffs(const std::vector<double>& b) {
+    const size_t m = b.size() - 1;
+    struct Tally { double v; size_t c; } t[32];
+    int nt = 0, last = 0;
+    bool general = false;
+    for (size_t i = 0; i < m && !general; ++i) {
+        const double dv = b[i + 1] - b[i];
+        if (nt && t[last].v == dv) { ++t[last].c; continue; }
+        int at = -1;
+        for (int q = 0; q < nt; ++q)
+            if (t[q].v == dv) { at = q; break; }
+        if (at < 0) {
+            if (nt == 32) { general = true; break; }
+            at = nt++;
+            t[at] = Tally{dv, 0};
+        }
+        ++t[at].c;
+        last = at;
+    }
+    if (general) {
+        std::vector<double> diffs(m);
+        for (size_t i = 0; i < m; ++i) diffs[i] = b[i + 1] - b[i];
+        return median_of(std::move(diffs));
+    }
+    std::sort(t, t + nt, [](const Tally& a, const Tally& c) { return a.v < c.v; });
+    auto at_rank = [&](size_t r) {   // the r-th smallest difference (0-based)
+        size_t seen = 0;
+        for (int q = 0; q < nt; ++q) {
+            seen += t[q].c;
+            if (r < seen) return t[q].v;
+        }
+        return t[nt - 1].v;
+    };
+    const double hi = at_rank(m / 2);
+    return m % 2 ? hi : 0.5 * (at_rank(m / 2 - 1) + hi);
+}
 }  // namespace
 
 int dpr_dataset_create_scaled(const double* X, int64_t n, int32_t d, int32_t log2_off, int32_t center_mode, double* centers_inout,
@@ -936,14 +975,12 @@ int dpr_dataset_create_scaled(const double* X, int64_t n, int32_t d, int32_t log
                     bad[j] = 1;
                     return;
                 }
-                std::vector<double> diffs(nb);
-                for (int i = 0; i < nb; ++i) diffs[i] = br[j][i + 1] - br[j][i];
                 const double range = colmax[j] - colmin[j];
                 HistCol c{};
                 c.col = raw.as<double>() + (int64_t)j * n;
                 c.nb = nb;
-                c.diddle = 1e-7 * (nb + 1 > 5 ? median_of(diffs) : (nb + 1 <= 3 ? range : std::max(range, median_of(diffs))));
-                c.inv_by = 1.0 / diffs[nb / 2];
+                c.diddle = 1e-7 * (nb + 1 > 5 ? median_of_diffs(br[j]) : (nb + 1 <= 3 ? range : std::max(range, median_of_diffs(br[j]))));
+                c.inv_by = 1.0 / (br[j][nb / 2 + 1] - br[j][nb / 2]);
                 // what r_pretty_breaks built the sequence from (its interior values are l + i * by)
                 c.l = br[j][0];
                 c.u = br[j][nb];

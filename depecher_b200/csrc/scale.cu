@@ -96,10 +96,19 @@ __global__ void log2_kernel(double* raw, int64_t n, int d, const double* __restr
 // (x - c_j) / sd in fp64 -> fp32, into the tile-major resident layout
 __global__ void scale_to_tiles_kernel(const double* __restrict__ raw, int64_t n, int d, const double* __restrict__ centre, double sd,
                                       float* __restrict__ out) {
-    const int64_t total = n * d;
+    // a thread takes one cell's four markers of a group: four coalesced column reads, one 16-byte store into the tile (a warp writes 512
+    // consecutive bytes; one marker per thread wrote 4 bytes of every 16: each sector of the tile in four to eight pieces)
+    const int groups = tile_groups(d);
+    const int64_t total = n * groups;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t j = t / n, i = t - j * n;
-        out[x_index(i, (int)j, d)] = (float)((raw[t] - centre[j]) / sd);
+        const int64_t g = t / n, i = t - g * n;
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = 4 * (int)g + q;
+            v[q] = j < d ? (float)((raw[(int64_t)j * n + i] - centre[j]) / sd) : 0.f;
+        }
+        *reinterpret_cast<float4*>(out + x_index(i, 4 * (int)g, d)) = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -191,7 +200,7 @@ int launch_hist_cols(const HistCol* d_cols, int d, int64_t n, unsigned int* coun
     return DPR_OK;
 }
 int launch_scale_to_tiles(const double* raw, int64_t n, int d, const double* centre, double sd, float* out, cudaStream_t st) {
-    scale_to_tiles_kernel<<<grid_for(n * d), 256, 0, st>>>(raw, n, d, centre, sd, out);
+    scale_to_tiles_kernel<<<grid_for(n * tile_groups(d)), 256, 0, st>>>(raw, n, d, centre, sd, out);
     count_launch();
     DPR_CUDA(cudaGetLastError());
     return DPR_OK;

@@ -1393,7 +1393,11 @@ static int grid_search_range(dpr_dataset_t ds, const int32_t* k, int32_t nk, con
             DPR_TRY(tables.alloc(sizeof(unsigned long long) * (size_t)cells * kk * kk, true));
             DPR_TRY(out.alloc(sizeof(double) * cells));
             score.pair_tables = tables.as<unsigned long long>();
-            for (int q = 0; q < 2 * cells; ++q) DPR_TRY(score.set_centres_device(q, fits.h_problems[q].mu));
+            if (score.k_max() == fits.k_max())   // both sessions keep their centre matrices back to back with the same stride: one copy
+                DPR_CUDA(cudaMemcpyAsync(score.h_problems[0].mu, fits.h_problems[0].mu, sizeof(double) * (size_t)fits.k_max() * d * (size_t)(2 * cells),
+                                         cudaMemcpyDeviceToDevice, ctx().stream));
+            else
+                for (int q = 0; q < 2 * cells; ++q) DPR_TRY(score.set_centres_device(q, fits.h_problems[q].mu));
             DPR_TRY(score.prepare());
             DPR_TRY(score.pass(kPassAssign, false));
             DPR_TRY(launch_ari_from_tables(cells, ds->n, kk, tables.as<unsigned long long>(), out.as<double>(), ctx().stream));
@@ -1424,7 +1428,15 @@ static int grid_search_range(dpr_dataset_t ds, const int32_t* k, int32_t nk, con
     if (timing)
         fprintf(stderr, "[dpr] grid_search %d problems: bootstrap %.2f ms, seeding %.2f, fits %.2f, scoring + ARI %.2f\n", cells, ms_since(t_start, t_boot),
                 ms_since(t_boot, t_seed), ms_since(t_seed, t_fit), ms_since(t_fit, t_score));
-    // 5. per-problem results: its ARI and the mean number of used clusters of its two fits
+    // 5. per-problem results: its ARI and the mean number of used clusters of its two fits.  The centres of all fits come back in ONE copy
+    //    (the session keeps them back to back, k_max x d doubles per fit): a copy and a synchronisation per fit cost 4 ms per 220-fit set
+    std::vector<double> all_mu;
+    const size_t mu_stride = (size_t)fits.k_max() * d;
+    if (centers_out) {
+        all_mu.resize(mu_stride * (size_t)F);
+        DPR_CUDA(cudaMemcpyAsync(all_mu.data(), fits.h_problems[0].mu, sizeof(double) * all_mu.size(), cudaMemcpyDeviceToHost, ctx().stream));
+        DPR_CUDA(cudaStreamSynchronize(ctx().stream));
+    }
     size_t coff = 0;
     for (int c = 0; c < cells; ++c) {
         const int j = ((c_lo + c) / nreg) % nk;
@@ -1433,8 +1445,8 @@ static int grid_search_range(dpr_dataset_t ds, const int32_t* k, int32_t nk, con
         for (int w = 0; w < 2; ++w) {
             for (int q = 0; q < k[j]; ++q) used += counts[(size_t)(2 * c + w) * fits.k_max() + q] > 0;
             if (centers_out) {
-                std::vector<double> rm((size_t)k[j] * d);
-                DPR_TRY(fits.get_centres(2 * c + w, rm.data()));
+                const double* src = all_mu.data() + mu_stride * (size_t)(2 * c + w);
+                std::vector<double> rm(src, src + (size_t)k[j] * d);
                 rowmajor_to_colmajor(rm, k[j], d, centers_out + coff);
                 coff += (size_t)k[j] * d;
             }
